@@ -1,0 +1,1520 @@
+"""DeviceArray — the device-resident value type autograd traces.
+
+It is what NumPy hands control to at the reference's raw-call boundary
+(autograd/tracer.py:94: ``f_raw(*args)`` on unboxed values) through
+``__array_ufunc__`` (NEP 13) and ``__array_function__`` (NEP 18), and what the
+VJP closures of autograd/numpy/numpy_vjps.py operate on through plain Python
+operators (``-g * x / y**2`` ...).  Shape/dtype/stride metadata lives on the
+host; payloads live in HBM and are only produced by libb200ag.so kernels.
+"""
+
+from __future__ import annotations
+
+import numbers
+import operator
+
+import numpy as np
+
+from . import backend, lazy
+from .lazy import BOOL, F32, F64, I32, I64, Const, Mat, Node, prod
+
+_Box = None  # autograd.tracer.Box, bound by install() (kept lazy so importing this module never needs autograd)
+
+
+def _is_box(x) -> bool:
+    return _Box is not None and isinstance(x, _Box)
+
+
+class DeviceArray:
+    __slots__ = ("_node", "__weakref__")
+    __array_priority__ = 1000.0
+
+    def __init__(self, node: Node):
+        self._node = node
+        node.nhandles += 1
+
+    def __del__(self):
+        try:
+            self._node.nhandles -= 1
+        except AttributeError:
+            pass
+
+    # ------------------------------------------------------------ metadata (pure host, never syncs)
+    @property
+    def shape(self):
+        return self._node.shape
+
+    @property
+    def dtype(self):
+        return self._node.dtype
+
+    @property
+    def ndim(self):
+        return len(self._node.shape)
+
+    @property
+    def size(self):
+        return prod(self._node.shape)
+
+    @property
+    def itemsize(self):
+        return self._node.dtype.itemsize
+
+    @property
+    def nbytes(self):
+        return self.size * self._node.dtype.itemsize
+
+    @property
+    def T(self):
+        return transpose(self)
+
+    @property
+    def is_lazy(self) -> bool:
+        return self._node.mat is None
+
+    def __len__(self):
+        if not self._node.shape:
+            raise TypeError("len() of unsized object")
+        return self._node.shape[0]
+
+    # ------------------------------------------------------------ materialisation / host transfer
+    def _mat(self) -> Mat:
+        node = self._node
+        return node.mat if node.mat is not None else lazy.materialize(node)
+
+    def _cmat(self) -> Mat:
+        """C-contiguous materialised payload (copies a strided / rolled view)."""
+        m = self._mat()
+        if m.is_contiguous:
+            return m
+        if m.shifts is not None:
+            # a rolled view is made contiguous by the generated identity kernel
+            return lazy.materialize(lazy.Node("positive", (lazy.leaf(m),), (m.dtype,), m.shape, m.dtype))
+        out = Mat.empty(m.shape, m.dtype)
+        backend.get().copy_strided(out.ptr, out.dtype, out.strides, m.ptr, m.dtype, m.strides, m.shape)
+        return out
+
+    def materialize(self):
+        """Force evaluation of pending lazy work behind this array (no host sync)."""
+        self._mat()
+        return self
+
+    def get(self) -> np.ndarray:
+        """Copy to host as a numpy.ndarray (synchronises)."""
+        m = self._cmat()
+        out = np.empty(m.shape, dtype=m.dtype)
+        backend.get().d2h(out, m.ptr)
+        return out
+
+    to_host = get
+
+    def item(self):
+        if self.size != 1:
+            raise ValueError("can only convert an array of size 1 to a Python scalar")
+        return self.get().reshape(()).item()
+
+    def tolist(self):
+        return self.get().tolist()
+
+    def __array__(self, dtype=None, copy=None):
+        raise TypeError(
+            "autograd_b200.DeviceArray refuses implicit conversion to a host numpy array "
+            "(it would hide a device→host copy); call .get() explicitly."
+        )
+
+    def __float__(self):
+        return float(self.item())
+
+    def __int__(self):
+        return int(self.item())
+
+    def __bool__(self):
+        if self.size != 1:
+            raise ValueError("The truth value of an array with more than one element is ambiguous. Use a.any() or a.all()")
+        return bool(self.item())
+
+    def __index__(self):
+        if self.dtype.kind not in "iu" or self.size != 1:
+            raise TypeError("only integer scalar arrays can be converted to a scalar index")
+        return int(self.item())
+
+    def __repr__(self):
+        return "DeviceArray(" + repr(self.get())[len("array("):]
+
+    def __str__(self):
+        return str(self.get())
+
+    def __hash__(self):
+        return id(self)
+
+    def __iter__(self):
+        if not self.shape:
+            raise TypeError("iteration over a 0-d array")
+        for i in range(self.shape[0]):
+            yield self[i]
+
+    def __array_namespace__(self, *, api_version=None):
+        import autograd.numpy as anp
+
+        return anp
+
+    @property
+    def __cuda_array_interface__(self):
+        m = self._cmat()
+        if m is not self._node.mat:  # keep the contiguous copy alive for as long as this handle lives
+            new = lazy.leaf(m)
+            new.nhandles += 1
+            self._node.nhandles -= 1
+            self._node = new
+        return {
+            "shape": m.shape,
+            "typestr": m.dtype.str,
+            "data": (m.ptr, False),
+            "version": 3,
+            "strides": None,
+            "stream": backend.get().stream_handle() or None,
+        }
+
+    # ------------------------------------------------------------ NumPy protocols
+    def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
+        for x in inputs:
+            if _is_box(x):
+                return NotImplemented
+        if method == "__call__":
+            op = UFUNC_OPS.get(ufunc)
+            if op is None:
+                raise TypeError(f"autograd_b200: numpy.{ufunc.__name__} has no device implementation")
+            out = kwargs.pop("out", None)
+            kwargs.pop("casting", None)
+            dtype = kwargs.pop("dtype", None)
+            if kwargs:
+                raise TypeError(f"autograd_b200: numpy.{ufunc.__name__} keyword(s) {sorted(kwargs)} are not supported on device arrays")
+            res = elementwise(op, ufunc, *inputs)
+            if dtype is not None and np.dtype(dtype) != res.dtype:
+                res = res.astype(dtype)
+            if out is not None:
+                (target,) = out if isinstance(out, tuple) else (out,)
+                if not isinstance(target, DeviceArray):
+                    raise TypeError("autograd_b200: out= must be a DeviceArray")
+                target._assign(res)
+                return target
+            return res
+        if method == "reduce":
+            name = UFUNC_REDUCE.get(ufunc)
+            if name is None:
+                raise TypeError(f"autograd_b200: numpy.{ufunc.__name__}.reduce has no device implementation")
+            kwargs.pop("out", None)
+            kwargs.pop("initial", None)
+            kwargs.pop("where", None)
+            axis = kwargs.pop("axis", 0)
+            keepdims = kwargs.pop("keepdims", False)
+            dtype = kwargs.pop("dtype", None)
+            return reduce_(inputs[0], name, axis, keepdims, dtype)
+        if method == "at":
+            if ufunc is not np.add:
+                raise TypeError(f"autograd_b200: numpy.{ufunc.__name__}.at has no device implementation")
+            target, idx, values = inputs
+            if not isinstance(target, DeviceArray):
+                raise TypeError("autograd_b200: np.add.at target must be a DeviceArray")
+            target._add_at(idx, values)
+            return None
+        return NotImplemented
+
+    def __array_function__(self, func, types, args, kwargs):
+        impl = FUNCTIONS.get(func)
+        if impl is None:
+            if func in DECOMPOSE:
+                return func._implementation(*args, **kwargs)
+            raise TypeError(f"autograd_b200: numpy.{func.__name__} has no device implementation")
+        return impl(*args, **kwargs)
+
+    # ------------------------------------------------------------ operators used by VJP closures
+    def _binop(self, opname, ufunc, other, reflected=False):
+        if _is_box(other):
+            return NotImplemented
+        return elementwise(opname, ufunc, other, self) if reflected else elementwise(opname, ufunc, self, other)
+
+    def __add__(self, o): return self._binop("add", np.add, o)
+    def __radd__(self, o): return self._binop("add", np.add, o, True)
+    def __sub__(self, o): return self._binop("subtract", np.subtract, o)
+    def __rsub__(self, o): return self._binop("subtract", np.subtract, o, True)
+    def __mul__(self, o): return self._binop("multiply", np.multiply, o)
+    def __rmul__(self, o): return self._binop("multiply", np.multiply, o, True)
+    def __truediv__(self, o): return self._binop("divide", np.true_divide, o)
+    def __rtruediv__(self, o): return self._binop("divide", np.true_divide, o, True)
+    def __floordiv__(self, o): return self._binop("floor_divide", np.floor_divide, o)
+    def __rfloordiv__(self, o): return self._binop("floor_divide", np.floor_divide, o, True)
+    def __mod__(self, o): return self._binop("remainder", np.remainder, o)
+    def __rmod__(self, o): return self._binop("remainder", np.remainder, o, True)
+    def __pow__(self, o): return self._binop("power", np.power, o)
+    def __rpow__(self, o): return self._binop("power", np.power, o, True)
+    def __matmul__(self, o): return NotImplemented if _is_box(o) else matmul(self, o)
+    def __rmatmul__(self, o): return NotImplemented if _is_box(o) else matmul(o, self)
+    def __neg__(self): return elementwise("negative", np.negative, self)
+    def __pos__(self): return self
+    def __abs__(self): return elementwise("abs", np.absolute, self)
+    def __invert__(self): return elementwise("logical_not", np.logical_not, self)
+    def __eq__(self, o): return self._binop("equal", np.equal, o)
+    def __ne__(self, o): return self._binop("not_equal", np.not_equal, o)
+    def __lt__(self, o): return self._binop("less", np.less, o)
+    def __le__(self, o): return self._binop("less_equal", np.less_equal, o)
+    def __gt__(self, o): return self._binop("greater", np.greater, o)
+    def __ge__(self, o): return self._binop("greater_equal", np.greater_equal, o)
+    def __and__(self, o): return self._binop("logical_and", np.logical_and, o)
+    def __or__(self, o): return self._binop("logical_or", np.logical_or, o)
+
+    # In-place operators rebind this handle to the new expression (VSpace._mut_add: ``x += y``,
+    # autograd/core.py:262-264, only ever touches accumulators autograd itself created).
+    def _assign(self, value):
+        value = asarray(value)
+        if value.shape != self.shape:
+            value = broadcast_to(value, self.shape)
+        if value.dtype != self.dtype:
+            value = value.astype(self.dtype)
+        old, new = self._node, value._node
+        new.nhandles += 1
+        old.nhandles -= 1
+        self._node = new
+
+    def __iadd__(self, o):
+        r = self.__add__(o)
+        if r is NotImplemented:
+            return r
+        self._assign(r)
+        return self
+
+    def __isub__(self, o):
+        r = self.__sub__(o)
+        if r is NotImplemented:
+            return r
+        self._assign(r)
+        return self
+
+    def __imul__(self, o):
+        r = self.__mul__(o)
+        if r is NotImplemented:
+            return r
+        self._assign(r)
+        return self
+
+    def __itruediv__(self, o):
+        r = self.__truediv__(o)
+        if r is NotImplemented:
+            return r
+        self._assign(r)
+        return self
+
+    # ------------------------------------------------------------ ndarray-style methods
+    def astype(self, dtype, order="K", casting="unsafe", subok=True, copy=True):
+        dtype = np.dtype(dtype)
+        if dtype == self.dtype:
+            return self
+        if dtype not in lazy.SUPPORTED:
+            backend.dtype_code(dtype)
+        return DeviceArray(lazy.make_cast(self._node, dtype))
+
+    def view(self, *args, **kwargs):
+        return self  # `.view(ndarray)` in autograd/numpy/numpy_wrapper.py:59 strips subclasses; nothing to strip here
+
+    def copy(self, order="C"):
+        m = self._mat()
+        out = Mat.empty(m.shape, m.dtype)
+        if m.shifts is not None:
+            return DeviceArray(lazy.leaf(self._cmat()))
+        backend.get().copy_strided(out.ptr, out.dtype, out.strides, m.ptr, m.dtype, m.strides, m.shape)
+        return DeviceArray(lazy.leaf(out))
+
+    def reshape(self, *shape, order="C"):
+        if len(shape) == 1 and not isinstance(shape[0], numbers.Integral):
+            shape = shape[0]
+        return reshape(self, shape)
+
+    def ravel(self, order="C"): return reshape(self, (-1,))
+    def flatten(self, order="C"): return reshape(self, (-1,)).copy()
+    def transpose(self, *axes):
+        if len(axes) == 1 and (axes[0] is None or not isinstance(axes[0], numbers.Integral)):
+            axes = axes[0]
+        return transpose(self, axes if axes else None)
+    def swapaxes(self, a, b): return swapaxes(self, a, b)
+    def squeeze(self, axis=None): return squeeze(self, axis)
+    def sum(self, axis=None, dtype=None, out=None, keepdims=False): return reduce_(self, "sum", axis, keepdims, dtype)
+    def prod(self, axis=None, dtype=None, out=None, keepdims=False): return reduce_(self, "prod", axis, keepdims, dtype)
+    def max(self, axis=None, out=None, keepdims=False): return reduce_(self, "max", axis, keepdims)
+    def min(self, axis=None, out=None, keepdims=False): return reduce_(self, "min", axis, keepdims)
+    def mean(self, axis=None, dtype=None, out=None, keepdims=False): return mean(self, axis, dtype, None, keepdims)
+    def var(self, axis=None, dtype=None, out=None, ddof=0, keepdims=False): return var(self, axis, dtype, None, ddof, keepdims)
+    def std(self, axis=None, dtype=None, out=None, ddof=0, keepdims=False): return std(self, axis, dtype, None, ddof, keepdims)
+    def all(self, axis=None, out=None, keepdims=False): return reduce_(self, "all", axis, keepdims)
+    def any(self, axis=None, out=None, keepdims=False): return reduce_(self, "any", axis, keepdims)
+    def argmax(self, axis=None, out=None, keepdims=False): return argreduce(self, "max", axis, keepdims)
+    def argmin(self, axis=None, out=None, keepdims=False): return argreduce(self, "min", axis, keepdims)
+    def dot(self, other): return dot(self, other)
+    def clip(self, a_min=None, a_max=None, out=None): return clip(self, a_min, a_max)
+    def repeat(self, repeats, axis=None): return repeat(self, repeats, axis)
+    def take(self, indices, axis=None): return take(self, indices, axis)
+    def round(self, decimals=0): return round_(self, decimals)
+    def conj(self): return self
+    conjugate = conj
+
+    @property
+    def real(self): return self
+
+    @property
+    def imag(self): return zeros(self.shape, self.dtype)
+
+    # ------------------------------------------------------------ indexing
+    def __getitem__(self, idx):
+        return getitem(self, idx)
+
+    def __setitem__(self, idx, value):
+        kind, info = _parse_index(self.shape, idx)
+        if kind != "basic":
+            raise NotImplementedError("autograd_b200: item assignment supports basic (slice/int) indices only")
+        self._own_buffer()
+        view = _basic_view(self._mat(), info)
+        value = asarray(value, dtype=self.dtype) if not isinstance(value, DeviceArray) else value
+        if value.dtype != self.dtype:
+            value = value.astype(self.dtype)
+        src = broadcast_to(value, view.shape)._mat()
+        if src.shifts is not None:
+            src = DeviceArray(lazy.leaf(src))._cmat()
+        backend.get().copy_strided(view.ptr, view.dtype, view.strides, src.ptr, src.dtype, src.strides, view.shape)
+
+    def _own_buffer(self):
+        """Make sure this handle is backed by real memory that may be written in place."""
+        node = self._node
+        if node.mat is None:
+            lazy.materialize(node)
+        m = node.mat
+        if m.shifts is not None or any(st == 0 and s > 1 for s, st in zip(m.shape, m.strides)):
+            c = self._cmat() if m.shifts is not None else None
+            if c is None:
+                c = Mat.empty(m.shape, m.dtype)
+                backend.get().copy_strided(c.ptr, c.dtype, c.strides, m.ptr, m.dtype, m.strides, m.shape)
+            new = lazy.leaf(c)
+            new.nhandles += 1
+            node.nhandles -= 1
+            self._node = new
+
+    def _add_at(self, idx, values):
+        """np.add.at(self, idx, values): unbuffered in-place accumulation (numpy_vjps.py:946-948)."""
+        self._own_buffer()
+        m = self._mat()
+        kind, info = _parse_index(self.shape, idx)
+        be = backend.get()
+        if kind == "basic":
+            view = _basic_view(m, info)
+            v = asarray(values)
+            if v.dtype != self.dtype:
+                v = v.astype(self.dtype)
+            src = broadcast_to(v, view.shape)
+            sm = src._mat()
+            if sm.shifts is not None:
+                sm = src._cmat()
+            be.add_strided(view.ptr, view.dtype, view.strides, sm.ptr, sm.strides, view.shape)
+            return
+        idx_arrays, idx_shape, n_lead = info
+        if not m.is_contiguous:
+            raise NotImplementedError("autograd_b200: np.add.at with array indices needs a contiguous target")
+        inner_shape = self.shape[n_lead:]
+        v = asarray(values)
+        if v.dtype != self.dtype:
+            v = v.astype(self.dtype)
+        v = broadcast_to(v, tuple(idx_shape) + tuple(inner_shape))
+        vm = v._cmat()
+        ptrs = [a._cmat() for a in idx_arrays]
+        be.scatter_add(m.ptr, vm.ptr, self.dtype, [p.ptr for p in ptrs], list(self.shape[:n_lead]), prod(idx_shape),
+                       prod(inner_shape))
+
+
+# =================================================================== construction
+def _upload(host: np.ndarray) -> DeviceArray:
+    host = np.asarray(host)
+    if host.dtype not in lazy.SUPPORTED:
+        if host.dtype.kind == "f":
+            host = host.astype(np.float64)
+        elif host.dtype.kind in "iu":
+            host = host.astype(np.int64)
+        else:
+            backend.dtype_code(host.dtype)
+    host = np.ascontiguousarray(host)
+    m = Mat.empty(host.shape, host.dtype)
+    if host.size:
+        backend.get().h2d(m.ptr, host)
+    return DeviceArray(lazy.leaf(m))
+
+
+def asarray(x, dtype=None) -> DeviceArray:
+    """Device version of ``np.asarray``: uploads host data, passes DeviceArrays through."""
+    if isinstance(x, DeviceArray):
+        return x if dtype is None else x.astype(dtype)
+    if isinstance(x, (list, tuple)) and any(isinstance(e, DeviceArray) for e in x):
+        return stack([asarray(e) for e in x]) if dtype is None else stack([asarray(e) for e in x]).astype(dtype)
+    host = np.asarray(x) if dtype is None else np.asarray(x, dtype=dtype)
+    return _upload(host)
+
+
+array = asarray
+to_device = asarray
+
+
+def _shape_tuple(shape):
+    if isinstance(shape, (numbers.Integral, np.integer)):
+        return (int(shape),)
+    return tuple(int(s) for s in shape)
+
+
+def full(shape, fill_value, dtype=None, **_ignored):
+    if isinstance(fill_value, DeviceArray):
+        return broadcast_to(fill_value if dtype is None else fill_value.astype(dtype), _shape_tuple(shape)).copy()
+    if dtype is None:
+        dtype = np.asarray(fill_value).dtype
+    dtype = np.dtype(dtype)
+    backend.dtype_code(dtype)
+    value = np.asarray(fill_value).astype(dtype).item()
+    return DeviceArray(lazy.make_full(value, _shape_tuple(shape), dtype))
+
+
+def zeros(shape, dtype=float, **_ignored):
+    return full(shape, 0, np.dtype(dtype))
+
+
+def ones(shape, dtype=float, **_ignored):
+    return full(shape, 1, np.dtype(dtype))
+
+
+def empty(shape, dtype=float, **_ignored):
+    return full(shape, 0, np.dtype(dtype))
+
+
+def zeros_like(a, dtype=None, **_ignored):
+    return zeros(np.shape(a), dtype or _dtype_of(a))
+
+
+def ones_like(a, dtype=None, **_ignored):
+    return ones(np.shape(a), dtype or _dtype_of(a))
+
+
+def empty_like(a, dtype=None, **_ignored):
+    return zeros(np.shape(a), dtype or _dtype_of(a))
+
+
+def full_like(a, fill_value, dtype=None, **_ignored):
+    return full(np.shape(a), fill_value, dtype or _dtype_of(a))
+
+
+def _dtype_of(a):
+    return a.dtype if hasattr(a, "dtype") else np.asarray(a).dtype
+
+
+def arange(*args, **kwargs):
+    return _upload(np.arange(*args, **kwargs))
+
+
+def linspace(*args, **kwargs):
+    return _upload(np.linspace(*args, **kwargs))
+
+
+def eye(*args, **kwargs):
+    return _upload(np.eye(*args, **kwargs))
+
+
+def meshgrid(*xi, copy=True, sparse=False, indexing="xy"):
+    """np.meshgrid on device: the outputs are zero-stride broadcast views (no payload is replicated)."""
+    arrs = [asarray(x).ravel() for x in xi]
+    nd = len(arrs)
+    out = []
+    for i, a in enumerate(arrs):
+        shp = [1] * nd
+        shp[i] = a.shape[0]
+        out.append(reshape(a, tuple(shp)))
+    if indexing == "xy" and nd > 1:
+        out[0] = reshape(out[0], (1, -1) + (1,) * (nd - 2))
+        out[1] = reshape(out[1], (-1, 1) + (1,) * (nd - 2))
+    if not sparse:
+        full_shape = lazy.broadcast_shapes([o.shape for o in out])
+        out = [broadcast_to(o, full_shape) for o in out]
+    return out
+
+
+# =================================================================== elementwise
+def _operand(x):
+    """DeviceArray / scalar / host array → lazy.Node or lazy.Const."""
+    if isinstance(x, DeviceArray):
+        return x._node
+    if isinstance(x, np.generic):
+        if x.dtype not in lazy.SUPPORTED:
+            return Const(x.item(), None)
+        return Const(x.item(), x.dtype)
+    if isinstance(x, (bool, int, float)):
+        return Const(x, None)
+    if isinstance(x, np.ndarray):
+        if x.ndim == 0:
+            return _operand(x[()])
+        if x.size > 1 and all(s == 0 for s in x.strides):
+            # host broadcast of a scalar (e.g. the `+ onp.zeros(shape)` idiom): stay symbolic
+            v = x.flat[0]
+            return lazy.make_full(v.item(), x.shape, x.dtype if x.dtype in lazy.SUPPORTED else F64)
+        return _upload(x)._node
+    if isinstance(x, (list, tuple)):
+        return asarray(x)._node
+    if isinstance(x, complex):
+        raise TypeError("autograd_b200: complex operands are not supported on the device")
+    raise TypeError(f"autograd_b200: cannot use operand of type {type(x).__name__} in a device computation")
+
+
+def elementwise(opname, ufunc, *inputs) -> DeviceArray:
+    args = [_operand(x) for x in inputs]
+    return DeviceArray(lazy.make_op(opname, ufunc, args))
+
+
+def where(cond, x=None, y=None):
+    if x is None and y is None:
+        raise NotImplementedError("autograd_b200: np.where(cond) (nonzero) is not implemented on device")
+    c, a, b = _operand(cond), _operand(x), _operand(y)
+    if type(c) is Const:
+        return asarray(x if c.value else y)
+    dts = []
+    for o, raw in ((a, x), (b, y)):
+        if type(o) is Node:
+            dts.append(o.dtype)
+        elif o.dtype is not None:
+            dts.append(o.dtype)
+        else:
+            dts.append(type(raw) if not isinstance(raw, np.ndarray) else raw.dtype)
+    out_dtype = np.result_type(*dts)
+    backend.dtype_code(out_dtype)
+    return DeviceArray(lazy.make_where(c, a, b, np.dtype(out_dtype)))
+
+
+def clip(a, a_min=None, a_max=None, out=None, **kw):
+    r = asarray(a)
+    if a_min is not None:
+        r = elementwise("maximum", np.maximum, r, a_min)
+    if a_max is not None:
+        r = elementwise("minimum", np.minimum, r, a_max)
+    return r
+
+
+def round_(a, decimals=0, out=None):
+    a = asarray(a)
+    if a.dtype.kind != "f":
+        return a
+    if decimals == 0:
+        return elementwise("rint", np.rint, a)
+    s = 10.0 ** decimals
+    return elementwise("rint", np.rint, a * s) / s
+
+
+def nan_to_num(x, copy=True, nan=0.0, posinf=None, neginf=None):
+    x = asarray(x)
+    fi = np.finfo(x.dtype)
+    r = where(elementwise("isnan", np.isnan, x), nan, x)
+    r = where(r == np.inf, fi.max if posinf is None else posinf, r)
+    return where(r == -np.inf, fi.min if neginf is None else neginf, r)
+
+
+def real(x): return asarray(x)
+def imag(x): return zeros_like(x)
+def iscomplexobj(x): return False
+def isrealobj(x): return True
+
+
+def isclose(a, b, rtol=1e-05, atol=1e-08, equal_nan=False):
+    a, b = asarray(a), asarray(b)
+    close = abs(a - b) <= (atol + rtol * abs(b))
+    both_inf = (a == b)
+    r = (close & elementwise("isfinite", np.isfinite, b)) | both_inf
+    if equal_nan:
+        r = r | (elementwise("isnan", np.isnan, a) & elementwise("isnan", np.isnan, b))
+    return r
+
+
+def allclose(a, b, rtol=1e-05, atol=1e-08, equal_nan=False):
+    return bool(reduce_(isclose(a, b, rtol, atol, equal_nan), "all", None, False))
+
+
+def array_equal(a1, a2, equal_nan=False):
+    a1, a2 = asarray(a1), asarray(a2)
+    if a1.shape != a2.shape:
+        return False
+    return bool(reduce_(a1 == a2, "all", None, False))
+
+
+# =================================================================== layout (views where possible)
+def _normalize_axis(axis, ndim):
+    if not -ndim <= axis < ndim:
+        raise np.exceptions.AxisError(axis, ndim)
+    return axis + ndim if axis < 0 else axis
+
+
+def _view(x: DeviceArray, shape, strides, offset_delta=0, shifts=None) -> DeviceArray:
+    m = x._mat()
+    return DeviceArray(lazy.leaf(Mat(m.buf, shape, strides, m.offset + offset_delta, m.dtype, shifts)))
+
+
+def reshape(a, shape=None, order="C", *, newshape=None, copy=None):
+    a = asarray(a)
+    if shape is None:
+        shape = newshape
+    if order not in ("C", None, "A", "K"):
+        raise NotImplementedError("autograd_b200: only C-order reshape is supported")
+    shape = list(_shape_tuple(shape))
+    size = a.size
+    if -1 in shape:
+        i = shape.index(-1)
+        rest = prod(s for j, s in enumerate(shape) if j != i)
+        shape[i] = size // rest if rest else 0
+    shape = tuple(shape)
+    if prod(shape) != size:
+        raise ValueError(f"cannot reshape array of size {size} into shape {shape}")
+    if shape == a.shape:
+        return a
+    node = a._node
+    if node.mat is None and _reshape_transparent(node):
+        return DeviceArray(_reshape_lazy(node, shape, {}))
+    m = a._mat()
+    new_strides = _reshape_strides(m, shape)
+    if new_strides is None:
+        m = a._cmat()
+        new_strides = lazy.c_strides(shape)
+    return DeviceArray(lazy.leaf(Mat(m.buf, shape, new_strides, m.offset, m.dtype)))
+
+
+def _reshape_transparent(node) -> bool:
+    """A pending expression can be reshaped symbolically when every operand is either a scalar or a
+    contiguous array of exactly the expression's shape (then flat indices line up)."""
+    shape = node.shape
+    stack, seen = [node], set()
+    while stack:
+        nd_ = stack.pop()
+        if nd_.nid in seen:
+            continue
+        seen.add(nd_.nid)
+        if len(seen) > 64:
+            return False
+        if nd_.mat is not None:
+            if nd_.shape == shape and nd_.mat.is_contiguous:
+                continue
+            if prod(nd_.shape) == 1:
+                continue
+            return False
+        if nd_.shape != shape and prod(nd_.shape) != 1:
+            return False
+        for a in nd_.args:
+            if type(a) is Node:
+                stack.append(a)
+    return True
+
+
+def _reshape_lazy(node, shape, memo):
+    hit = memo.get(node.nid)
+    if hit is not None:
+        return hit
+    if prod(node.shape) == 1:
+        new_shape = ()
+    else:
+        new_shape = shape
+    if node.mat is not None:
+        m = node.mat
+        if new_shape == ():
+            res = lazy.leaf(Mat(m.buf, (), (), m.offset, m.dtype))
+        else:
+            res = lazy.leaf(Mat(m.buf, shape, lazy.c_strides(shape), m.offset, m.dtype))
+    else:
+        args = tuple(_reshape_lazy(a, shape, memo) if type(a) is Node else a for a in node.args)
+        res = Node(node.op, args, node.in_dtypes, new_shape if node.op != "full" else new_shape, node.dtype)
+    memo[node.nid] = res
+    return res
+
+
+def _reshape_strides(m: Mat, new_shape):
+    """Strides of a no-copy reshape of view ``m`` or None when a copy is unavoidable."""
+    if m.shifts is not None:
+        return None
+    if m.is_contiguous:
+        return lazy.c_strides(new_shape)
+    old = [(s, st) for s, st in zip(m.shape, m.strides) if s != 1]
+    new_strides = [0] * len(new_shape)
+    oi, ni = 0, 0
+    nn = len(new_shape)
+    while ni < nn and new_shape[ni] == 1:
+        ni += 1
+    while oi < len(old) and ni < nn:
+        # gather a group of old dims and new dims with equal element counts
+        op_, np_ = old[oi][0], new_shape[ni]
+        oj, nj = oi + 1, ni + 1
+        while op_ != np_:
+            if op_ < np_:
+                if oj >= len(old):
+                    return None
+                op_ *= old[oj][0]
+                oj += 1
+            else:
+                if nj >= nn:
+                    return None
+                np_ *= new_shape[nj]
+                nj += 1
+        for k in range(oi, oj - 1):  # the old group must itself be contiguous
+            if old[k][1] != old[k + 1][1] * old[k + 1][0]:
+                return None
+        st = old[oj - 1][1]
+        for k in range(nj - 1, ni - 1, -1):
+            new_strides[k] = st
+            st *= new_shape[k]
+        oi, ni = oj, nj
+        while ni < nn and new_shape[ni] == 1:
+            ni += 1
+    if oi != len(old) or ni != nn:
+        return None
+    return tuple(new_strides)
+
+
+def ravel(a, order="C"):
+    return reshape(a, (-1,))
+
+
+def transpose(a, axes=None):
+    a = asarray(a)
+    nd = a.ndim
+    if axes is None:
+        axes = tuple(range(nd - 1, -1, -1))
+    else:
+        axes = tuple(_normalize_axis(int(ax), nd) for ax in axes)
+        if sorted(axes) != list(range(nd)):
+            raise ValueError("axes don't match array")
+    if axes == tuple(range(nd)):
+        return a
+    m = a._mat()
+    shifts = None if m.shifts is None else tuple(m.shifts[ax] for ax in axes)
+    return _view(a, tuple(m.shape[ax] for ax in axes), tuple(m.strides[ax] for ax in axes), 0, shifts)
+
+
+def swapaxes(a, axis1, axis2):
+    a = asarray(a)
+    nd = a.ndim
+    axis1, axis2 = _normalize_axis(axis1, nd), _normalize_axis(axis2, nd)
+    axes = list(range(nd))
+    axes[axis1], axes[axis2] = axes[axis2], axes[axis1]
+    return transpose(a, axes)
+
+
+def moveaxis(a, source, destination):
+    a = asarray(a)
+    nd = a.ndim
+    src = [_normalize_axis(s, nd) for s in ([source] if isinstance(source, numbers.Integral) else source)]
+    dst = [_normalize_axis(d, nd) for d in ([destination] if isinstance(destination, numbers.Integral) else destination)]
+    order = [n for n in range(nd) if n not in src]
+    for d, s in sorted(zip(dst, src)):
+        order.insert(d, s)
+    return transpose(a, order)
+
+
+def expand_dims(a, axis):
+    a = asarray(a)
+    axes = (axis,) if isinstance(axis, numbers.Integral) else tuple(axis)
+    nd = a.ndim + len(axes)
+    axes = sorted(_normalize_axis(ax, nd) for ax in axes)
+    shape = list(a.shape)
+    for ax in axes:
+        shape.insert(ax, 1)
+    return reshape(a, tuple(shape))
+
+
+def squeeze(a, axis=None):
+    a = asarray(a)
+    if axis is None:
+        shape = tuple(s for s in a.shape if s != 1)
+    else:
+        axes = (axis,) if isinstance(axis, numbers.Integral) else tuple(axis)
+        axes = [_normalize_axis(ax, a.ndim) for ax in axes]
+        for ax in axes:
+            if a.shape[ax] != 1:
+                raise ValueError("cannot select an axis to squeeze out which has size not equal to one")
+        shape = tuple(s for i, s in enumerate(a.shape) if i not in axes)
+    return reshape(a, shape)
+
+
+def atleast_1d(*arys):
+    res = [reshape(asarray(a), (1,)) if np.ndim(a) == 0 else asarray(a) for a in arys]
+    return res[0] if len(res) == 1 else tuple(res)
+
+
+def atleast_2d(*arys):
+    res = []
+    for a in arys:
+        a = asarray(a)
+        if a.ndim == 0:
+            a = reshape(a, (1, 1))
+        elif a.ndim == 1:
+            a = reshape(a, (1, a.shape[0]))
+        res.append(a)
+    return res[0] if len(res) == 1 else tuple(res)
+
+
+def broadcast_to(a, shape, subok=False):
+    a = asarray(a)
+    shape = _shape_tuple(shape)
+    if a.shape == shape:
+        return a
+    if lazy.broadcast_shapes([a.shape, shape]) != shape:
+        raise ValueError(f"operands could not be broadcast together with remapped shapes [original->remapped]: {a.shape} and requested shape {shape}")
+    if a._node.mat is None and prod(a.shape) == 1 and a._node.op == "full":
+        c = a._node.args[0]
+        return DeviceArray(lazy.make_full(c.value, shape, a.dtype))
+    m = a._mat()
+    off = len(shape) - len(m.shape)
+    strides = [0] * len(shape)
+    shifts = [0] * len(shape)
+    for i, (s, st) in enumerate(zip(m.shape, m.strides)):
+        if s != 1:
+            strides[off + i] = st
+            if m.shifts is not None:
+                shifts[off + i] = m.shifts[i]
+    return _view(a, shape, tuple(strides), 0, tuple(shifts) if m.shifts is not None and any(shifts) else None)
+
+
+def flip(a, axis=None):
+    a = asarray(a)
+    nd = a.ndim
+    axes = range(nd) if axis is None else ([axis] if isinstance(axis, numbers.Integral) else axis)
+    idx = [slice(None)] * nd
+    for ax in axes:
+        idx[_normalize_axis(ax, nd)] = slice(None, None, -1)
+    return a[tuple(idx)]
+
+
+def flipud(a): return flip(a, 0)
+def fliplr(a): return flip(a, 1)
+
+
+def roll(a, shift, axis=None):
+    """np.roll as an index transform: the result is a circularly shifted VIEW that fused kernels read
+    in place (the VJP is the opposite shift, numpy_vjps.py:193)."""
+    a = asarray(a)
+    if axis is None:
+        return reshape(roll(reshape(a, (-1,)), shift, 0), a.shape)
+    axes = (axis,) if isinstance(axis, numbers.Integral) else tuple(axis)
+    shifts_in = (shift,) * len(axes) if isinstance(shift, numbers.Integral) else tuple(shift)
+    if len(shifts_in) != len(axes):
+        raise ValueError("shift and axis must have the same length")
+    m = a._mat()
+    shifts = list(m.shifts) if m.shifts is not None else [0] * a.ndim
+    for s, ax in zip(shifts_in, axes):
+        ax = _normalize_axis(ax, a.ndim)
+        n = a.shape[ax]
+        if n:
+            shifts[ax] = (shifts[ax] + int(s)) % n
+    return _view(a, m.shape, m.strides, 0, tuple(shifts) if any(shifts) else None)
+
+
+def concatenate(arrays, axis=0, out=None, dtype=None, casting="same_kind"):
+    arrays = [asarray(a) for a in arrays]
+    if not arrays:
+        raise ValueError("need at least one array to concatenate")
+    if axis is None:
+        arrays = [ravel(a) for a in arrays]
+        axis = 0
+    nd = arrays[0].ndim
+    if nd == 0:
+        raise ValueError("zero-dimensional arrays cannot be concatenated")
+    axis = _normalize_axis(axis, nd)
+    out_dtype = np.result_type(*[a.dtype for a in arrays]) if dtype is None else np.dtype(dtype)
+    shape = list(arrays[0].shape)
+    for a in arrays[1:]:
+        if a.ndim != nd or any(a.shape[i] != shape[i] for i in range(nd) if i != axis):
+            raise ValueError("all the input array dimensions except for the concatenation axis must match exactly")
+    shape[axis] = sum(a.shape[axis] for a in arrays)
+    out_m = Mat.empty(shape, out_dtype)
+    be = backend.get()
+    pos = 0
+    for a in arrays:
+        if a.size == 0:
+            continue
+        m = a._mat()
+        if m.shifts is not None:
+            m = a._cmat()
+        dst_off = pos * out_m.strides[axis]
+        be.copy_strided(out_m.ptr + dst_off * out_dtype.itemsize, out_dtype, out_m.strides, m.ptr, m.dtype, m.strides,
+                        m.shape)
+        pos += a.shape[axis]
+    return DeviceArray(lazy.leaf(out_m))
+
+
+def stack(arrays, axis=0, out=None):
+    arrays = [asarray(a) for a in arrays]
+    nd = arrays[0].ndim + 1
+    axis = _normalize_axis(axis, nd)
+    return concatenate([expand_dims(a, axis) for a in arrays], axis)
+
+
+def repeat(a, repeats, axis=None):
+    a = asarray(a)
+    if not isinstance(repeats, numbers.Integral):
+        raise NotImplementedError("autograd_b200: np.repeat supports an integer repeat count only")
+    if axis is None:
+        a = ravel(a)
+        axis = 0
+    axis = _normalize_axis(axis, a.ndim)
+    shape = a.shape
+    expanded = reshape(a, shape[: axis + 1] + (1,) + shape[axis + 1:])
+    tiled = broadcast_to(expanded, shape[: axis + 1] + (int(repeats),) + shape[axis + 1:])
+    return reshape(tiled, shape[:axis] + (shape[axis] * int(repeats),) + shape[axis + 1:])
+
+
+def tile(a, reps):
+    a = asarray(a)
+    reps = (reps,) if isinstance(reps, numbers.Integral) else tuple(reps)
+    nd = max(a.ndim, len(reps))
+    a = reshape(a, (1,) * (nd - a.ndim) + a.shape)
+    reps = (1,) * (nd - len(reps)) + reps
+    inter, final, bshape = [], [], []
+    for s, r in zip(a.shape, reps):
+        inter += [1, s]
+        bshape += [r, s]
+        final.append(r * s)
+    return reshape(broadcast_to(reshape(a, tuple(inter)), tuple(bshape)), tuple(final))
+
+
+def pad(array, pad_width, mode="constant", **kwargs):
+    if mode != "constant":
+        raise NotImplementedError("autograd_b200: np.pad supports mode='constant' only")
+    value = kwargs.get("constant_values", 0)
+    a = asarray(array)
+    pw = np.broadcast_to(np.asarray(pad_width, dtype=np.int64), (a.ndim, 2))
+    shape = tuple(int(s + l + r) for s, (l, r) in zip(a.shape, pw))
+    out = full(shape, value, a.dtype)
+    out._own_buffer()
+    idx = tuple(slice(int(l), int(l) + s) for s, (l, r) in zip(a.shape, pw))
+    out[idx] = a
+    return out
+
+
+# =================================================================== indexing
+def _parse_index(shape, idx):
+    """Classify ``idx``: ("basic", [(kind, ...)]) or ("adv", (index arrays, index shape, n leading dims))."""
+    if not isinstance(idx, tuple):
+        idx = (idx,)
+    has_array = any(isinstance(i, (DeviceArray, np.ndarray, list)) for i in idx)
+    if not has_array:
+        n_ell = sum(1 for i in idx if i is Ellipsis)
+        if n_ell > 1:
+            raise IndexError("an index can only have a single ellipsis ('...')")
+        n_real = sum(1 for i in idx if i is not None and i is not Ellipsis)
+        if n_real > len(shape):
+            raise IndexError(f"too many indices for array: array is {len(shape)}-dimensional, but {n_real} were indexed")
+        ops = []
+        dim = 0
+        for i in idx:
+            if i is Ellipsis:
+                for _ in range(len(shape) - n_real):
+                    ops.append(("slice", dim, slice(None)))
+                    dim += 1
+            elif i is None:
+                ops.append(("new",))
+            elif isinstance(i, slice):
+                ops.append(("slice", dim, i))
+                dim += 1
+            elif isinstance(i, (numbers.Integral, np.integer)):
+                n = shape[dim]
+                j = int(i)
+                if not -n <= j < n:
+                    raise IndexError(f"index {j} is out of bounds for axis {dim} with size {n}")
+                ops.append(("int", dim, j + n if j < 0 else j))
+                dim += 1
+            else:
+                raise IndexError(f"unsupported index {i!r}")
+        while dim < len(shape):
+            ops.append(("slice", dim, slice(None)))
+            dim += 1
+        return "basic", ops
+    # advanced: integer arrays on the leading axes, optionally followed by full slices
+    arrays = []
+    for k, i in enumerate(idx):
+        if isinstance(i, slice) and i == slice(None):
+            if any(not (isinstance(j, slice) and j == slice(None)) and j is not Ellipsis for j in idx[k:]):
+                raise NotImplementedError("autograd_b200: index arrays must be on the leading axes")
+            break
+        if i is Ellipsis:
+            break
+        if isinstance(i, (numbers.Integral, np.integer)):
+            arrays.append(np.asarray(int(i), dtype=np.int64))
+        else:
+            arrays.append(i)
+    if len(arrays) > len(shape):
+        raise IndexError("too many indices for array")
+    dev = []
+    for a in arrays:
+        if not isinstance(a, DeviceArray):
+            a = np.asarray(a)
+            if a.dtype == np.bool_:
+                raise NotImplementedError("autograd_b200: boolean mask indexing is not implemented on device")
+            a = _upload(a.astype(np.int64))
+        elif a.dtype == BOOL:
+            raise NotImplementedError("autograd_b200: boolean mask indexing is not implemented on device")
+        elif a.dtype != I64:
+            a = a.astype(np.int64)
+        dev.append(a)
+    idx_shape = lazy.broadcast_shapes([a.shape for a in dev])
+    dev = [broadcast_to(a, idx_shape) for a in dev]
+    return "adv", (dev, idx_shape, len(dev))
+
+
+def _basic_view(m: Mat, ops) -> Mat:
+    if m.shifts is not None:
+        raise AssertionError("rolled views must be made contiguous before slicing")
+    shape, strides, offset = [], [], m.offset
+    for op in ops:
+        if op[0] == "new":
+            shape.append(1)
+            strides.append(0)
+        elif op[0] == "int":
+            _, dim, j = op
+            offset += j * m.strides[dim]
+        else:
+            _, dim, sl = op
+            start, stop, step = sl.indices(m.shape[dim])
+            n = max(0, (stop - start + (step - (1 if step > 0 else -1))) // step)
+            shape.append(n)
+            strides.append(m.strides[dim] * step)
+            offset += start * m.strides[dim]
+    return Mat(m.buf, tuple(shape), tuple(strides), offset, m.dtype)
+
+
+def getitem(a: DeviceArray, idx):
+    if _is_box(idx):
+        return NotImplemented
+    kind, info = _parse_index(a.shape, idx)
+    if kind == "basic":
+        m = a._mat()
+        if m.shifts is not None:
+            m = a._cmat()
+        return DeviceArray(lazy.leaf(_basic_view(m, info)))
+    idx_arrays, idx_shape, n_lead = info
+    m = a._cmat()
+    inner_shape = a.shape[n_lead:]
+    out = Mat.empty(tuple(idx_shape) + tuple(inner_shape), a.dtype)
+    mats = [i._cmat() for i in idx_arrays]
+    backend.get().gather(out.ptr, m.ptr, a.dtype, [p.ptr for p in mats], list(a.shape[:n_lead]), prod(idx_shape),
+                         prod(inner_shape))
+    return DeviceArray(lazy.leaf(out))
+
+
+def take(a, indices, axis=None, out=None, mode="raise"):
+    a = asarray(a)
+    if axis is None:
+        return ravel(a)[indices]
+    axis = _normalize_axis(axis, a.ndim)
+    if axis == 0:
+        return a[indices]
+    moved = moveaxis(a, axis, 0)
+    res = moved[indices]
+    nidx = np.ndim(indices)
+    return moveaxis(res, tuple(range(nidx)), tuple(range(axis, axis + nidx)))
+
+
+# =================================================================== reductions
+def _axes_tuple(axis, ndim):
+    if axis is None:
+        return tuple(range(ndim))
+    if isinstance(axis, (numbers.Integral, np.integer)):
+        axis = (axis,)
+    axes = tuple(sorted(_normalize_axis(int(ax), ndim) for ax in axis))
+    if len(set(axes)) != len(axes):
+        raise ValueError("duplicate value in 'axis'")
+    return axes
+
+
+def reduce_(a, op, axis=None, keepdims=False, dtype=None):
+    """sum / prod / max / min / all / any over ``axis`` (None, int or tuple of ints)."""
+    a = asarray(a)
+    axes = _axes_tuple(axis, a.ndim)
+    in_dtype = a.dtype
+    if op in ("all", "any"):
+        a = a.astype(np.bool_).astype(np.int64) if a.dtype != BOOL else a.astype(np.int64)
+        kern_op, out_dtype, work_dtype = ("min" if op == "all" else "max"), BOOL, I64
+    elif op in ("sum", "prod"):
+        if dtype is not None:
+            work_dtype = np.dtype(dtype)
+        elif in_dtype.kind in "bi":
+            work_dtype = I64
+        else:
+            work_dtype = in_dtype
+        if work_dtype != a.dtype:
+            a = a.astype(work_dtype)
+        kern_op, out_dtype = op, work_dtype
+    else:  # max / min keep the dtype
+        out_dtype = in_dtype
+        work_dtype = in_dtype if in_dtype in (F64, F32, I64) else I64
+        if work_dtype != a.dtype:
+            a = a.astype(work_dtype)
+        kern_op = op
+    shape = a.shape
+    kept_shape = tuple(1 if i in axes else s for i, s in enumerate(shape))
+    final_shape = kept_shape if keepdims else tuple(s for i, s in enumerate(shape) if i not in axes)
+    if not axes:
+        res = a
+    elif a.size == 0 or any(shape[ax] == 0 for ax in axes):
+        if op in ("max", "min"):
+            raise ValueError("zero-size array to reduction operation which has no identity")
+        ident = {"sum": 0, "prod": 1, "all": 1, "any": 0}[op]
+        res = full(kept_shape, ident, work_dtype)
+    else:
+        be = backend.get()
+        cur = a._cmat()
+        cur_shape = list(shape)
+        # reduce one run of adjacent axes at a time, last run first (keeps earlier axis numbers valid)
+        runs, run = [], [axes[-1]]
+        for ax in reversed(axes[:-1]):
+            if ax == run[0] - 1:
+                run.insert(0, ax)
+            else:
+                runs.append(run)
+                run = [ax]
+        runs.append(run)
+        for run in runs:
+            outer = prod(cur_shape[: run[0]])
+            red = prod(cur_shape[run[0]: run[-1] + 1])
+            inner = prod(cur_shape[run[-1] + 1:])
+            out = Mat.empty((outer, inner), work_dtype)
+            be.reduce(out.ptr, cur.ptr, work_dtype, kern_op, outer, red, inner)
+            cur = out
+            for ax in run:
+                cur_shape[ax] = 1
+        res = DeviceArray(lazy.leaf(Mat(cur.buf, kept_shape, lazy.c_strides(kept_shape), 0, work_dtype)))
+    if res.shape != final_shape:
+        res = reshape(res, final_shape)
+    if res.dtype != out_dtype:
+        res = res.astype(out_dtype)
+    return res
+
+
+def sum_(a, axis=None, dtype=None, out=None, keepdims=False, **kw):
+    return reduce_(a, "sum", axis, keepdims, dtype)
+
+
+def prod_(a, axis=None, dtype=None, out=None, keepdims=False, **kw):
+    return reduce_(a, "prod", axis, keepdims, dtype)
+
+
+def amax(a, axis=None, out=None, keepdims=False, **kw):
+    return reduce_(a, "max", axis, keepdims)
+
+
+def amin(a, axis=None, out=None, keepdims=False, **kw):
+    return reduce_(a, "min", axis, keepdims)
+
+
+def all_(a, axis=None, out=None, keepdims=False, **kw):
+    return reduce_(a, "all", axis, keepdims)
+
+
+def any_(a, axis=None, out=None, keepdims=False, **kw):
+    return reduce_(a, "any", axis, keepdims)
+
+
+def count_nonzero(a, axis=None, keepdims=False):
+    return reduce_(asarray(a) != 0, "sum", axis, keepdims)
+
+
+def _count(shape, axes):
+    return prod(shape[ax] for ax in axes)
+
+
+def mean(a, axis=None, dtype=None, out=None, keepdims=False, **kw):
+    a = asarray(a)
+    axes = _axes_tuple(axis, a.ndim)
+    if a.dtype.kind in "bi":
+        a = a.astype(np.float64)
+    s = reduce_(a, "sum", axis, keepdims, dtype)
+    return elementwise("divide", np.true_divide, s, _count(a.shape, axes))
+
+
+def var(a, axis=None, dtype=None, out=None, ddof=0, keepdims=False, **kw):
+    a = asarray(a)
+    axes = _axes_tuple(axis, a.ndim)
+    if a.dtype.kind in "bi":
+        a = a.astype(np.float64)
+    mu = mean(a, axis, keepdims=True)
+    d = a - mu
+    s = reduce_(d * d, "sum", axis, keepdims)
+    return elementwise("divide", np.true_divide, s, max(_count(a.shape, axes) - ddof, 0))
+
+
+def std(a, axis=None, dtype=None, out=None, ddof=0, keepdims=False, **kw):
+    return elementwise("sqrt", np.sqrt, var(a, axis, dtype, out, ddof, keepdims))
+
+
+def argreduce(a, op, axis=None, keepdims=False):
+    a = asarray(a)
+    if axis is None:
+        flat = ravel(a)
+        res = argreduce(flat, op, 0, False)
+        return reshape(res, (1,) * a.ndim) if keepdims else res
+    axis = _normalize_axis(axis, a.ndim)
+    work = a if a.dtype in (F64, F32, I64) else a.astype(np.int64)
+    m = work._cmat()
+    shape = a.shape
+    outer, red, inner = prod(shape[:axis]), shape[axis], prod(shape[axis + 1:])
+    if red == 0:
+        raise ValueError("attempt to get argmax of an empty sequence")
+    out_shape = shape[:axis] + ((1,) if keepdims else ()) + shape[axis + 1:]
+    out = Mat.empty(out_shape, I64)
+    backend.get().argreduce(out.ptr, m.ptr, work.dtype, op, outer, red, inner)
+    return DeviceArray(lazy.leaf(out))
+
+
+def argmax(a, axis=None, out=None, keepdims=False): return argreduce(a, "max", axis, keepdims)
+def argmin(a, axis=None, out=None, keepdims=False): return argreduce(a, "min", axis, keepdims)
+
+
+def logsumexp(a, axis=None, b=None, keepdims=False, return_sign=False):
+    """scipy.special.logsumexp on device (fused max / exp / sum / log kernel; special.py:120)."""
+    if b is not None or return_sign:
+        raise NotImplementedError("autograd_b200: logsumexp supports b=None, return_sign=False only")
+    a = asarray(a)
+    if a.dtype.kind != "f":
+        a = a.astype(np.float64)
+    axes = _axes_tuple(axis, a.ndim)
+    shape = a.shape
+    kept_shape = tuple(1 if i in axes else s for i, s in enumerate(shape))
+    final_shape = kept_shape if keepdims else tuple(s for i, s in enumerate(shape) if i not in axes)
+    if a.ndim == 0:
+        return a
+    # bring the reduced axes together: they must form one adjacent run for the fused kernel
+    if list(axes) != list(range(axes[0], axes[-1] + 1)):
+        keep = [i for i in range(a.ndim) if i not in axes]
+        a = transpose(a, keep + list(axes))
+        shape = a.shape
+        axes = tuple(range(len(keep), a.ndim))
+    m = a._cmat()
+    outer, red, inner = prod(shape[: axes[0]]), prod(shape[axes[0]: axes[-1] + 1]), prod(shape[axes[-1] + 1:])
+    out = Mat.empty((outer, inner), a.dtype)
+    if red == 0:
+        return full(final_shape, -np.inf, a.dtype)
+    backend.get().logsumexp(out.ptr, m.ptr, a.dtype, outer, red, inner)
+    return DeviceArray(lazy.leaf(Mat(out.buf, final_shape, lazy.c_strides(final_shape), 0, a.dtype)))
+
+
+# =================================================================== contractions
+def _float_result(a, b):
+    dt = np.result_type(a.dtype, b.dtype)
+    if dt.kind != "f":
+        dt = F64
+    if dt not in (F64, F32):
+        backend.dtype_code(dt)
+    return np.dtype(dt)
+
+
+def _as_gemm_operand(x: DeviceArray):
+    """A 2-D (or batched 3-D) operand whose payload the GEMM kernel can address by strides."""
+    if x.dtype not in (F64, F32):
+        x = x.astype(np.float64)
+    m = x._mat()
+    if m.shifts is not None:
+        m = x._cmat()
+    return m
+
+
+def _gemm2d(a: DeviceArray, b: DeviceArray, out_dtype=None) -> DeviceArray:
+    """(M,K) @ (K,N) on the DMMA kernel; operands may be arbitrary strided 2-D views."""
+    M, K = a.shape
+    K2, N = b.shape
+    if K != K2:
+        raise ValueError(f"shapes {a.shape} and {b.shape} not aligned: {K} (dim 1) != {K2} (dim 0)")
+    out_dtype = out_dtype or _float_result(a, b)
+    am, bm = _as_gemm_operand(a), _as_gemm_operand(b)
+    out = Mat.empty((M, N), out_dtype)
+    if M and N:
+        backend.get().gemm(out.ptr, out_dtype, (N, 1, 0), am.ptr, am.dtype, (am.strides[0], am.strides[1], 0),
+                           bm.ptr, bm.dtype, (bm.strides[0], bm.strides[1], 0), M, N, K, 1)
+    return DeviceArray(lazy.leaf(out))
+
+
+def tensordot(a, b, axes=2):
+    a, b = asarray(a), asarray(b)
+    if isinstance(axes, (numbers.Integral, np.integer)):
+        n = int(axes)
+        axes_a, axes_b = list(range(a.ndim - n, a.ndim)), list(range(0, n))
+    else:
+        axes_a, axes_b = axes
+        axes_a = [axes_a] if isinstance(axes_a, (numbers.Integral, np.integer)) else list(axes_a)
+        axes_b = [axes_b] if isinstance(axes_b, (numbers.Integral, np.integer)) else list(axes_b)
+    axes_a = [_normalize_axis(int(x), a.ndim) for x in axes_a]
+    axes_b = [_normalize_axis(int(x), b.ndim) for x in axes_b]
+    if len(axes_a) != len(axes_b) or any(a.shape[i] != b.shape[j] for i, j in zip(axes_a, axes_b)):
+        raise ValueError("shape-mismatch for sum")
+    free_a = [i for i in range(a.ndim) if i not in axes_a]
+    free_b = [i for i in range(b.ndim) if i not in axes_b]
+    M = prod(a.shape[i] for i in free_a)
+    K = prod(a.shape[i] for i in axes_a)
+    N = prod(b.shape[i] for i in free_b)
+    out_shape = tuple(a.shape[i] for i in free_a) + tuple(b.shape[i] for i in free_b)
+    a2 = reshape(transpose(a, free_a + axes_a), (M, K))
+    b2 = reshape(transpose(b, axes_b + free_b), (K, N))
+    if K == 0:
+        return zeros(out_shape, _float_result(a, b))
+    return reshape(_gemm2d(a2, b2), out_shape)
+
+
+def dot(a, b, out=None):
+    a, b = asarray(a), asarray(b)
+    if a.ndim == 0 or b.ndim == 0:
+        return a * b
+    if a.ndim == 1 and b.ndim == 1:
+        if a.shape != b.shape:
+            raise ValueError(f"shapes {a.shape} and {b.shape} not aligned")
+        return reduce_(a * b, "sum", None, False)
+    if b.ndim == 1:
+        return tensordot(a, b, ([a.ndim - 1], [0]))
+    return tensordot(a, b, ([a.ndim - 1], [b.ndim - 2]))
+
+
+def matmul(a, b, out=None, **kw):
+    a, b = asarray(a), asarray(b)
+    if a.ndim == 0 or b.ndim == 0:
+        raise ValueError("matmul: Input operand does not have enough dimensions")
+    if a.ndim <= 2 and b.ndim <= 2:
+        return dot(a, b)
+    a_vec, b_vec = a.ndim == 1, b.ndim == 1
+    if a_vec:
+        a = reshape(a, (1, a.shape[0]))
+    if b_vec:
+        b = reshape(b, (b.shape[0], 1))
+    batch_shape = lazy.broadcast_shapes([a.shape[:-2], b.shape[:-2]])
+    M, K = a.shape[-2:]
+    K2, N = b.shape[-2:]
+    if K != K2:
+        raise ValueError(f"matmul: core dimension mismatch {K} vs {K2}")
+    out_dtype = _float_result(a, b)
+    nb = prod(batch_shape)
+    ab = reshape(broadcast_to(a, batch_shape + (M, K)).copy() if a.shape[:-2] != batch_shape else a, (nb, M, K))
+    bb = reshape(broadcast_to(b, batch_shape + (K, N)).copy() if b.shape[:-2] != batch_shape else b, (nb, K, N))
+    am, bm = _as_gemm_operand(ab), _as_gemm_operand(bb)
+    out = Mat.empty((nb, M, N), out_dtype)
+    if nb and M and N:
+        backend.get().gemm(out.ptr, out_dtype, (N, 1, M * N), am.ptr, am.dtype, (am.strides[1], am.strides[2], am.strides[0]),
+                           bm.ptr, bm.dtype, (bm.strides[1], bm.strides[2], bm.strides[0]), M, N, K, nb)
+    res = reshape(DeviceArray(lazy.leaf(out)), batch_shape + (M, N))
+    if a_vec:
+        res = squeeze(res, -2)
+    if b_vec:
+        res = squeeze(res, -1)
+    return res
+
+
+def inner(a, b):
+    a, b = asarray(a), asarray(b)
+    if a.ndim == 0 or b.ndim == 0:
+        return a * b
+    return tensordot(a, b, ([a.ndim - 1], [b.ndim - 1]))
+
+
+def outer(a, b, out=None):
+    a, b = ravel(asarray(a)), ravel(asarray(b))
+    return reshape(a, (-1, 1)) * reshape(b, (1, -1))
+
+
+
+# =================================================================== convolution (NCHW, tiny channel counts)
+def _conv_operands(x, w):
+    x, w = asarray(x), asarray(w)
+    dt = _float_result(x, w)
+    if x.dtype != dt:
+        x = x.astype(dt)
+    if w.dtype != dt:
+        w = w.astype(dt)
+    return x, w, dt
+
+
+def conv2d(x, w, mode="valid", flip=True):
+    """x[N,C,H,W] (*) w[C,F,kh,kw] -> [N,F,Ho,Wo]; ``flip`` = true convolution (signal.py:49-54)."""
+    x, w, dt = _conv_operands(x, w)
+    N, C, H, W = x.shape
+    C2, F, kh, kw = w.shape
+    if C != C2:
+        raise ValueError(f"convolve: channel mismatch {C} vs {C2}")
+    if mode == "valid":
+        Ho, Wo = H - kh + 1, W - kw + 1
+    elif mode == "full":
+        Ho, Wo = H + kh - 1, W + kw - 1
+    else:
+        raise NotImplementedError(f"autograd_b200: convolve mode {mode!r} is not implemented on device")
+    if Ho <= 0 or Wo <= 0:
+        raise ValueError("One array must be larger than the other along all convolved dimensions")
+    out = Mat.empty((N, F, Ho, Wo), dt)
+    backend.get().conv2d(out.ptr, x._cmat().ptr, w._cmat().ptr, dt, N, C, H, W, F, kh, kw, 0 if mode == "valid" else 1,
+                         1 if flip else 0)
+    return DeviceArray(lazy.leaf(out))
+
+
+def conv2d_input_grad(g, w, x_shape, mode="valid"):
+    """VJP of conv2d wrt x (signal.py:153-214, argnum 0): correlate g with the channel-swapped filters."""
+    wt = swapaxes(asarray(w), 0, 1)  # [F, C, kh, kw]
+    return conv2d(g, wt, mode="full" if mode == "valid" else "valid", flip=False)
+
+
+def conv2d_filter_grad(g, x, w_shape, mode="valid"):
+    """VJP of conv2d wrt w (signal.py:153-214, argnum 1): batch-summed valid correlation of x with g."""
+    if mode != "valid":
+        raise NotImplementedError("autograd_b200: filter gradient of a 'full' convolution is not implemented on device")
+    g, x, dt = _conv_operands(g, x)
+    N, C, H, W = x.shape
+    _, F, kh, kw = w_shape
+    out = Mat.empty((C, F, kh, kw), dt)
+    backend.get().conv2d_wgrad(out.ptr, x._cmat().ptr, g._cmat().ptr, dt, N, C, H, W, F, kh, kw)
+    return DeviceArray(lazy.leaf(out))
+
+
+# =================================================================== dispatch tables
+UFUNC_OPS = {
+    np.add: "add", np.subtract: "subtract", np.multiply: "multiply", np.true_divide: "divide",
+    np.negative: "negative", np.positive: "positive", np.power: "power", np.float_power: "power",
+    np.square: "square", np.reciprocal: "reciprocal", np.absolute: "abs", np.fabs: "abs", np.sign: "sign",
+    np.exp: "exp", np.exp2: "exp2", np.expm1: "expm1", np.log: "log", np.log2: "log2", np.log10: "log10",
+    np.log1p: "log1p", np.sqrt: "sqrt", np.cbrt: "cbrt",
+    np.sin: "sin", np.cos: "cos", np.tan: "tan", np.arcsin: "arcsin", np.arccos: "arccos", np.arctan: "arctan",
+    np.sinh: "sinh", np.cosh: "cosh", np.tanh: "tanh", np.arcsinh: "arcsinh", np.arccosh: "arccosh",
+    np.arctanh: "arctanh", np.arctan2: "arctan2", np.hypot: "hypot", np.logaddexp: "logaddexp",
+    np.floor: "floor", np.ceil: "ceil", np.trunc: "trunc", np.rint: "rint",
+    np.remainder: "remainder", np.floor_divide: "floor_divide",
+    np.maximum: "maximum", np.minimum: "minimum", np.fmax: "fmax", np.fmin: "fmin",
+    np.equal: "equal", np.not_equal: "not_equal", np.less: "less", np.less_equal: "less_equal",
+    np.greater: "greater", np.greater_equal: "greater_equal",
+    np.logical_and: "logical_and", np.logical_or: "logical_or", np.logical_xor: "logical_xor",
+    np.logical_not: "logical_not", np.isfinite: "isfinite", np.isnan: "isnan", np.isinf: "isinf",
+    np.conjugate: "conjugate", np.copysign: "copysign",
+}
+UFUNC_REDUCE = {np.add: "sum", np.multiply: "prod", np.maximum: "max", np.minimum: "min",
+                np.logical_and: "all", np.logical_or: "any"}
+
+
+def _result_type(*args):
+    return np.result_type(*[a.dtype if isinstance(a, DeviceArray) else a for a in args])
+
+
+def _np_shape(a): return a.shape
+def _np_ndim(a): return a.ndim
+def _np_size(a, axis=None): return a.size if axis is None else a.shape[axis]
+
+
+FUNCTIONS = {
+    np.shape: _np_shape, np.ndim: _np_ndim, np.size: _np_size, np.result_type: _result_type,
+    np.iscomplexobj: iscomplexobj, np.isrealobj: isrealobj,
+    np.reshape: reshape, np.ravel: ravel, np.transpose: transpose, np.swapaxes: swapaxes, np.moveaxis: moveaxis,
+    np.expand_dims: expand_dims, np.squeeze: squeeze, np.atleast_1d: atleast_1d, np.atleast_2d: atleast_2d,
+    np.broadcast_to: broadcast_to, np.flip: flip, np.flipud: flipud, np.fliplr: fliplr, np.roll: roll,
+    np.concatenate: concatenate, np.stack: stack, np.repeat: repeat, np.tile: tile, np.pad: pad, np.take: take,
+    np.sum: sum_, np.prod: prod_, np.max: amax, np.amax: amax, np.min: amin, np.amin: amin, np.mean: mean,
+    np.var: var, np.std: std, np.all: all_, np.any: any_, np.count_nonzero: count_nonzero,
+    np.argmax: argmax, np.argmin: argmin,
+    np.dot: dot, np.matmul: matmul, np.tensordot: tensordot, np.inner: inner, np.outer: outer,
+    np.where: where, np.clip: clip, np.round: round_, np.around: round_, np.nan_to_num: nan_to_num,
+    np.real: real, np.imag: imag, np.isclose: isclose, np.allclose: allclose, np.array_equal: array_equal,
+    np.zeros_like: zeros_like, np.ones_like: ones_like, np.empty_like: empty_like, np.full_like: full_like,
+    np.copy: lambda a, **kw: asarray(a).copy(),
+    np.astype: lambda a, dtype, copy=True, **kw: asarray(a).astype(dtype),
+    np.meshgrid: meshgrid, np.linspace: linspace,
+}
+# NumPy's own pure-Python implementations of these only call other dispatched functions.
+DECOMPOSE = {np.hstack, np.vstack, np.dstack, np.column_stack, np.atleast_3d, np.rot90, np.kron}

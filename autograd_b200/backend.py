@@ -1,0 +1,244 @@
+"""Device backend: the only place that talks to libb200ag.so.
+
+Everything above (``DeviceArray``, the lazy expression graph, the NumPy
+dispatch tables, the autograd registrations) calls ``backend.get()`` and works
+on raw device pointers (Python ints) plus shape/stride metadata kept on the
+host.  There is one production implementation, :class:`CudaBackend`.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+DTYPE_CODE = {
+    np.dtype(np.float64): 0,
+    np.dtype(np.float32): 1,
+    np.dtype(np.int64): 2,
+    np.dtype(np.int32): 3,
+    np.dtype(np.bool_): 4,
+}
+REDUCE_CODE = {"sum": 0, "max": 1, "min": 2, "prod": 3}
+
+
+def dtype_code(dt) -> int:
+    try:
+        return DTYPE_CODE[np.dtype(dt)]
+    except KeyError:
+        raise TypeError(
+            f"autograd_b200: dtype {np.dtype(dt)} is not supported on the device "
+            "(supported: float64, float32, int64, int32, bool)"
+        ) from None
+
+
+def _i64_array(seq):
+    n = len(seq)
+    return (C.c_int64 * max(n, 1))(*seq)
+
+
+class CudaBackend:
+    """libb200ag.so on one B200 (one process per GPU)."""
+
+    name = "cuda"
+
+    def __init__(self, device: int | None = None):
+        from . import _lib
+
+        self._lib = _lib.lib
+        self._check = _lib.check
+        if device is None:
+            device = int(os.environ.get("B200AG_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+        self.device = device
+        self._check(self._lib.b200ag_init(device))
+        self._kernels = {}  # Program.key -> compiled kernel record
+        sms, major, minor, mem = C.c_int(), C.c_int(), C.c_int(), C.c_size_t()
+        self._check(self._lib.b200ag_device_info(C.byref(sms), C.byref(major), C.byref(minor), C.byref(mem)))
+        self.sm_count = sms.value
+        self.total_mem = mem.value
+
+    # ------------------------------------------------------------ memory
+    def malloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        self._check(self._lib.b200ag_malloc(nbytes, C.byref(p)))
+        return p.value or 0
+
+    def free(self, ptr: int) -> None:
+        self._lib.b200ag_free(ptr)
+
+    def h2d(self, ptr: int, host: np.ndarray) -> None:
+        host = np.ascontiguousarray(host)
+        self._check(self._lib.b200ag_memcpy_h2d(ptr, host.ctypes.data, host.nbytes))
+
+    def d2h(self, host: np.ndarray, ptr: int) -> None:
+        assert host.flags.c_contiguous
+        self._check(self._lib.b200ag_memcpy_d2h(host.ctypes.data, ptr, host.nbytes))
+
+    def d2d(self, dst: int, src: int, nbytes: int) -> None:
+        self._check(self._lib.b200ag_memcpy_d2d(dst, src, nbytes))
+
+    def memset(self, ptr: int, byte: int, nbytes: int) -> None:
+        self._check(self._lib.b200ag_memset(ptr, byte, nbytes))
+
+    def host_alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        self._check(self._lib.b200ag_host_alloc(nbytes, C.byref(p)))
+        return p.value
+
+    def host_free(self, ptr: int) -> None:
+        self._check(self._lib.b200ag_host_free(ptr))
+
+    def mem_stats(self):
+        a, b, c = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        self._check(self._lib.b200ag_mem_stats(C.byref(a), C.byref(b), C.byref(c)))
+        return {"in_use": a.value, "cached": b.value, "peak_in_use": c.value}
+
+    def empty_cache(self) -> None:
+        self._check(self._lib.b200ag_empty_cache())
+
+    # ------------------------------------------------------------ runtime
+    def synchronize(self) -> None:
+        self._check(self._lib.b200ag_synchronize())
+
+    def launch_count(self) -> int:
+        n = C.c_uint64()
+        self._check(self._lib.b200ag_launch_count(C.byref(n)))
+        return n.value
+
+    def stream_handle(self) -> int:
+        p = C.c_void_p()
+        self._check(self._lib.b200ag_stream(C.byref(p)))
+        return p.value or 0
+
+    def event_create(self) -> int:
+        p = C.c_void_p()
+        self._check(self._lib.b200ag_event_create(C.byref(p)))
+        return p.value
+
+    def event_record(self, ev: int) -> None:
+        self._check(self._lib.b200ag_event_record(ev))
+
+    def event_synchronize(self, ev: int) -> None:
+        self._check(self._lib.b200ag_event_synchronize(ev))
+
+    def event_elapsed_ms(self, a: int, b: int) -> float:
+        ms = C.c_float()
+        self._check(self._lib.b200ag_event_elapsed_ms(a, b, C.byref(ms)))
+        return ms.value
+
+    def event_destroy(self, ev: int) -> None:
+        self._check(self._lib.b200ag_event_destroy(ev))
+
+    # ------------------------------------------------------------ CUDA graphs
+    def graph_begin(self) -> None:
+        self._check(self._lib.b200ag_graph_begin())
+
+    def graph_end(self) -> int:
+        p = C.c_void_p()
+        self._check(self._lib.b200ag_graph_end(C.byref(p)))
+        return p.value
+
+    def graph_launch(self, g: int) -> None:
+        self._check(self._lib.b200ag_graph_launch(g))
+
+    def graph_destroy(self, g: int) -> None:
+        self._lib.b200ag_graph_destroy(g)
+
+    def graph_num_nodes(self, g: int) -> int:
+        n = C.c_size_t()
+        self._check(self._lib.b200ag_graph_num_nodes(g, C.byref(n)))
+        return n.value
+
+    # ------------------------------------------------------------ generated elementwise kernels
+    def compile(self, source: str, name: str):
+        """NVRTC-compile ``source`` for sm_100a and return a launchable kernel handle."""
+        from . import kernel_cache
+
+        cubin = kernel_cache.load(source)
+        if cubin is None:
+            p, n = C.c_void_p(), C.c_size_t()
+            self._check(self._lib.b200ag_rtc_compile(source.encode(), (name + ".cu").encode(), C.byref(p), C.byref(n)))
+            cubin = C.string_at(p.value, n.value)
+            self._lib.b200ag_rtc_free(p)
+            kernel_cache.store(source, cubin)
+        k = C.c_void_p()
+        buf = C.create_string_buffer(cubin, len(cubin))
+        self._check(self._lib.b200ag_module_load(buf, len(cubin), name.encode(), C.byref(k)))
+        return k.value, buf  # keep the image alive alongside the handle
+
+    def run_program(self, program, leaf_ptrs, const_values, out_ptrs, n: int) -> None:
+        """Launch the fused elementwise kernel generated for ``program`` (see codegen.py)."""
+        rec = self._kernels.get(program.key)
+        if rec is None:
+            from . import codegen
+
+            source, name, packer = codegen.generate(program)
+            handle, image = self.compile(source, name)
+            rec = (handle, image, packer, program.launch_config(self.sm_count))
+            self._kernels[program.key] = rec
+        handle, _image, packer, (block, elems_per_block, max_grid) = rec
+        if n == 0:
+            return
+        params = packer(n, leaf_ptrs, const_values, out_ptrs, program)
+        grid = min((n + elems_per_block - 1) // elems_per_block, max_grid)
+        self._check(self._lib.b200ag_kernel_launch(handle, grid, block, 0, params, len(params)))
+
+    # ------------------------------------------------------------ static kernels
+    def copy_strided(self, dst, dst_dt, dst_strides, src, src_dt, src_strides, shape) -> None:
+        nd = len(shape)
+        self._check(self._lib.b200ag_copy_strided(
+            dst, dtype_code(dst_dt), _i64_array(dst_strides), src, dtype_code(src_dt), _i64_array(src_strides),
+            _i64_array(shape), nd))
+
+    def add_strided(self, dst, dt, dst_strides, src, src_strides, shape) -> None:
+        nd = len(shape)
+        self._check(self._lib.b200ag_add_strided(
+            dst, dtype_code(dt), _i64_array(dst_strides), src, _i64_array(src_strides), _i64_array(shape), nd))
+
+    def reduce(self, dst, src, dt, op: str, outer: int, red: int, inner: int) -> None:
+        self._check(self._lib.b200ag_reduce(dst, src, dtype_code(dt), REDUCE_CODE[op], outer, red, inner))
+
+    def argreduce(self, dst, src, dt, op: str, outer: int, red: int, inner: int) -> None:
+        self._check(self._lib.b200ag_argreduce(dst, src, dtype_code(dt), REDUCE_CODE[op], outer, red, inner))
+
+    def logsumexp(self, dst, src, dt, outer: int, red: int, inner: int) -> None:
+        self._check(self._lib.b200ag_logsumexp(dst, src, dtype_code(dt), outer, red, inner))
+
+    def gemm(self, c, c_dt, c_str, a, a_dt, a_str, b, b_dt, b_str, M, N, K, batch=1) -> None:
+        """C[b] = A[b] @ B[b]; *_str = (row_stride, col_stride, batch_stride) in elements."""
+        self._check(self._lib.b200ag_gemm(
+            c, dtype_code(c_dt), *c_str, a, dtype_code(a_dt), *a_str, b, dtype_code(b_dt), *b_str, M, N, K, batch))
+
+    def gather(self, dst, src, dt, idx_ptrs, dims, n_index: int, inner: int) -> None:
+        arr = (C.c_void_p * len(idx_ptrs))(*idx_ptrs)
+        self._check(self._lib.b200ag_gather(dst, src, dtype_code(dt), arr, len(idx_ptrs), _i64_array(dims),
+                                            n_index, inner))
+
+    def scatter_add(self, dst, src, dt, idx_ptrs, dims, n_index: int, inner: int) -> None:
+        arr = (C.c_void_p * len(idx_ptrs))(*idx_ptrs)
+        self._check(self._lib.b200ag_scatter_add(dst, src, dtype_code(dt), arr, len(idx_ptrs), _i64_array(dims),
+                                                 n_index, inner))
+
+    def conv2d(self, out, a, b, dt, N, Cc, H, W, F, kh, kw, mode: int, flip: int) -> None:
+        self._check(self._lib.b200ag_conv2d(out, a, b, dtype_code(dt), N, Cc, H, W, F, kh, kw, mode, flip))
+
+    def conv2d_wgrad(self, db, a, g, dt, N, Cc, H, W, F, kh, kw) -> None:
+        self._check(self._lib.b200ag_conv2d_wgrad(db, a, g, dtype_code(dt), N, Cc, H, W, F, kh, kw))
+
+
+_current = None
+
+
+def get():
+    """The active backend; created on first use.  Raises if the CUDA library or a GPU is missing."""
+    global _current
+    if _current is None:
+        _current = CudaBackend()
+    return _current
+
+
+def set_backend(b) -> None:
+    """Install a backend object (used by the CPU test-suite to exercise host logic without a GPU)."""
+    global _current
+    _current = b

@@ -1,0 +1,262 @@
+"""Registration of the device type with autograd's own extension points.
+
+Nothing in autograd is modified on disk.  ``install()`` performs the calls a
+third-party array type is expected to make (docs/tutorial.md:225-282):
+
+* ``Box.register``  (autograd/tracer.py:176-180)  — DeviceArrayBox for DeviceArray
+* ``VSpace.register`` (autograd/core.py:281-286)  — DeviceVSpace
+* ``defvjp`` re-registration (autograd/core.py:68-99) for the few rules whose
+  reference bodies force a host ndarray (``onp.asarray`` in dot_adjoint_0/1,
+  numpy_vjps.py:624,638; ``onp.zeros`` in repeat_to_match_shape, :427) and for the
+  two SciPy-backed primitives that coerce their input (scipy/special.py:120
+  logsumexp, scipy/signal.py:10 convolve).  Every override dispatches on the
+  operand type and hands plain-ndarray calls back to the reference rule.
+* creation functions of ``autograd.numpy`` (zeros/ones/full/arange/linspace/
+  meshgrid/eye) are rebound to device-producing versions because NEP 18 cannot
+  intercept a call that has no array argument (examples/fluidsim/fluidsim.py:19,50;
+  examples/rnn.py:21).
+"""
+
+from __future__ import annotations
+
+import os
+import sys
+from functools import partial
+
+import numpy as onp
+
+from . import array as A
+from .array import DeviceArray
+
+_installed = False
+DeviceArrayBox = None
+DeviceVSpace = None
+
+
+def _import_autograd():
+    try:
+        import autograd  # noqa: F401
+    except ModuleNotFoundError:
+        here = os.path.dirname(os.path.abspath(__file__))
+        for cand in (os.path.join(here, "..", "baseline", "_ref"), "/root/reference"):
+            if os.path.isdir(os.path.join(cand, "autograd")):
+                sys.path.insert(0, os.path.abspath(cand))
+                break
+        import autograd  # noqa: F401
+    return sys.modules["autograd"]
+
+
+def _unbox(x):
+    from autograd.tracer import getval
+
+    return getval(x)
+
+
+def _on_device(*xs) -> bool:
+    for x in xs:
+        if isinstance(_unbox(x), DeviceArray):
+            return True
+    return False
+
+
+def install(creation: bool = True):
+    """Register DeviceArray with autograd.  Idempotent."""
+    global _installed, DeviceArrayBox, DeviceVSpace
+    if _installed:
+        return
+    _import_autograd()
+    import autograd.numpy as anp
+    import autograd.numpy.numpy_vjps as nv
+    import autograd.numpy.numpy_wrapper as nw
+    import autograd.scipy.signal as asignal
+    import autograd.scipy.special as aspecial
+    from autograd.extend import Box, VSpace, defjvp, defvjp, primitive
+    from autograd.numpy.numpy_boxes import ArrayBox
+
+    A._Box = Box
+
+    # ------------------------------------------------------------ Box
+    class _DeviceArrayBox(ArrayBox):
+        __slots__ = []
+
+        def __iter__(self):
+            for i in range(len(self)):
+                yield self[i]
+
+    _DeviceArrayBox.__name__ = "DeviceArrayBox"
+    _DeviceArrayBox.register(DeviceArray)
+    DeviceArrayBox = _DeviceArrayBox
+
+    # ------------------------------------------------------------ VSpace (contract: tests/test_vspaces.py:10-131)
+    class _DeviceVSpace(VSpace):
+        def __init__(self, value):
+            self.shape = value.shape
+            self.dtype = value.dtype
+
+        @property
+        def size(self):
+            return A.prod(self.shape)
+
+        @property
+        def ndim(self):
+            return len(self.shape)
+
+        def zeros(self):
+            return A.zeros(self.shape, self.dtype)
+
+        def ones(self):
+            return A.ones(self.shape, self.dtype)
+
+        def standard_basis(self):
+            for idxs in onp.ndindex(*self.shape):
+                vect = onp.zeros(self.shape, dtype=self.dtype)
+                vect[idxs] = 1
+                yield A.asarray(vect)
+
+        def randn(self):
+            return A.asarray(onp.array(onp.random.randn(*self.shape)).astype(self.dtype))
+
+        def _inner_prod(self, x, y):
+            return A.dot(A.ravel(A.asarray(x)), A.ravel(A.asarray(y)))
+
+    _DeviceVSpace.__name__ = "DeviceVSpace"
+    VSpace.register(DeviceArray, lambda x: _DeviceVSpace(x))
+    DeviceVSpace = _DeviceVSpace
+
+    # ------------------------------------------------------------ broadcast-back of reduction cotangents
+    ref_repeat = nv.repeat_to_match_shape
+
+    def repeat_to_match_shape(g, shape, dtype, axis, keepdims):
+        """numpy_vjps.py:416-427 with the host ``onp.zeros(shape)`` replaced by a symbolic device zero
+        (no HBM traffic: the broadcast is folded into whatever kernel consumes it)."""
+        if not _on_device(g):
+            return ref_repeat(g, shape, dtype, axis, keepdims)
+        if shape == ():
+            return g, 1
+        axis_ = list(axis) if isinstance(axis, tuple) else axis
+        new_shape = onp.array(shape)
+        new_shape[axis_] = 1
+        num_reps = onp.prod(onp.array(shape)[axis_])
+        return anp.reshape(g, tuple(int(s) for s in new_shape)) + A.zeros(shape, dtype), num_reps
+
+    nv.repeat_to_match_shape = repeat_to_match_shape
+    aspecial.repeat_to_match_shape = repeat_to_match_shape
+
+    # ------------------------------------------------------------ dot adjoints (numpy_vjps.py:615-663)
+    @primitive
+    def dev_dot_adjoint_0(B, G, A_meta, B_meta):
+        _, A_ndim, A_dtype, _ = A_meta
+        _, B_ndim, _, _ = B_meta
+        if B_ndim == 0 or B_ndim == 1 or A_ndim == 0:
+            contract_num = max(0, B_ndim - (A_ndim != 0))
+            out = onp.tensordot(G, B, contract_num)
+        else:
+            out = onp.tensordot(G, onp.swapaxes(B, -1, -2), B_ndim - 1)
+        return A.asarray(out).astype(A_dtype)
+
+    @primitive
+    def dev_dot_adjoint_1(A_, G, A_meta, B_meta):
+        _, A_ndim, _, _ = A_meta
+        _, B_ndim, B_dtype, _ = B_meta
+        needs_transpose = B_ndim > 1 and A_ndim != 0
+        swap = (lambda x: onp.swapaxes(x, -1, -2)) if needs_transpose else (lambda x: x)
+        if A_ndim == 0 or A_ndim == 1 or B_ndim == 0:
+            contract_num = max(0, A_ndim - (B_ndim != 0))
+            out = swap(onp.tensordot(G, A_, contract_num))
+        else:
+            out = swap(onp.tensordot(G, A_, [range(-A_ndim - B_ndim + 2, -B_ndim + 1), range(A_ndim - 1)]))
+        return A.asarray(out).astype(B_dtype)
+
+    ref_dot_vjp_0, ref_dot_vjp_1 = nv.dot_vjp_0, nv.dot_vjp_1
+
+    def dot_vjp_0(ans, A_, B):
+        if not _on_device(ans, A_, B):
+            return ref_dot_vjp_0(ans, A_, B)
+        A_meta, B_meta = anp.metadata(A_), anp.metadata(B)
+        return lambda g: nv.match_complex(A_, dev_dot_adjoint_0(B, g, A_meta, B_meta))
+
+    def dot_vjp_1(ans, A_, B):
+        if not _on_device(ans, A_, B):
+            return ref_dot_vjp_1(ans, A_, B)
+        A_meta, B_meta = anp.metadata(A_), anp.metadata(B)
+        return lambda g: nv.match_complex(B, dev_dot_adjoint_1(A_, g, A_meta, B_meta))
+
+    defvjp(anp.dot, dot_vjp_0, dot_vjp_1)
+    defvjp(
+        dev_dot_adjoint_0,
+        lambda ans, B, g, An, Bn: lambda A_: nv.match_complex(B, dev_dot_adjoint_1(A_, g, An, Bn)),
+        lambda ans, B, g, An, Bn: lambda A_: nv.match_complex(g, anp.dot(A_, B)),
+    )
+    defvjp(
+        dev_dot_adjoint_1,
+        lambda ans, A_, g, An, Bn: lambda B: nv.match_complex(A_, dev_dot_adjoint_0(B, g, An, Bn)),
+        lambda ans, A_, g, An, Bn: lambda B: nv.match_complex(g, anp.dot(A_, B)),
+    )
+
+    # ------------------------------------------------------------ logsumexp (scipy/special.py:120-147)
+    ref_logsumexp = aspecial.logsumexp
+
+    def _logsumexp_raw(x, axis=None, b=None, keepdims=False, return_sign=False):
+        if isinstance(x, DeviceArray):
+            if b is not None and not (isinstance(b, float) and b == 1.0):
+                raise NotImplementedError("autograd_b200: logsumexp with weights b is not implemented on device")
+            return A.logsumexp(x, axis=axis, keepdims=keepdims, return_sign=return_sign)
+        return ref_logsumexp.fun(x, axis=axis, b=b, keepdims=keepdims, return_sign=return_sign)
+
+    logsumexp = primitive(_logsumexp_raw)
+    logsumexp.__name__ = "logsumexp"
+    defvjp(logsumexp, aspecial.make_grad_logsumexp)
+    defjvp(logsumexp, aspecial.fwd_grad_logsumexp)
+    aspecial.logsumexp = logsumexp
+
+    # ------------------------------------------------------------ convolve (scipy/signal.py:10-217)
+    ref_convolve = asignal.convolve
+
+    def _is_nchw(A_, B, axes, dot_axes):
+        if axes is None or dot_axes is None:
+            return False
+        try:
+            ok = ([list(a) for a in axes] == [[2, 3], [2, 3]] and [list(a) for a in dot_axes] == [[1], [0]])
+        except TypeError:
+            return False
+        return ok and onp.ndim(A_) == 4 and onp.ndim(B) == 4
+
+    def _convolve_raw(A_, B, axes=None, dot_axes=None, mode="full"):
+        if isinstance(A_, DeviceArray) or isinstance(B, DeviceArray):
+            if not _is_nchw(A_, B, axes, dot_axes) or mode not in ("valid", "full"):
+                raise NotImplementedError(
+                    "autograd_b200: device convolve supports A[N,C,H,W] * B[C,F,kh,kw] with "
+                    "axes=([2,3],[2,3]), dot_axes=([1],[0]), mode 'valid' or 'full'")
+            return A.conv2d(A.asarray(A_), A.asarray(B), mode=mode, flip=True)
+        return ref_convolve.fun(A_, B, axes=axes, dot_axes=dot_axes, mode=mode)
+
+    convolve = primitive(_convolve_raw)
+    convolve.__name__ = "convolve"
+    conv_input_grad = primitive(A.conv2d_input_grad)
+    conv_filter_grad = primitive(A.conv2d_filter_grad)
+
+    def convolve_vjp(argnum, ans, A_, B, axes=None, dot_axes=None, mode="full"):
+        if not _on_device(ans, A_, B):
+            return asignal.grad_convolve(argnum, ans, A_, B, axes=axes, dot_axes=dot_axes, mode=mode)
+        a_shape = anp.shape(A_)
+        if argnum == 0:
+            return lambda g: conv_input_grad(g, B, a_shape, mode)
+        return lambda g: conv_filter_grad(g, A_, anp.shape(B), mode)
+
+    defvjp(convolve, partial(convolve_vjp, 0), partial(convolve_vjp, 1))
+    asignal.convolve = convolve
+
+    # ------------------------------------------------------------ creation functions
+    if creation:
+        for name, fn in (("zeros", A.zeros), ("ones", A.ones), ("full", A.full), ("empty", A.empty),
+                         ("arange", A.arange), ("linspace", A.linspace), ("eye", A.eye), ("meshgrid", A.meshgrid)):
+            wrapped = primitive(fn)
+            wrapped.__name__ = name
+            setattr(nw, name, wrapped)
+            setattr(anp, name, wrapped)
+
+    _installed = True
+
+
+def is_installed() -> bool:
+    return _installed

@@ -1,0 +1,469 @@
+"""Lazy elementwise expression graph and its flush into fused kernels.
+
+Every NumPy ufunc call that reaches the device type (forward primitives at
+autograd/tracer.py:94 and the operator chains inside VJP closures,
+autograd/numpy/numpy_vjps.py:76-191) only records a :class:`Node` here.  Nothing
+is computed until a value is needed (a reduction, a contraction, a gather, a host
+read); then the whole DAG behind that value is compiled into ONE grid-stride
+kernel that reads each distinct input once and writes each needed output once —
+the "tape fusion" of BASELINE.json's north_star.  Each arithmetic op keeps
+NumPy's loop dtype and is rounded on its own (``--fmad=false``), so a fused chain
+gives the same bits as the chain of NumPy ufunc calls it replaces.
+"""
+
+from __future__ import annotations
+
+import itertools
+import math
+
+import numpy as np
+
+from . import backend
+
+F64 = np.dtype(np.float64)
+F32 = np.dtype(np.float32)
+I64 = np.dtype(np.int64)
+I32 = np.dtype(np.int32)
+BOOL = np.dtype(np.bool_)
+SUPPORTED = (F64, F32, I64, I32, BOOL)
+
+_ids = itertools.count(1)
+
+# Relative ALU cost of one op (used to decide what to keep vs. recompute).
+_COST = {
+    "add": 1, "subtract": 1, "multiply": 1, "negative": 1, "positive": 0, "square": 1, "abs": 1, "sign": 2,
+    "where": 1, "cast": 1, "full": 0, "maximum": 2, "minimum": 2, "fmax": 2, "fmin": 2,
+    "equal": 1, "not_equal": 1, "less": 1, "less_equal": 1, "greater": 1, "greater_equal": 1,
+    "logical_and": 1, "logical_or": 1, "logical_not": 1, "logical_xor": 1,
+    "isfinite": 1, "isnan": 1, "isinf": 1, "floor": 1, "ceil": 1, "trunc": 1, "rint": 1,
+    "divide": 6, "reciprocal": 6, "sqrt": 6, "remainder": 8, "floor_divide": 8,
+}
+_DEFAULT_COST = 12  # transcendental functions
+
+# An interior node that Python can still see (a VJP closure holds it) is written
+# out as an extra output of the fused kernel once recomputing it would cost more
+# than this; cheaper ones are simply recomputed by whoever needs them later.
+KEEP_COST = 12
+# Hard caps that force a flush while a graph is still being built.
+MAX_NODES = 1500
+MAX_LEAVES = 48
+
+
+class Buffer:
+    """Owner of one device allocation; freed back to the pool when unreferenced."""
+
+    __slots__ = ("ptr", "nbytes", "__weakref__")
+
+    def __init__(self, nbytes: int):
+        self.nbytes = int(nbytes)
+        self.ptr = backend.get().malloc(self.nbytes)
+
+    def __del__(self):
+        ptr, self.ptr = self.ptr, 0
+        if ptr:
+            try:
+                backend.get().free(ptr)
+            except Exception:
+                pass
+
+
+def c_strides(shape):
+    st, acc = [], 1
+    for s in reversed(shape):
+        st.append(acc)
+        acc *= s
+    return tuple(reversed(st))
+
+
+def prod(shape) -> int:
+    n = 1
+    for s in shape:
+        n *= s
+    return n
+
+
+class Mat:
+    """A materialised array: a strided (optionally circularly shifted) window on a Buffer."""
+
+    __slots__ = ("buf", "shape", "strides", "offset", "dtype", "shifts")
+
+    def __init__(self, buf, shape, strides, offset, dtype, shifts=None):
+        self.buf = buf
+        self.shape = tuple(shape)
+        self.strides = tuple(strides)
+        self.offset = offset
+        self.dtype = dtype
+        self.shifts = shifts  # None or per-dim circular shift (np.roll as an index transform)
+
+    @property
+    def ptr(self) -> int:
+        return self.buf.ptr + self.offset * self.dtype.itemsize
+
+    @property
+    def is_contiguous(self) -> bool:
+        if self.shifts is not None:
+            return False
+        acc = 1
+        for s, st in zip(reversed(self.shape), reversed(self.strides)):
+            if s != 1 and st != acc:
+                return False
+            acc *= s
+        return True
+
+    @staticmethod
+    def empty(shape, dtype):
+        shape = tuple(int(s) for s in shape)
+        return Mat(Buffer(prod(shape) * dtype.itemsize), shape, c_strides(shape), 0, dtype)
+
+
+class Const:
+    """A host scalar operand.  ``dtype is None`` marks a weak Python scalar (NEP 50)."""
+
+    __slots__ = ("value", "dtype")
+
+    def __init__(self, value, dtype=None):
+        self.value = value
+        self.dtype = dtype
+
+
+_EMPTY = frozenset()
+
+
+class Node:
+    __slots__ = ("op", "args", "in_dtypes", "shape", "dtype", "mat", "nid", "lo", "cost", "leafset", "nhandles",
+                 "__weakref__")
+
+    def __init__(self, op, args, in_dtypes, shape, dtype, mat=None):
+        self.op = op
+        self.args = args
+        self.in_dtypes = in_dtypes
+        self.shape = shape
+        self.dtype = dtype
+        self.mat = mat
+        self.nid = next(_ids)
+        self.nhandles = 0
+        if mat is None:
+            lo, cost, leafset = self.nid, _COST.get(op, _DEFAULT_COST), _EMPTY
+            for a in args:
+                if type(a) is Node:
+                    if a.mat is None:
+                        if a.lo < lo:
+                            lo = a.lo
+                        cost += a.cost
+                        leafset = leafset | a.leafset if leafset else a.leafset
+                    else:
+                        leafset = leafset | a.leafset
+            self.lo = lo
+            self.cost = cost if cost < 1 << 30 else 1 << 30
+            self.leafset = leafset
+        else:
+            self.lo = self.nid
+            self.cost = 0
+            self.leafset = frozenset((self.nid,))
+
+
+def leaf(mat: Mat) -> Node:
+    return Node(None, (), (), mat.shape, mat.dtype, mat)
+
+
+# ---------------------------------------------------------------- dtype resolution (NumPy's own rules)
+_resolve_cache = {}
+
+
+def _type_key(a):
+    if type(a) is Node:
+        return a.dtype
+    if a.dtype is not None:
+        return a.dtype
+    v = a.value
+    if isinstance(v, bool):
+        return BOOL
+    if isinstance(v, int):
+        return int
+    if isinstance(v, float):
+        return float
+    raise TypeError(f"autograd_b200: unsupported scalar operand {v!r} of type {type(v).__name__}")
+
+
+def resolve(ufunc, args):
+    """(input loop dtypes, output dtype) NumPy would use for ``ufunc(*args)``."""
+    key = (ufunc,) + tuple(_type_key(a) for a in args)
+    hit = _resolve_cache.get(key)
+    if hit is None:
+        sig = key[1:] + (None,) * ufunc.nout
+        try:
+            res = ufunc.resolve_dtypes(sig)
+        except TypeError as e:
+            raise TypeError(f"autograd_b200: {ufunc.__name__} is not defined for operand types {key[1:]}: {e}") from None
+        ins, out = tuple(res[: ufunc.nin]), res[ufunc.nin]
+        for d in ins + (out,):
+            if d not in SUPPORTED:
+                raise TypeError(
+                    f"autograd_b200: {ufunc.__name__}{key[1:]} needs dtype {d}, which the device backend does not support"
+                )
+        hit = (ins, out)
+        _resolve_cache[key] = hit
+    return hit
+
+
+def broadcast_shapes(shapes):
+    first = shapes[0]
+    same = True
+    for s in shapes:
+        if s != first:
+            same = False
+            break
+    if same:
+        return first
+    nd = max(len(s) for s in shapes)
+    out = [1] * nd
+    for s in shapes:
+        off = nd - len(s)
+        for i, d in enumerate(s):
+            j = off + i
+            if d != 1:
+                if out[j] == 1:
+                    out[j] = d
+                elif out[j] != d:
+                    raise ValueError(f"operands could not be broadcast together with shapes {' '.join(map(str, shapes))}")
+    return tuple(out)
+
+
+def make_op(op, ufunc, args):
+    """Record ``ufunc(*args)``; args are Nodes and Consts."""
+    in_dtypes, out_dtype = resolve(ufunc, args)
+    shapes = [a.shape for a in args if type(a) is Node]
+    shape = broadcast_shapes(shapes) if shapes else ()
+    node = Node(op, tuple(args), in_dtypes, shape, out_dtype)
+    _maybe_flush_growing(node)
+    return node
+
+
+def make_where(c, x, y, out_dtype):
+    shapes = [a.shape for a in (c, x, y) if type(a) is Node]
+    shape = broadcast_shapes(shapes) if shapes else ()
+    node = Node("where", (c, x, y), (BOOL, out_dtype, out_dtype), shape, out_dtype)
+    _maybe_flush_growing(node)
+    return node
+
+
+def make_cast(x, dtype):
+    return Node("cast", (x,), (x.dtype,), x.shape, dtype)
+
+
+def make_full(value, shape, dtype):
+    return Node("full", (Const(value, dtype),), (dtype,), tuple(shape), dtype)
+
+
+def _maybe_flush_growing(node):
+    if len(node.leafset) > MAX_LEAVES:
+        materialize(node)
+    elif node.nid - node.lo > MAX_NODES:
+        order, _ = _collect([node])
+        if len(order) > MAX_NODES:
+            materialize(node)
+        else:
+            node.lo = node.nid - len(order)  # tighten the bound so we do not re-walk every op
+
+
+# ---------------------------------------------------------------- flush
+class Program:
+    """Structural description of one fused kernel; ``key`` identifies the generated code."""
+
+    __slots__ = ("instrs", "leaves", "consts", "outputs", "ndim", "idx64", "vec", "key", "cost")
+
+    def __init__(self, instrs, leaves, consts, outputs, ndim, idx64, vec, cost):
+        self.instrs = instrs      # tuple of (op, in_dtype chars, out dtype char, arg refs)
+        self.leaves = leaves      # tuple of (dtype char, layout class 'C'|'S'|'G', has_shift)
+        self.consts = consts      # tuple of C scalar kinds: 'd' | 'q' | '?'
+        self.outputs = outputs    # tuple of (instr index, dtype char)
+        self.ndim = ndim          # collapsed iteration dims (0 when no 'G' leaf needs coordinates)
+        self.idx64 = idx64
+        self.vec = vec            # elements per thread per step on the vector path
+        self.cost = cost
+        self.key = (instrs, leaves, consts, outputs, ndim, idx64, vec)
+
+    def launch_config(self, sm_count):
+        block = 256
+        return block, block * self.vec, sm_count * 16
+
+
+# small exact constants are baked into the source (lets the compiler fold x*1, x**2 ...)
+_BAKED = {0.0, 1.0, -1.0, 2.0, -2.0, 0.5, -0.5, 3.0, 4.0, 0.25}
+
+
+def _collect(roots):
+    """Topological order of the un-materialised nodes behind ``roots`` plus the distinct leaves."""
+    order, seen, leaves = [], set(), []
+    stack = [(r, False) for r in roots]
+    while stack:
+        node, done = stack.pop()
+        if done:
+            order.append(node)
+            continue
+        if node.nid in seen:
+            continue
+        seen.add(node.nid)
+        if node.mat is not None:
+            leaves.append(node)
+            continue
+        stack.append((node, True))
+        for a in node.args:
+            if type(a) is Node and a.nid not in seen:
+                stack.append((a, False))
+    return order, leaves
+
+
+def _aligned_strides(mat, root_shape):
+    """Element strides (and shifts) of ``mat`` broadcast against ``root_shape`` (right-aligned)."""
+    nd = len(root_shape)
+    off = nd - len(mat.shape)
+    strides = [0] * nd
+    shifts = [0] * nd
+    for i, (s, st) in enumerate(zip(mat.shape, mat.strides)):
+        if s != 1:
+            strides[off + i] = st
+            if mat.shifts is not None:
+                shifts[off + i] = mat.shifts[i]
+    return strides, shifts
+
+
+def _collapse_dims(root_shape, leaf_layouts):
+    """Drop unit dims, then merge adjacent iteration dims that every general-layout leaf walks contiguously."""
+    keep = [i for i, d in enumerate(root_shape) if d != 1]
+    dims = [root_shape[i] for i in keep]
+    lay = [([s[i] for i in keep], [sh[i] for i in keep]) for s, sh in leaf_layouts]
+    i = len(dims) - 1
+    while i > 0:
+        if all(not sh[i] and not sh[i - 1] and s[i - 1] == s[i] * dims[i] for s, sh in lay):
+            for s, sh in lay:
+                s[i - 1] = s[i]
+                del s[i], sh[i]
+            dims[i - 1] *= dims[i]
+            del dims[i]
+        i -= 1
+    if not dims:
+        dims = [1]
+        lay = [([0], [0]) for _ in lay]
+    return dims, lay
+
+
+def materialize(root: Node) -> Mat:
+    """Compute ``root`` (and any still-visible expensive interior node) with one fused kernel."""
+    if root.mat is not None:
+        return root.mat
+    order, leaf_nodes = _collect([root])
+    root_shape = root.shape
+    n = prod(root_shape)
+
+    # interior nodes that Python still holds and that are costly to recompute become extra outputs
+    outs = [root]
+    for nd_ in order:
+        if nd_ is not root and nd_.nhandles > 0 and nd_.cost >= KEEP_COST and nd_.shape == root_shape:
+            outs.append(nd_)
+
+    # ---- leaves: classify layout relative to the iteration space
+    leaf_index, leaf_descs, leaf_ptrs, g_layouts, g_slots = {}, [], [], [], []
+    dedup = {}
+    for ln in leaf_nodes:
+        m = ln.mat
+        strides, shifts = _aligned_strides(m, root_shape)
+        sig = (m.buf.ptr, m.offset, m.dtype.char, tuple(strides), tuple(shifts))
+        if sig in dedup:
+            leaf_index[ln.nid] = dedup[sig]
+            continue
+        has_shift = any(shifts)
+        if all(st == 0 for st in strides) or n <= 1:
+            cls = "S"
+        elif not has_shift and m.shape == root_shape and m.is_contiguous:
+            cls = "C"
+        else:
+            cls = "G"
+        idx = len(leaf_descs)
+        dedup[sig] = idx
+        leaf_index[ln.nid] = idx
+        leaf_descs.append((m.dtype.char, cls, has_shift))
+        leaf_ptrs.append([m.ptr, None, None])
+        if cls == "G":
+            g_layouts.append((strides, shifts))
+            g_slots.append(idx)
+
+    if g_layouts:
+        dims, lay = _collapse_dims(root_shape, g_layouts)
+        for slot, (s, sh) in zip(g_slots, lay):
+            leaf_ptrs[slot][1] = s
+            leaf_ptrs[slot][2] = sh
+        ndim = len(dims)
+    else:
+        dims, ndim = [], 0
+
+    # ---- instructions
+    const_kinds, const_values, const_dedup = [], [], {}
+    instr_index, instrs = {}, []
+    for nd_ in order:
+        refs = []
+        for a, in_dt in zip(nd_.args, nd_.in_dtypes):
+            if type(a) is Node:
+                if a.mat is not None:
+                    refs.append(("l", leaf_index[a.nid]))
+                else:
+                    refs.append(("n", instr_index[a.nid]))
+            else:
+                v = a.value
+                kind = "d" if in_dt.kind == "f" else ("?" if in_dt.kind == "b" else "q")
+                if kind == "d":
+                    v = float(np.asarray(v).astype(in_dt))  # NumPy's cast of the scalar to the loop dtype
+                elif kind == "q":
+                    v = int(v)
+                else:
+                    v = bool(v)
+                if (kind == "d" and v in _BAKED and not (v == 0.0 and math.copysign(1.0, v) < 0)) or (
+                    kind == "q" and -4 <= v <= 4
+                ) or kind == "?":
+                    refs.append(("k", v if kind != "d" else float(v)))
+                else:
+                    ck = (kind, v)
+                    ci = const_dedup.get(ck)
+                    if ci is None:
+                        ci = len(const_kinds)
+                        const_dedup[ck] = ci
+                        const_kinds.append(kind)
+                        const_values.append(v)
+                    refs.append(("c", ci))
+        instr_index[nd_.nid] = len(instrs)
+        instrs.append((nd_.op, tuple(d.char for d in nd_.in_dtypes), nd_.dtype.char, tuple(refs)))
+
+    outputs = tuple((instr_index[o.nid], o.dtype.char) for o in outs)
+
+    # ---- vector width: 16-byte accesses on every contiguous leaf and output when alignment allows
+    max_item = max([o.dtype.itemsize for o in outs] + [np.dtype(c).itemsize for c, cls, _ in leaf_descs if cls == "C"])
+    vec = max(1, 16 // max_item)
+    total_cost = sum(_COST.get(nd_.op, _DEFAULT_COST) for nd_ in order)
+    if total_cost > 400 or n < 4096:
+        vec = 1  # heavy bodies are ALU-bound: keep the code size down
+    if vec > 1:
+        for (ch, cls, _), lp in zip(leaf_descs, leaf_ptrs):
+            if cls == "C" and lp[0] % (np.dtype(ch).itemsize * vec):
+                vec = 1
+                break
+    max_extent = n
+    for lp in leaf_ptrs:
+        if lp[1] is not None:
+            ext = sum(abs(s) * (d - 1) for s, d in zip(lp[1], dims)) + 1
+            max_extent = max(max_extent, ext)
+    idx64 = max_extent >= (1 << 31) - (1 << 24)
+
+    program = Program(tuple(instrs), tuple(leaf_descs), tuple(const_kinds), outputs, ndim, idx64, vec, total_cost)
+
+    out_mats = [Mat.empty(root_shape, o.dtype) for o in outs]
+    backend.get().run_program(program, (leaf_ptrs, dims), const_values, [m.ptr for m in out_mats], n)
+    for o, m in zip(outs, out_mats):
+        o.mat = m
+    # drop the graph behind everything that is now materialised or no longer needed
+    for nd_ in order:
+        if nd_.mat is not None:
+            nd_.args = ()
+            nd_.cost = 0
+            nd_.lo = nd_.nid
+            nd_.leafset = frozenset((nd_.nid,))
+    return root.mat

@@ -1,0 +1,177 @@
+/*
+ * b200ag.h — C ABI of libb200ag.so, the sm_100a kernel library behind the
+ * device-resident array type that plugs into HIPS/autograd.
+ *
+ * The reference (autograd 1.9.1) is pure Python and has no FFI of its own: its
+ * "kernel boundary" is the raw NumPy call at autograd/tracer.py:94 (forward)
+ * and the NumPy operators used inside VJP closures (autograd/core.py:30,
+ * autograd/numpy/numpy_vjps.py).  Every entry point below names the NumPy /
+ * SciPy behaviour (and the reference call site that reaches it) it replaces.
+ *
+ * Conventions
+ *   - plain C: raw device pointers, int64 shapes/strides (in ELEMENTS), enums as
+ *     int.  No torch / Python types cross this boundary.
+ *   - every function returns 0 on success; non-zero means failure and
+ *     b200ag_last_error() holds a message (the ctypes layer raises RuntimeError).
+ *   - kernels never allocate: outputs are preallocated by the caller
+ *     (autograd's lifetime model: intermediates live as long as VJP closures
+ *     hold them, docs/updateguide.md:71).
+ *   - all work is enqueued on ONE library-owned stream (b200ag_stream); the
+ *     reference is single-threaded (tracer.py:154 global trace_stack).
+ */
+#ifndef B200AG_H
+#define B200AG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200AG_MAX_DIMS 8
+
+/* dtype codes (NumPy dtypes the five BASELINE configs produce) */
+enum {
+  B200AG_F64 = 0,  /* numpy.float64 — autograd's default */
+  B200AG_F32 = 1,  /* numpy.float32 */
+  B200AG_I64 = 2,  /* numpy.int64   (astype(int), np.mod indices; fluidsim.py:56-62) */
+  B200AG_I32 = 3,  /* numpy.int32 */
+  B200AG_BOOL = 4  /* numpy.bool_   (comparison masks; numpy_vjps.py:521,911) */
+};
+
+/* reduction codes */
+enum { B200AG_SUM = 0, B200AG_MAX = 1, B200AG_MIN = 2, B200AG_PROD = 3 };
+
+/* ---------------------------------------------------------------- runtime */
+int b200ag_init(int device);                /* select GPU, create stream; idempotent */
+int b200ag_shutdown(void);
+const char* b200ag_last_error(void);
+int b200ag_device_count(int* n);
+int b200ag_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem);
+int b200ag_stream(void** stream);           /* cudaStream_t every kernel is launched on */
+int b200ag_synchronize(void);
+int b200ag_launch_count(uint64_t* n);       /* kernels launched by this library so far */
+
+/* ---------------------------------------------------------------- memory
+ * Replaces numpy's allocator for array payloads (np.zeros/np.empty results,
+ * ufunc outputs).  Caching, stream-ordered on the library stream. */
+int b200ag_malloc(size_t nbytes, void** ptr);
+int b200ag_free(void* ptr);
+int b200ag_empty_cache(void);
+int b200ag_mem_stats(size_t* in_use, size_t* cached, size_t* peak_in_use);
+int b200ag_host_alloc(size_t nbytes, void** ptr);   /* pinned host staging */
+int b200ag_host_free(void* ptr);
+int b200ag_memcpy_h2d(void* dst, const void* src, size_t nbytes);   /* async on the stream */
+int b200ag_memcpy_d2h(void* dst, const void* src, size_t nbytes);   /* returns after the copy */
+int b200ag_memcpy_d2d(void* dst, const void* src, size_t nbytes);
+int b200ag_memset(void* dst, int byte, size_t nbytes);
+
+/* ---------------------------------------------------------------- events (bench timing on the library stream) */
+int b200ag_event_create(void** ev);
+int b200ag_event_record(void* ev);
+int b200ag_event_synchronize(void* ev);
+int b200ag_event_elapsed_ms(void* start, void* stop, float* ms);
+int b200ag_event_destroy(void* ev);
+
+/* ---------------------------------------------------------------- generated elementwise kernels
+ * Replaces NumPy ufunc inner loops (tracer.py:94 → numpy add/multiply/exp/...)
+ * and the operator chains inside VJP closures (numpy_vjps.py:76-191).  The
+ * Python layer emits CUDA C for a fused expression DAG; these compile it for
+ * sm_100a (NVRTC, --fmad=false so every op is individually rounded like a
+ * NumPy ufunc) and launch it. */
+int b200ag_rtc_compile(const char* src, const char* name, void** cubin, size_t* cubin_size);
+int b200ag_rtc_free(void* cubin);
+int b200ag_rtc_log(const char** log);       /* log of the last compile */
+int b200ag_module_load(const void* cubin, size_t size, const char* kernel_name, void** kernel);
+int b200ag_kernel_launch(void* kernel, uint32_t grid, uint32_t block, uint32_t smem,
+                         const void* params, size_t params_size);   /* one by-value struct param */
+int b200ag_kernel_max_active_blocks(void* kernel, int block, size_t smem, int* nblocks);
+
+/* ---------------------------------------------------------------- layout
+ * Strided copy with dtype conversion: ndarray.astype / np.ascontiguousarray /
+ * transposed & sliced views made contiguous / np.concatenate pieces / np.pad
+ * interior (numpy_wrapper.py:57-59, numpy_vjps.py:246-251,750-759,957-975).
+ * dst and src are described by shape + element strides (may be 0 or negative). */
+int b200ag_copy_strided(void* dst, int dst_dtype, const int64_t* dst_strides,
+                        const void* src, int src_dtype, const int64_t* src_strides,
+                        const int64_t* shape, int ndim);
+/* dst[...] += src[...] over a strided destination window (VJP of basic slicing:
+ * np.add.at(A, slice_tuple, g), numpy_vjps.py:941-950) */
+int b200ag_add_strided(void* dst, int dtype, const int64_t* dst_strides,
+                       const void* src, const int64_t* src_strides,
+                       const int64_t* shape, int ndim);
+
+/* ---------------------------------------------------------------- reductions
+ * np.sum / np.max / np.min / np.prod over one contiguous group of axes of a
+ * C-contiguous array viewed as [outer, reduce, inner] (numpy_vjps.py:443-530,
+ * unbroadcast :883-892). */
+int b200ag_reduce(void* dst, const void* src, int dtype, int op,
+                  int64_t outer, int64_t reduce, int64_t inner);
+/* argmax/argmin over the reduce axis of [outer, reduce, inner]; first occurrence
+ * wins (numpy semantics); dst is int64. */
+int b200ag_argreduce(int64_t* dst, const void* src, int dtype, int op,
+                     int64_t outer, int64_t reduce, int64_t inner);
+
+/* ---------------------------------------------------------------- contractions
+ * C[M,N] = A[M,K] · B[K,N] with arbitrary element strides on every operand, so
+ * swapaxes/transpose views feed the kernel without a copy.  Accumulates in
+ * FP64 on the DMMA tensor pipe (mma.sync m8n8k4.f64); inputs may be f32 or f64
+ * (NumPy promotes f32·f64 → f64, examples/rnn.py:21) and the result is
+ * rounded to c_dtype on store (onp.asarray(out, dtype=A_dtype),
+ * numpy_vjps.py:624,638).  batch > 1 = stacked matmul with batch strides.
+ * Replaces np.dot / np.matmul / np.tensordot (numpy_vjps.py:567-742). */
+int b200ag_gemm(void* C, int c_dtype, int64_t c_rs, int64_t c_cs, int64_t c_bs,
+                const void* A, int a_dtype, int64_t a_rs, int64_t a_cs, int64_t a_bs,
+                const void* B, int b_dtype, int64_t b_rs, int64_t b_cs, int64_t b_bs,
+                int64_t M, int64_t N, int64_t K, int64_t batch);
+
+/* ---------------------------------------------------------------- gather / scatter-add
+ * out[i] = src[idx0[i], idx1[i], ..., :] (integer-array indexing on the leading
+ * nidx axes, ArrayBox.__getitem__, numpy_boxes.py:16-18) and its VJP
+ * np.add.at(A, idx, g) with duplicate indices accumulated (numpy_vjps.py:941-950).
+ * Negative indices wrap like NumPy.  inner = product of the trailing,
+ * un-indexed dimensions (contiguous). */
+int b200ag_gather(void* dst, const void* src, int dtype,
+                  const int64_t* const* idx, int nidx, const int64_t* src_dims,
+                  int64_t n_index, int64_t inner);
+int b200ag_scatter_add(void* dst, const void* src, int dtype,
+                       const int64_t* const* idx, int nidx, const int64_t* dst_dims,
+                       int64_t n_index, int64_t inner);
+
+/* ---------------------------------------------------------------- logsumexp
+ * scipy.special.logsumexp(a, axis, keepdims=True) over the middle axis of
+ * [outer, reduce, inner], following SciPy 1.18.1 _logsumexp (max; m = #max;
+ * s = sum exp(a - max) over the non-max entries; log1p(s/m) + log(m) + max);
+ * reference primitive: autograd/scipy/special.py:120. */
+int b200ag_logsumexp(void* dst, const void* src, int dtype,
+                     int64_t outer, int64_t reduce, int64_t inner);
+
+/* ---------------------------------------------------------------- convolution
+ * autograd.scipy.signal.convolve(A, B, axes=([2,3],[2,3]), dot_axes=([1],[0]),
+ * mode) for A[N,C,H,W], B[C,F,kh,kw] → out[N,F,Ho,Wo] (true convolution: the
+ * kernel is flipped), mode 0 = valid, 1 = full (autograd/scipy/signal.py:10-65),
+ * plus the weight-gradient form used by its VJP (signal.py:153-214):
+ * dB[C,F,kh,kw] = sum_n valid-correlate(A[n,c], G[n,f]). */
+int b200ag_conv2d(void* out, const void* A, const void* B, int dtype,
+                  int64_t N, int64_t C, int64_t H, int64_t W,
+                  int64_t F, int64_t kh, int64_t kw, int mode, int flip);
+int b200ag_conv2d_wgrad(void* dB, const void* A, const void* G, int dtype,
+                        int64_t N, int64_t C, int64_t H, int64_t W,
+                        int64_t F, int64_t kh, int64_t kw);
+
+/* ---------------------------------------------------------------- CUDA graphs
+ * Capture everything the library enqueues between begin and end (a recorded
+ * forward+backward tape) and replay it with one launch (core.py:26-33 is the
+ * loop being replayed).  Memory allocated while capturing stays owned by the
+ * graph until it is destroyed. */
+int b200ag_graph_begin(void);
+int b200ag_graph_end(void** graph);
+int b200ag_graph_launch(void* graph);
+int b200ag_graph_destroy(void* graph);
+int b200ag_graph_num_nodes(void* graph, size_t* n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200AG_H */
