@@ -14,7 +14,7 @@ without the built library raises.
 
 from . import array, backend, lazy
 from .array import DeviceArray, asarray, to_device
-from .install import install, is_installed
+from .install import host_arrays, install, is_installed
 
 
 def synchronize() -> None:
@@ -25,5 +25,5 @@ def to_host(x):
     return x.get() if isinstance(x, DeviceArray) else x
 
 
-__all__ = ["DeviceArray", "asarray", "to_device", "to_host", "install", "is_installed", "synchronize", "array",
+__all__ = ["host_arrays", "DeviceArray", "asarray", "to_device", "to_host", "install", "is_installed", "synchronize", "array",
            "backend", "lazy"]

@@ -181,6 +181,8 @@ class DeviceArray:
             if _is_box(x):
                 return NotImplemented
         if method == "__call__":
+            if ufunc is np.matmul:  # a generalized ufunc, not an elementwise one
+                return matmul(*inputs)
             op = UFUNC_OPS.get(ufunc)
             if op is None:
                 raise TypeError(f"autograd_b200: numpy.{ufunc.__name__} has no device implementation")
@@ -581,7 +583,7 @@ def where(cond, x=None, y=None):
         elif o.dtype is not None:
             dts.append(o.dtype)
         else:
-            dts.append(type(raw) if not isinstance(raw, np.ndarray) else raw.dtype)
+            dts.append(o.value)  # weak Python scalar (NEP 50): pass the value, not its type
     out_dtype = np.result_type(*dts)
     backend.dtype_code(out_dtype)
     return DeviceArray(lazy.make_where(c, a, b, np.dtype(out_dtype)))
@@ -672,7 +674,7 @@ def reshape(a, shape=None, order="C", *, newshape=None, copy=None):
         return a
     node = a._node
     if node.mat is None and _reshape_transparent(node):
-        return DeviceArray(_reshape_lazy(node, shape, {}))
+        return DeviceArray(_reshape_lazy(node, shape, node.shape, {}))
     m = a._mat()
     new_strides = _reshape_strides(m, shape)
     if new_strides is None:
@@ -707,14 +709,11 @@ def _reshape_transparent(node) -> bool:
     return True
 
 
-def _reshape_lazy(node, shape, memo):
+def _reshape_lazy(node, shape, root_shape, memo):
     hit = memo.get(node.nid)
     if hit is not None:
         return hit
-    if prod(node.shape) == 1:
-        new_shape = ()
-    else:
-        new_shape = shape
+    new_shape = shape if node.shape == root_shape else ()  # anything else is a size-1 broadcast operand
     if node.mat is not None:
         m = node.mat
         if new_shape == ():
@@ -722,8 +721,8 @@ def _reshape_lazy(node, shape, memo):
         else:
             res = lazy.leaf(Mat(m.buf, shape, lazy.c_strides(shape), m.offset, m.dtype))
     else:
-        args = tuple(_reshape_lazy(a, shape, memo) if type(a) is Node else a for a in node.args)
-        res = Node(node.op, args, node.in_dtypes, new_shape if node.op != "full" else new_shape, node.dtype)
+        args = tuple(_reshape_lazy(a, shape, root_shape, memo) if type(a) is Node else a for a in node.args)
+        res = Node(node.op, args, node.in_dtypes, new_shape, node.dtype)
     memo[node.nid] = res
     return res
 
@@ -1443,7 +1442,8 @@ def conv2d(x, w, mode="valid", flip=True):
     if Ho <= 0 or Wo <= 0:
         raise ValueError("One array must be larger than the other along all convolved dimensions")
     out = Mat.empty((N, F, Ho, Wo), dt)
-    backend.get().conv2d(out.ptr, x._cmat().ptr, w._cmat().ptr, dt, N, C, H, W, F, kh, kw, 0 if mode == "valid" else 1,
+    xm, wm = x._cmat(), w._cmat()  # keep the (possibly temporary) contiguous payloads alive across the launch
+    backend.get().conv2d(out.ptr, xm.ptr, wm.ptr, dt, N, C, H, W, F, kh, kw, 0 if mode == "valid" else 1,
                          1 if flip else 0)
     return DeviceArray(lazy.leaf(out))
 
@@ -1462,7 +1462,8 @@ def conv2d_filter_grad(g, x, w_shape, mode="valid"):
     N, C, H, W = x.shape
     _, F, kh, kw = w_shape
     out = Mat.empty((C, F, kh, kw), dt)
-    backend.get().conv2d_wgrad(out.ptr, x._cmat().ptr, g._cmat().ptr, dt, N, C, H, W, F, kh, kw)
+    xm, gm = x._cmat(), g._cmat()
+    backend.get().conv2d_wgrad(out.ptr, xm.ptr, gm.ptr, dt, N, C, H, W, F, kh, kw)
     return DeviceArray(lazy.leaf(out))
 
 

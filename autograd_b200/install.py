@@ -19,6 +19,7 @@ third-party array type is expected to make (docs/tutorial.md:225-282):
 
 from __future__ import annotations
 
+import contextlib
 import os
 import sys
 from functools import partial
@@ -246,11 +247,58 @@ def install(creation: bool = True):
     defvjp(convolve, partial(convolve_vjp, 0), partial(convolve_vjp, 1))
     asignal.convolve = convolve
 
+    # ------------------------------------------------------------ np.array(...) on device values
+    # numpy_wrapper.py:83-108: ``array`` funnels into two primitives that call ``_np.array`` (not NEP-18
+    # dispatchable); jacobian() reaches them through np.stack (differential_operators.py:76).
+    ref_from_scalar, ref_from_args = nw._array_from_scalar_or_array, nw.array_from_args
+
+    def _from_scalar_raw(array_args, array_kwargs, scalar):
+        if isinstance(scalar, DeviceArray):
+            out = scalar
+            dtype = array_kwargs.get("dtype", array_args[0] if array_args else None)
+            if dtype is not None:
+                out = out.astype(dtype)
+            ndmin = array_kwargs.get("ndmin", 0)
+            if ndmin > out.ndim:
+                out = A.reshape(out, (1,) * (ndmin - out.ndim) + out.shape)
+            return out
+        return ref_from_scalar.fun(array_args, array_kwargs, scalar)
+
+    def _from_args_raw(array_args, array_kwargs, *args):
+        if any(isinstance(a, DeviceArray) for a in args):
+            out = A.stack([A.asarray(a) for a in args])
+            dtype = array_kwargs.get("dtype", array_args[0] if array_args else None)
+            return out if dtype is None else out.astype(dtype)
+        return ref_from_args.fun(array_args, array_kwargs, *args)
+
+    from_scalar = primitive(_from_scalar_raw)
+    from_args = primitive(_from_args_raw)
+    defvjp(from_scalar, nv.array_from_scalar_or_array_gradmaker, argnums=(2, 3))
+    from autograd.extend import defvjp_argnum
+
+    defvjp_argnum(from_args, nv.array_from_args_gradmaker)
+    from autograd.extend import defjvp_argnum, vspace
+
+    # forward rules restated from numpy_jvps.py:26-32
+    defjvp_argnum(from_args, lambda argnum, g, ans, args, kwargs: nv.untake(g, argnum - 2, vspace(ans)))
+    defjvp(from_scalar, None, None, lambda g, ans, args, kwargs, _: nw._array_from_scalar_or_array(args, kwargs, g))
+    nw._array_from_scalar_or_array = from_scalar
+    nw.array_from_args = from_args
+    anp._array_from_scalar_or_array = from_scalar
+    anp.array_from_args = from_args
+
     # ------------------------------------------------------------ creation functions
     if creation:
+        def switchable(dev_fn, host_fn):
+            def create(*args, **kwargs):
+                if _host_creation_depth or any(isinstance(a, onp.ndarray) for a in args):
+                    return host_fn(*args, **kwargs)
+                return dev_fn(*args, **kwargs)
+            return create
+
         for name, fn in (("zeros", A.zeros), ("ones", A.ones), ("full", A.full), ("empty", A.empty),
                          ("arange", A.arange), ("linspace", A.linspace), ("eye", A.eye), ("meshgrid", A.meshgrid)):
-            wrapped = primitive(fn)
+            wrapped = primitive(switchable(fn, getattr(onp, name)))
             wrapped.__name__ = name
             setattr(nw, name, wrapped)
             setattr(anp, name, wrapped)
@@ -260,3 +308,18 @@ def install(creation: bool = True):
 
 def is_installed() -> bool:
     return _installed
+
+
+_host_creation_depth = 0
+
+
+@contextlib.contextmanager
+def host_arrays():
+    """Inside this block ``autograd.numpy.zeros/ones/arange/...`` create host ndarrays again, so the
+    unmodified reference path (autograd on NumPy) can run in the same process as the device path."""
+    global _host_creation_depth
+    _host_creation_depth += 1
+    try:
+        yield
+    finally:
+        _host_creation_depth -= 1

@@ -1,0 +1,607 @@
+"""Parity cases shared by the CPU (fake backend: host logic) and GPU (CUDA backend: kernels) suites.
+
+Every case builds seeded host inputs, runs the SAME expression on numpy.ndarray (the oracle: NumPy is
+what the reference executes at autograd/tracer.py:94) and on DeviceArray, and compares with the
+north_star tolerances: bit-exact for bool/int results, 1e-12 for f64 elementwise, 1e-10 for f64
+reductions/contractions, 1e-5 for f32 — relative to the max-norm of the reference.
+"""
+
+from __future__ import annotations
+
+import numpy as onp
+
+import autograd_b200 as b200
+
+TOL_ELEMENTWISE = 1e-12
+TOL_REDUCE = 1e-10
+TOL_F32 = 1e-5
+
+
+def to_dev(x):
+    if isinstance(x, onp.ndarray):
+        return b200.asarray(x)
+    if isinstance(x, (list, tuple)):
+        return type(x)(to_dev(e) for e in x)
+    if isinstance(x, dict):
+        return {k: to_dev(v) for k, v in x.items()}
+    return x
+
+
+def to_host(x):
+    if isinstance(x, b200.DeviceArray):
+        return x.get()
+    if isinstance(x, (list, tuple)):
+        return type(x)(to_host(e) for e in x)
+    if isinstance(x, dict):
+        return {k: to_host(v) for k, v in x.items()}
+    return x
+
+
+def leaves(t):
+    if isinstance(t, (list, tuple)):
+        return [l for x in t for l in leaves(x)]
+    if isinstance(t, dict):
+        return [l for k in sorted(t) for l in leaves(t[k])]
+    return [t]
+
+
+def assert_close(got, want, tol, what=""):
+    got, want = onp.asarray(got), onp.asarray(want)
+    assert got.shape == want.shape, f"{what}: shape {got.shape} != {want.shape}"
+    assert got.dtype == want.dtype, f"{what}: dtype {got.dtype} != {want.dtype}"
+    if want.dtype.kind in "biu" or tol == 0:
+        assert onp.array_equal(got, want, equal_nan=want.dtype.kind == "f"), f"{what}: not bit-exact"
+        return
+    if want.dtype == onp.float32:
+        tol = max(tol, TOL_F32)
+    finite = onp.isfinite(want)
+    assert onp.array_equal(finite, onp.isfinite(got)), f"{what}: non-finite pattern differs"
+    assert onp.array_equal(got[~finite], want[~finite], equal_nan=True), f"{what}: inf/nan values differ"
+    if finite.any():
+        scale = onp.max(onp.abs(want[finite]))
+        err = onp.max(onp.abs(got[finite].astype(onp.float64) - want[finite].astype(onp.float64)))
+        assert err <= tol * max(scale, 1e-300), f"{what}: max abs err {err:.3e} > {tol:g} * {scale:.3e}"
+
+
+def check(fn, *host_args, tol=TOL_ELEMENTWISE, what=""):
+    """fn(np_module_like, *args) evaluated on host and device."""
+    with onp.errstate(all="ignore"):
+        want = fn(*host_args)
+    got = fn(*to_dev(list(host_args)))
+    for g, w in zip(leaves(to_host(got)), leaves(want)):
+        assert_close(g, w, tol, what or getattr(fn, "__name__", "case"))
+
+
+def rs(seed=0):
+    return onp.random.RandomState(seed)
+
+
+# =============================================================== elementwise
+UNARY = ["negative", "exp", "log", "log1p", "expm1", "tanh", "sinh", "cosh", "sin", "cos", "tan", "sqrt", "square",
+         "abs", "sign", "floor", "ceil", "trunc", "rint", "reciprocal", "exp2", "log2", "log10", "arctan", "arcsin",
+         "arccos", "arcsinh", "isfinite", "isnan", "isinf", "logical_not"]
+BINARY = ["add", "subtract", "multiply", "true_divide", "power", "maximum", "minimum", "fmax", "fmin", "remainder",
+          "floor_divide", "arctan2", "hypot", "logaddexp", "equal", "not_equal", "less", "less_equal", "greater",
+          "greater_equal", "logical_and", "logical_or", "logical_xor"]
+
+
+def case_unary(name, dtype=onp.float64, n=4099):
+    x = rs(1).randn(n).astype(dtype) * 2
+    if name in ("log", "sqrt", "log2", "log10", "reciprocal"):
+        x = onp.abs(x) + 0.1
+    if name in ("log1p",):
+        x = onp.abs(x)
+    if name in ("arcsin", "arccos"):
+        x = onp.clip(x / 4, -1, 1)
+    x[:4] = [0.0, -0.0, 1.0, -1.0] if name not in ("log", "sqrt", "log2", "log10", "reciprocal") else [1.0, 2.0, 0.5, 4.0]
+    f = getattr(onp, name)
+    # CUDA libm functions are within 1-2 ulp of glibc's; transcendental results get a few ulp of slack
+    exact = name in ("negative", "square", "abs", "sign", "floor", "ceil", "trunc", "rint", "isfinite", "isnan",
+                     "isinf", "logical_not", "sqrt", "reciprocal")
+    check(lambda a: f(a), x, tol=0 if exact else TOL_ELEMENTWISE, what=f"{name}[{onp.dtype(dtype).name}]")
+
+
+def case_binary(name, dtype=onp.float64):
+    r = rs(2)
+    a = (r.randn(37, 53) * 3).astype(dtype)
+    b = (r.randn(37, 53) * 3).astype(dtype)
+    if name == "power":
+        a = onp.abs(a) + 0.1
+    if name in ("remainder", "floor_divide"):
+        b[onp.abs(b) < 0.3] = 0.7
+    f = getattr(onp, name)
+    exact = name in ("add", "subtract", "multiply", "true_divide", "maximum", "minimum", "fmax", "fmin", "remainder",
+                     "floor_divide", "equal", "not_equal", "less", "less_equal", "greater", "greater_equal",
+                     "logical_and", "logical_or", "logical_xor")
+    check(lambda x, y: f(x, y), a, b, tol=0 if exact else TOL_ELEMENTWISE, what=f"{name}[{onp.dtype(dtype).name}]")
+
+
+def case_nan_inf_propagation():
+    x = onp.array([onp.nan, onp.inf, -onp.inf, 0.0, -0.0, 1.5, -2.5, 1e308, 5e-324])
+    y = onp.array([1.0, onp.nan, 2.0, -0.0, 0.0, onp.inf, -onp.inf, 1e308, 2.0])
+    check(lambda a, b: (onp.maximum(a, b), onp.minimum(a, b), onp.fmax(a, b), onp.fmin(a, b), a + b, a * b, a / b,
+                        onp.sign(a), onp.abs(a), onp.isfinite(a), a == b, a < b), x, y, tol=0, what="nan/inf")
+
+
+def case_broadcasting():
+    r = rs(3)
+    a, b, c, s = r.randn(7, 1, 5), r.randn(3, 5), r.randn(5), r.randn()
+    check(lambda a, b, c: a * b + c - 2.5 * a / (b * b + 1.0), a, b, c, tol=0, what="broadcast chain")
+    check(lambda a, c: (a + c) * s, a, c, tol=0, what="python-float scalar")
+    check(lambda a: a + onp.float64(1.5), a, tol=0, what="numpy scalar")
+    check(lambda b: 1 - b, b, tol=0, what="int scalar rsub")
+    check(lambda b: 2 ** b, b, what="rpow")
+
+
+def case_dtype_promotion():
+    r = rs(4)
+    f32, f64 = r.randn(33).astype(onp.float32), r.randn(33)
+    i64, i32 = r.randint(-50, 50, 33), r.randint(-50, 50, 33).astype(onp.int32)
+    bl = r.rand(33) > 0.5
+    check(lambda a, b: a + b, f32, f64, tol=0, what="f32+f64")
+    check(lambda a: a * 2.0, f32, tol=0, what="f32*pyfloat stays f32")
+    check(lambda a: a * 2, i64, tol=0, what="i64*pyint")
+    check(lambda a: a * 2.5, i64, tol=0, what="i64*pyfloat")
+    check(lambda a, b: a + b, i32, i64, tol=0, what="i32+i64")
+    check(lambda a, b: a / b, i64, i64 * 0 + 3, tol=0, what="int true_divide")
+    check(lambda a, b: a * b, f64, bl, tol=0, what="f64*bool")
+    check(lambda a: onp.exp(a), i64 % 5, what="exp(int)")
+    check(lambda a, b: a == b, i64, f64, tol=0, what="int==float")
+    check(lambda a: a.astype(onp.float32), f64, tol=0, what="astype f32")
+    check(lambda a: (a * 7.3).astype(int), f64, tol=0, what="astype int truncation")
+    check(lambda a: a.astype(bool), f64 * (r.rand(33) > 0.3), tol=0, what="astype bool")
+    check(lambda a, b: onp.where(b, a, 0.0), f32, bl, tol=0, what="where f32 / py float")
+    check(lambda a, b: onp.where(b, a, a * 2), i64, bl, tol=0, what="where int")
+
+
+def case_integer_semantics():
+    r = rs(5)
+    a = r.randint(-100, 100, 257)
+    b = r.randint(1, 9, 257) * onp.where(r.rand(257) > 0.5, 1, -1)
+    check(lambda a, b: (a % b, a // b, onp.mod(a, 7), onp.mod(a, -7), a ** 2, onp.abs(a), -a, onp.sign(a)), a, b, tol=0,
+          what="floored int mod / floordiv")
+    x = r.randn(257) * 20
+    check(lambda x: (onp.mod(x, 3.0), onp.mod(x, -3.0), onp.floor(x), onp.floor(x).astype(int) % 16), x, tol=0,
+          what="floored float mod")
+
+
+def case_power_special_exponents():
+    x = onp.abs(rs(6).randn(301)) + 0.05
+    check(lambda x: (x ** 2, x ** 1, x ** 0, x ** -1, x ** 0.5, x ** 3, x ** 2.5, x ** -2), x, what="pow const")
+    check(lambda x: x ** 2, -x, tol=0, what="square of negative")
+
+
+def case_fused_chain_matches_unfused():
+    x = rs(7).randn(100003)
+    def f(x):
+        t = onp.exp(-2 * x)
+        u = (1.0 - t) / (1.0 + t)
+        return u * u - x * 0.25 + onp.tanh(x) / (1.0 + x * x)
+    check(f, x, what="fused chain")
+
+
+def case_large_vector_tail():
+    for n in (1, 2, 3, 255, 256, 257, 4095, 4097, 100001):
+        x = rs(n).randn(n)
+        y = rs(n + 1).randn(n)
+        check(lambda a, b: a * b + a, x, y, tol=0, what=f"n={n}")
+        check(lambda a: a[1:] * 2.0, x, tol=0, what=f"misaligned view n={n}") if n > 1 else None
+
+
+# =============================================================== layout
+def case_views():
+    r = rs(8)
+    a = r.randn(6, 8, 10)
+    check(lambda a: a.T + 1.0, a, tol=0, what="T")
+    check(lambda a: onp.swapaxes(a, 0, 2) * 2, a, tol=0, what="swapaxes")
+    check(lambda a: onp.transpose(a, (1, 2, 0)) - 1, a, tol=0, what="transpose perm")
+    check(lambda a: a[1:5, ::2, ::-1] + 0.5, a, tol=0, what="slices")
+    check(lambda a: a[2], a, tol=0, what="int index view")
+    check(lambda a: a[:, None, 3, :] * 1.0, a, tol=0, what="newaxis")
+    check(lambda a: a[..., -1], a, tol=0, what="ellipsis")
+    check(lambda a: onp.reshape(a, (48, 10)) + 0, a, tol=0, what="reshape")
+    check(lambda a: onp.reshape(a.T, (10, 48)) + 0, a, tol=0, what="reshape of transposed (copy)")
+    check(lambda a: onp.ravel(a[:, ::2]), a, tol=0, what="ravel strided")
+    check(lambda a: onp.expand_dims(a, 1).shape == (6, 1, 8, 10) and onp.squeeze(a[:, :1], 1), a, tol=0, what="squeeze")
+    check(lambda a: onp.broadcast_to(a[:, :1, :], (6, 8, 10)) + a, a, tol=0, what="broadcast_to")
+    check(lambda a: onp.moveaxis(a, 0, -1) + 0, a, tol=0, what="moveaxis")
+    check(lambda a: onp.flip(a, 1) + 0, a, tol=0, what="flip")
+    check(lambda a: (a + 1.0).reshape(-1) * 2, a, tol=0, what="lazy reshape stays fused")
+    check(lambda a: a.copy().T.copy(), a, tol=0, what="copy of transpose (tiled transpose kernel)")
+    big = r.randn(130, 70)
+    check(lambda a: a.T.copy(), big, tol=0, what="2-D transpose copy")
+    check(lambda a: a.astype(onp.float32).T.copy(), big, tol=0, what="2-D transpose copy f32")
+
+
+def case_roll():
+    r = rs(9)
+    a = r.randn(16, 24)
+    for shift, axis in ((1, 0), (-1, 0), (1, 1), (-1, 1), (5, 0), (-7, 1), (16, 0), (0, 1)):
+        check(lambda a: onp.roll(a, shift, axis=axis), a, tol=0, what=f"roll {shift} axis {axis}")
+    check(lambda a: onp.roll(a, 1, axis=0) + onp.roll(a, -1, axis=0) + onp.roll(a, 1, axis=1) + onp.roll(a, -1, axis=1),
+          a, tol=0, what="stencil of rolls")
+    check(lambda a: onp.roll(onp.roll(a, 2, axis=0), -3, axis=1) * 2.0, a, tol=0, what="roll of roll")
+    check(lambda a: onp.roll(a, 3), a, tol=0, what="flat roll")
+    check(lambda a: onp.roll(a + 1.0, 1, axis=1), a, tol=0, what="roll of pending expression")
+    check(lambda a: onp.roll(a, 1, axis=0).T + 0, a, tol=0, what="transpose of rolled")
+    check(lambda a: onp.roll(a, 1, axis=0)[2:5], a, tol=0, what="slice of rolled")
+
+
+def case_concat_repeat_pad():
+    r = rs(10)
+    a, b, c = r.randn(4, 5), r.randn(3, 5), r.randn(4, 2)
+    check(lambda a, b: onp.concatenate([a, b], 0), a, b, tol=0, what="concat0")
+    check(lambda a, c: onp.concatenate([a, c], axis=1), a, c, tol=0, what="concat1")
+    check(lambda a, c: onp.hstack((a, c, onp.ones((4, 1)))), a, c, tol=0, what="hstack with ones")
+    check(lambda a, b: onp.vstack((a, b)), a, b, tol=0, what="vstack")
+    check(lambda a: onp.stack([a, a * 2], axis=1), a, tol=0, what="stack")
+    check(lambda a: onp.concatenate([a.astype(onp.float32), a]), a, tol=0, what="concat promotes")
+    check(lambda a: onp.repeat(a[:1], 7, axis=0), a, tol=0, what="repeat row")
+    check(lambda a: onp.repeat(a, 3, axis=1), a, tol=0, what="repeat general")
+    check(lambda a: onp.repeat(a, 2), a, tol=0, what="repeat flat")
+    check(lambda a: onp.tile(a, (2, 3)), a, tol=0, what="tile")
+    check(lambda a: onp.pad(a, ((1, 2), (0, 3)), mode="constant"), a, tol=0, what="pad")
+    check(lambda a: onp.concatenate([onp.ravel(a), onp.ravel(a.T)]), a, tol=0, what="flatten-style concat")
+
+
+def case_indexing():
+    r = rs(11)
+    f = r.randn(12, 9)
+    i = r.randint(0, 12, 200)
+    j = r.randint(0, 9, 200)
+    check(lambda f, i, j: f[i, j], f, i, j, tol=0, what="pair gather")
+    check(lambda f, i: f[i], f, i, tol=0, what="row gather")
+    check(lambda f, i: f[i - 12], f, i, tol=0, what="negative indices")
+    check(lambda f, i, j: f[i.reshape(10, 20), j.reshape(10, 20)], f, i, j, tol=0, what="2-D index arrays")
+    check(lambda f: f[[0, 0, 3]], f, tol=0, what="list index with duplicates")
+    check(lambda f, i: onp.take(f, i, axis=0), f, i, tol=0, what="take axis 0")
+    check(lambda f, j: onp.take(f, j, axis=1), f, j, tol=0, what="take axis 1")
+    v = r.randn(200)
+
+    def scatter(f, i, j, v):
+        out = onp.zeros(f.shape) if isinstance(f, onp.ndarray) else b200.array.zeros(f.shape)
+        onp.add.at(out, (i, j), v)
+        return out
+
+    check(scatter, f, i, j, v, tol=TOL_REDUCE, what="add.at with duplicates")
+
+    def scatter_rows(f, i):
+        out = onp.zeros(f.shape) if isinstance(f, onp.ndarray) else b200.array.zeros(f.shape)
+        onp.add.at(out, i, f[i] * 0.5)
+        return out
+
+    check(scatter_rows, f, i, tol=TOL_REDUCE, what="add.at rows")
+
+    def scatter_slice(f):
+        out = onp.zeros(f.shape) if isinstance(f, onp.ndarray) else b200.array.zeros(f.shape)
+        onp.add.at(out, (slice(2, 8), slice(None, None, 2)), f[2:8, ::2])
+        onp.add.at(out, 3, f[3])
+        return out
+
+    check(scatter_slice, f, tol=0, what="add.at slices")
+
+    def setitem(f):
+        out = f * 1.0
+        out[1:3] = 7.0
+        out[:, 0] = f[:, 1]
+        return out
+
+    check(setitem, f, tol=0, what="setitem")
+
+
+# =============================================================== reductions
+def case_reductions():
+    r = rs(12)
+    a = r.randn(13, 7, 11)
+    for axis in (None, 0, 1, 2, -1, (0, 1), (1, 2), (0, 2), (0, 1, 2)):
+        for kd in (False, True):
+            check(lambda a: onp.sum(a, axis=axis, keepdims=kd), a, tol=TOL_REDUCE, what=f"sum {axis} {kd}")
+            check(lambda a: onp.max(a, axis=axis, keepdims=kd), a, tol=0, what=f"max {axis} {kd}")
+            check(lambda a: onp.min(a, axis=axis, keepdims=kd), a, tol=0, what=f"min {axis} {kd}")
+            check(lambda a: onp.mean(a, axis=axis, keepdims=kd), a, tol=TOL_REDUCE, what=f"mean {axis} {kd}")
+    check(lambda a: onp.prod(a[:, :3, :2], axis=1), a, tol=TOL_REDUCE, what="prod")
+    check(lambda a: (onp.var(a, axis=1), onp.std(a, axis=(0, 2), ddof=1)), a, tol=TOL_REDUCE, what="var/std")
+    check(lambda a: onp.sum(a > 0.3, axis=1), a, tol=0, what="sum of bool -> int64")
+    check(lambda a: onp.sum((a * 10).astype(int)), a, tol=0, what="int sum")
+    check(lambda a: (onp.all(a > -10), onp.any(a > 10), onp.any(a > 1, axis=2)), a, tol=0, what="all/any")
+    check(lambda a: a.sum(axis=0).max(), a, tol=TOL_REDUCE, what="methods")
+    check(lambda a: onp.sum(a.astype(onp.float32), axis=1), a, tol=TOL_F32, what="f32 sum")
+    check(lambda a: (onp.argmax(a, axis=1), onp.argmin(a, axis=0), onp.argmax(a)), a, tol=0, what="argmax")
+    t = onp.array([[1.0, 3.0, 3.0, 2.0], [5.0, 5.0, 1.0, 5.0]])
+    check(lambda t: (onp.argmax(t, axis=1), onp.max(t, axis=1)), t, tol=0, what="argmax ties: first wins")
+
+
+def case_big_reductions():
+    r = rs(13)
+    v = r.randn(1 << 20)
+    check(lambda v: onp.sum(v), v, tol=TOL_REDUCE, what="sum 1M")
+    check(lambda v: onp.max(v), v, tol=0, what="max 1M")
+    m = r.randn(256, 200)
+    check(lambda m: onp.sum(m, axis=0), m, tol=TOL_REDUCE, what="column sum (bias grad)")
+    check(lambda m: onp.sum(m, axis=1), m, tol=TOL_REDUCE, what="row sum")
+    w = r.randn(33, 6, 12, 2, 12, 2)
+    check(lambda w: onp.max(onp.max(w, axis=3), axis=4), w, tol=0, what="maxpool-style double max")
+    check(lambda m: onp.sum(m * m), m, tol=TOL_REDUCE, what="sum of squares")
+    check(lambda v: onp.dot(v, v), v, tol=TOL_REDUCE, what="dot 1-D 1M")
+
+
+def case_logsumexp():
+    from scipy.special import logsumexp as sp_lse
+
+    r = rs(14)
+    a = r.randn(64, 10) * 5
+
+    def lse(x, **kw):
+        return sp_lse(x, **kw) if isinstance(x, onp.ndarray) else b200.array.logsumexp(x, **kw)
+
+    check(lambda a: lse(a, axis=1, keepdims=True), a, tol=TOL_REDUCE, what="lse rows keepdims")
+    check(lambda a: lse(a, axis=0), a, tol=TOL_REDUCE, what="lse cols")
+    check(lambda a: lse(a), a, tol=TOL_REDUCE, what="lse all")
+    b = r.randn(5, 128, 3)
+    check(lambda b: lse(b, axis=1), b, tol=TOL_REDUCE, what="lse middle axis")
+    c = onp.array([[1000.0, 1000.0, -1000.0], [-onp.inf, -onp.inf, -onp.inf], [0.0, onp.inf, 1.0], [3.0, 3.0, 3.0]])
+    check(lambda c: lse(c, axis=1), c, tol=TOL_REDUCE, what="lse extremes / ties / -inf rows")
+    check(lambda a: lse(a.astype(onp.float32), axis=1), a, tol=TOL_F32, what="lse f32")
+
+
+# =============================================================== contractions
+def case_gemm():
+    r = rs(15)
+    for (m, k, n) in ((1, 1, 1), (7, 5, 3), (64, 64, 64), (65, 33, 129), (256, 784, 200), (130, 17, 260)):
+        a, b = r.randn(m, k), r.randn(k, n)
+        check(lambda a, b: onp.dot(a, b), a, b, tol=TOL_REDUCE, what=f"dot {m}x{k}x{n}")
+    a, b = r.randn(70, 90), r.randn(70, 50)
+    check(lambda a, b: onp.dot(a.T, b), a, b, tol=TOL_REDUCE, what="A^T B (weight grad)")
+    check(lambda a, b: onp.dot(b, b.T), a, b, tol=TOL_REDUCE, what="B B^T")
+    check(lambda a, b: onp.tensordot(a, b, [[0], [0]]), a, b, tol=TOL_REDUCE, what="tensordot axes0")
+    check(lambda a, b: onp.dot(a[:, ::2].T, b[:, 1::2]), a, b, tol=TOL_REDUCE, what="strided operands")
+    v = r.randn(90)
+    check(lambda a, v: (onp.dot(a, v), onp.dot(v, a.T)), a, v, tol=TOL_REDUCE, what="mat-vec / vec-mat")
+    x64, w32 = r.randn(40, 29), r.randn(29, 16).astype(onp.float32)
+    check(lambda x, w: onp.dot(x, w), x64, w32, tol=TOL_REDUCE, what="f64 @ f32 -> f64 (LSTM promotion)")
+    check(lambda x, w: onp.dot(x.astype(onp.float32), w), x64, w32, tol=TOL_F32, what="f32 @ f32")
+    t3, t4 = r.randn(4, 5, 6), r.randn(6, 5, 7)
+    check(lambda a, b: onp.tensordot(a, b, [[1, 2], [1, 0]]), t3, t4, tol=TOL_REDUCE, what="tensordot 2 axes")
+    check(lambda a, b: onp.tensordot(a, b, 1), t3, t4, tol=TOL_REDUCE, what="tensordot int axes")
+    check(lambda a, b: onp.dot(a, b), t3, t4[:, :, 0].T.copy()[:, :6].T if False else r.randn(6, 3), tol=TOL_REDUCE,
+          what="3-D dot 2-D")
+    b3a, b3b = r.randn(5, 8, 9), r.randn(5, 9, 4)
+    check(lambda a, b: onp.matmul(a, b), b3a, b3b, tol=TOL_REDUCE, what="batched matmul")
+    check(lambda a, b: a @ b[0], b3a, b3b, tol=TOL_REDUCE, what="matmul broadcast batch")
+    check(lambda a, b: (onp.inner(a, a), onp.outer(a[0], b[0])), r.randn(3, 4), r.randn(2, 5), tol=TOL_REDUCE,
+          what="inner/outer")
+
+
+def case_conv2d():
+    from autograd.scipy.signal import convolve
+
+    r = rs(16)
+    A, B = r.randn(5, 3, 12, 10), r.randn(3, 4, 5, 3)
+    for mode in ("valid", "full"):
+        check(lambda A, B: convolve(A, B, axes=([2, 3], [2, 3]), dot_axes=([1], [0]), mode=mode), A, B,
+              tol=TOL_REDUCE, what=f"convolve {mode}")
+
+
+# =============================================================== registries exposed to the test modules
+OP_CASES = {
+    "nan_inf": case_nan_inf_propagation,
+    "broadcasting": case_broadcasting,
+    "dtype_promotion": case_dtype_promotion,
+    "integer_semantics": case_integer_semantics,
+    "power_special": case_power_special_exponents,
+    "fused_chain": case_fused_chain_matches_unfused,
+    "vector_tail": case_large_vector_tail,
+    "views": case_views,
+    "roll": case_roll,
+    "concat_repeat_pad": case_concat_repeat_pad,
+    "indexing": case_indexing,
+    "reductions": case_reductions,
+    "big_reductions": case_big_reductions,
+    "logsumexp": case_logsumexp,
+    "gemm": case_gemm,
+    "conv2d": case_conv2d,
+}
+
+
+# =============================================================== autograd-level cases (grad through the device type)
+def _ref(fn, *args, **kw):
+    """Run `fn` on the reference path (autograd on NumPy) inside this process."""
+    with b200.host_arrays(), onp.errstate(all="ignore"):
+        return fn(*args, **kw)
+
+
+def check_grad(make_fn, host_args, tol, what, argnum=0):
+    """grad(f)(*args) on DeviceArrays vs the same call on ndarrays through unmodified autograd."""
+    from autograd import grad
+
+    want = _ref(grad(make_fn, argnum), *host_args)
+    got = to_host(grad(make_fn, argnum)(*to_dev(list(host_args))))
+    for i, (g, w) in enumerate(zip(leaves(got), leaves(want))):
+        assert_close(g, w, tol, f"{what} leaf {i}")
+
+
+def grad_case_mlp(batch=32, sizes=(20, 16, 12, 10)):
+    from examples import workloads as w
+
+    params, X, T = w.mlp_data(batch=batch, layer_sizes=sizes)
+    check_grad(w.mlp_objective, (params, X, T, 1.0), TOL_REDUCE, "C1 mlp")
+
+
+def grad_case_tanh(n=1001, max_order=4):
+    from examples import workloads as w
+
+    x = onp.linspace(-7, 7, n)
+    for order in range(max_order + 1):
+        f = w.tanh_nth_derivative(order)
+        want = _ref(f, x)
+        got = f(b200.asarray(x)).get()
+        assert_close(got, want, TOL_ELEMENTWISE, f"C2 tanh derivative order {order}")
+
+
+def grad_case_lstm(T=3, B=8, H=16, C=12):
+    from examples import workloads as w
+
+    params, X, Y = w.lstm_data(seq_len=T, batch=B, hidden=H, chars=C)
+    check_grad(w.lstm_objective, (params, X, Y), TOL_F32, "C3 lstm")
+    # the reference computes activations in float64 (NumPy promotion through np.ones, rnn.py:21) and
+    # hands float32 gradients back (numpy_vjps.py:624,638): dtype is part of the contract
+    from autograd import grad
+
+    g = grad(w.lstm_objective)(to_dev(params), b200.asarray(X), b200.asarray(Y))
+    assert all(v.dtype == onp.float32 for v in g.values())
+
+
+def grad_case_fluid(rows=16, cols=16, steps=2):
+    from autograd import value_and_grad
+
+    from examples import workloads as w
+
+    p, s0, tg = w.fluid_data(rows, cols)
+    vw, gw = _ref(value_and_grad(w.fluid_objective), p, s0, tg, rows, cols, steps)
+    vg, gg = value_and_grad(w.fluid_objective)(b200.asarray(p), b200.asarray(s0), b200.asarray(tg), rows, cols, steps)
+    assert_close(vg.get(), onp.asarray(vw), TOL_REDUCE, "C4 loss")
+    assert_close(gg.get(), gw, TOL_REDUCE, "C4 grad")
+    # forward smoke field must be bit-identical (every forward op is one correctly rounded IEEE op)
+    sw = _ref(w.fluid_simulate, p[: rows * cols].reshape(rows, cols), p[rows * cols:].reshape(rows, cols), s0, steps)
+    dp = b200.asarray(p)
+    sg = w.fluid_simulate(dp[: rows * cols].reshape(rows, cols), dp[rows * cols:].reshape(rows, cols),
+                          b200.asarray(s0), steps)
+    assert_close(sg.get(), sw, 0, "C4 forward bit-exact")
+
+
+def grad_case_convnet(batch=6):
+    from examples import workloads as w
+
+    n, _pred, loss = w.convnet_make()
+    W, X, T = w.convnet_data(batch, n)
+    check_grad(loss, (W, X, T), TOL_REDUCE, "C5 convnet")
+
+
+def grad_case_operators():
+    """make_vjp / jacobian / value_and_grad / elementwise_grad / nesting on small functions
+    (mirrors reference tests/test_wrappers.py, tests/test_jacobian.py)."""
+    import autograd.numpy as np
+    from autograd import elementwise_grad, grad, jacobian, make_vjp, value_and_grad
+
+    r = rs(20)
+    x = r.randn(7)
+    A = r.randn(5, 7)
+
+    f = lambda x: np.sum(np.sin(x) * x ** 2) + np.dot(x, x)
+    check_grad(f, (x,), TOL_REDUCE, "grad sin*x^2")
+    want = _ref(grad(grad(f)), x) if False else None  # grad of non-scalar is invalid; use hessian-vector below
+    hv = lambda x, v: np.dot(grad(f)(x), v)
+    v = r.randn(7)
+    check_grad(hv, (x, v), TOL_REDUCE, "hessian-vector product (nested grad)")
+
+    g = lambda x: np.tanh(np.dot(A_, x))
+    for A_ in (A,):
+        want = _ref(jacobian(lambda x: np.tanh(np.dot(A_, x))), x)
+        Ad = b200.asarray(A_)
+        got = jacobian(lambda x: np.tanh(np.dot(Ad, x)))(b200.asarray(x)).get()
+        assert_close(got, want, TOL_REDUCE, "jacobian")
+
+    vw, gw = _ref(value_and_grad(f), x)
+    vg, gg = value_and_grad(f)(b200.asarray(x))
+    assert_close(vg.get(), onp.asarray(vw), TOL_REDUCE, "value_and_grad value")
+    assert_close(gg.get(), gw, TOL_REDUCE, "value_and_grad grad")
+
+    vjp_w, ans_w = _ref(make_vjp(lambda x: np.exp(x) / (1 + x ** 2)), x)
+    vjp_g, ans_g = make_vjp(lambda x: np.exp(x) / (1 + x ** 2))(b200.asarray(x))
+    assert_close(ans_g.get(), ans_w, TOL_ELEMENTWISE, "make_vjp value")
+    assert_close(vjp_g(b200.asarray(v)).get(), _ref(vjp_w, v), TOL_ELEMENTWISE, "make_vjp cotangent")
+
+    h = lambda x: np.log1p(x ** 2) * np.cos(x)
+    e3 = elementwise_grad(elementwise_grad(elementwise_grad(h)))
+    assert_close(e3(b200.asarray(x)).get(), _ref(e3, x), 1e-11, "3x nested elementwise_grad")
+
+
+def grad_case_vjp_rules():
+    """VJPs of the op families on the hot path vs the reference rules (numpy_vjps.py) on NumPy."""
+    import autograd.numpy as np
+
+    r = rs(21)
+    a, b, c = r.randn(6, 5), r.randn(5), r.randn(6, 1)
+    pos = onp.abs(r.randn(6, 5)) + 0.5
+    fns = {
+        "broadcast add/mul": (lambda a, b, c: np.sum((a + b) * c - a / (b * b + 1.0)), (a, b, c)),
+        "power": (lambda p, b: np.sum(p ** b + p ** 2.0 + 2.0 ** p), (pos, b)),
+        "unary chain": (lambda a: np.sum(np.exp(np.tanh(a)) + np.log(a * a + 1) - np.sqrt(a * a + 2) + np.abs(a)), (a,)),
+        "maximum/minimum": (lambda a, c: np.sum(np.maximum(a, c) * np.minimum(a, 0.1)), (a, c)),
+        "sum axis": (lambda a: np.sum(np.sum(a, axis=0) ** 2), (a,)),
+        "mean keepdims": (lambda a: np.sum((a - np.mean(a, axis=1, keepdims=True)) ** 2), (a,)),
+        "max": (lambda a: np.sum(np.max(a, axis=1) * np.array([1., 2., 3., 4., 5., 6.])), (a,)),
+        "max ties": (lambda a: np.max(np.round(a)), (a,)),
+        "roll": (lambda a: np.sum(np.roll(a, 1, axis=0) * a + np.roll(a, -2, axis=1) ** 2), (a,)),
+        "reshape/transpose": (lambda a: np.sum(np.reshape(a.T, (6, 5)) * a), (a,)),
+        "concatenate": (lambda a, c: np.sum(np.concatenate([a, c], axis=1) ** 2 * np.arange(6.0)), (a, c)),
+        "getitem slice": (lambda a: np.sum(a[1:4, ::2] ** 2) + np.sum(a[2]), (a,)),
+        "getitem fancy": (lambda a: np.sum(a[onp.array([0, 0, 3, 5]), onp.array([1, 1, 2, 4])] ** 2), (a,)),
+        "where": (lambda a: np.sum(np.where(a > 0, a * a, -a)), (a,)),
+        "dot": (lambda a, b: np.sum(np.dot(a, b) ** 2), (a, b)),
+        "dot T": (lambda a: np.sum(np.dot(a.T, a)), (a,)),
+        "tensordot": (lambda a: np.sum(np.tensordot(a, a, [[0], [0]]) ** 2), (a,)),
+        "matmul": (lambda a: np.sum((a @ a.T) ** 2), (a,)),
+        "repeat": (lambda c: np.sum(np.repeat(c, 4, axis=1) * np.arange(4.0)), (c,)),
+        "astype f32": (lambda a: np.sum(a.astype(onp.float32) ** 2), (a,)),
+        "var/std": (lambda a: np.sum(np.var(a, axis=0)) + np.sum(np.std(a, axis=1)), (a,)),
+    }
+    for name, (fn, args) in fns.items():
+        for argnum in range(len(args)):
+            check_grad(fn, args, TOL_REDUCE, f"vjp {name} arg{argnum}", argnum)
+
+
+def grad_case_check_grads():
+    """The reference's own finite-difference checker (autograd/test_util.py:60-78) driven through the
+    device VSpace: modes rev+fwd, order 2."""
+    import autograd.numpy as np
+    from autograd.test_util import check_grads
+
+    r = rs(22)
+    x = b200.asarray(r.randn(4, 3))
+    y = b200.asarray(r.randn(3))
+    check_grads(lambda x: np.tanh(x) * x, modes=["rev"], order=2)(x)
+    check_grads(lambda x, y: np.sum(np.dot(x, y) ** 2) + np.sum(x * y), modes=["rev"], order=2)(x, y)
+    check_grads(lambda x: np.sum(x, axis=0) / (1 + np.max(x, axis=0) ** 2), modes=["rev"], order=2)(x)
+    check_grads(lambda x: np.roll(x, 1, axis=0) * x, modes=["rev", "fwd"], order=2)(x)
+    check_grads(lambda x: np.exp(x) / (1.0 + np.exp(x)), modes=["fwd"], order=2)(x)
+
+
+def grad_case_vspace_axioms():
+    """VSpace contract of reference tests/test_vspaces.py:10-131 on DeviceVSpace."""
+    from autograd.extend import vspace
+
+    r = rs(23)
+    x = b200.asarray(r.randn(3, 2))
+    vs = vspace(x)
+    assert vs.size == 6 and vs.shape == (3, 2) and vs.dtype == onp.float64 and vs.ndim == 2
+    assert vs == vspace(b200.asarray(r.randn(3, 2)))
+    y, z = vs.randn(), vs.randn()
+    assert vspace(y) == vs and vspace(vs.zeros()) == vs and vspace(vs.ones()) == vs
+    assert_close(vs.add(y, z).get(), y.get() + z.get(), 0, "add")
+    assert_close(vs.scalar_mul(y, 2.5).get(), y.get() * 2.5, 0, "scalar_mul")
+    ip = float(vs.inner_prod(y, z))
+    assert abs(ip - float(onp.sum(y.get() * z.get()))) < 1e-12
+    assert abs(ip - float(vs.inner_prod(z, y))) < 1e-12
+    basis = list(vs.standard_basis())
+    assert len(basis) == vs.size
+    for i, bi in enumerate(basis):
+        for j, bj in enumerate(basis):
+            assert float(vs.inner_prod(bi, bj)) == (1.0 if i == j else 0.0)
+    acc = vs.zeros()
+    acc = vs.mut_add(acc, y)
+    acc = vs.mut_add(acc, z)
+    assert_close(acc.get(), y.get() + z.get(), 0, "mut_add")
+
+
+GRAD_CASES = {
+    "c1_mlp": grad_case_mlp,
+    "c2_tanh": grad_case_tanh,
+    "c3_lstm": grad_case_lstm,
+    "c4_fluid": grad_case_fluid,
+    "c5_convnet": grad_case_convnet,
+    "operators": grad_case_operators,
+    "vjp_rules": grad_case_vjp_rules,
+    "check_grads": grad_case_check_grads,
+    "vspace_axioms": grad_case_vspace_axioms,
+}
