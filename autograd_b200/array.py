@@ -99,10 +99,13 @@ class DeviceArray:
         self._mat()
         return self
 
-    def get(self) -> np.ndarray:
-        """Copy to host as a numpy.ndarray (synchronises)."""
+    def get(self, out=None) -> np.ndarray:
+        """Copy to host as a numpy.ndarray (synchronises).  ``out`` may be a preallocated (e.g. pinned) array."""
         m = self._cmat()
-        out = np.empty(m.shape, dtype=m.dtype)
+        if out is None:
+            out = np.empty(m.shape, dtype=m.dtype)
+        elif out.shape != m.shape or out.dtype != m.dtype or not out.flags.c_contiguous:
+            raise ValueError("get(out=...): out must be a C-contiguous array of the same shape and dtype")
         backend.get().d2h(out, m.ptr)
         return out
 
@@ -458,6 +461,36 @@ def asarray(x, dtype=None) -> DeviceArray:
 
 array = asarray
 to_device = asarray
+
+
+def pinned_empty(shape, dtype=float) -> np.ndarray:
+    """A numpy array backed by page-locked host memory (full-rate, truly asynchronous H2D/D2H copies)."""
+    import ctypes
+
+    shape = _shape_tuple(shape)
+    dtype = np.dtype(dtype)
+    nbytes = max(prod(shape) * dtype.itemsize, 1)
+    be = backend.get()
+    ptr = be.host_alloc(nbytes)
+    buf = (ctypes.c_char * nbytes).from_address(ptr)
+    arr = np.frombuffer(buf, dtype=dtype, count=prod(shape)).reshape(shape)
+    _PINNED[id(buf)] = (buf, ptr)
+    import weakref
+
+    weakref.finalize(arr.base if arr.base is not None else arr, _release_pinned, id(buf), be)
+    return arr
+
+
+_PINNED = {}
+
+
+def _release_pinned(key, be):
+    rec = _PINNED.pop(key, None)
+    if rec is not None:
+        try:
+            be.host_free(rec[1])
+        except Exception:
+            pass
 
 
 def _shape_tuple(shape):

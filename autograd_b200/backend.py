@@ -53,6 +53,7 @@ class CudaBackend:
         self.device = device
         self._check(self._lib.b200ag_init(device))
         self._kernels = {}  # Program.key -> compiled kernel record
+        self.profile = None  # set to a list to collect (program, n, start_event, stop_event) per fused launch
         sms, major, minor, mem = C.c_int(), C.c_int(), C.c_int(), C.c_size_t()
         self._check(self._lib.b200ag_device_info(C.byref(sms), C.byref(major), C.byref(minor), C.byref(mem)))
         self.sm_count = sms.value
@@ -182,7 +183,14 @@ class CudaBackend:
             return
         params = packer(n, leaf_ptrs, const_values, out_ptrs, program)
         grid = min((n + elems_per_block - 1) // elems_per_block, max_grid)
-        self._check(self._lib.b200ag_kernel_launch(handle, grid, block, 0, params, len(params)))
+        if self.profile is None:
+            self._check(self._lib.b200ag_kernel_launch(handle, grid, block, 0, params, len(params)))
+        else:
+            e0, e1 = self.event_create(), self.event_create()
+            self.event_record(e0)
+            self._check(self._lib.b200ag_kernel_launch(handle, grid, block, 0, params, len(params)))
+            self.event_record(e1)
+            self.profile.append((program, n, e0, e1))
 
     # ------------------------------------------------------------ static kernels
     def copy_strided(self, dst, dst_dt, dst_strides, src, src_dt, src_strides, shape) -> None:
