@@ -268,11 +268,12 @@ def run_b200(args):
     cpu = {"value": cpu_value, "unit": UNIT, "cores": 1, "kind": "reference", "sample": sample,
            "host_cpu_count": os.cpu_count()}
 
-    # parity spot check on the bench inputs themselves (first 2^16 points of the resident vector)
-    k = min(n, 1 << 16)
-    got = f(x[:k]).get()
+    # parity spot check on the bench inputs themselves: 2^16 points strided across the whole resident vector,
+    # error relative to the max-norm of the reference result (the derivative crosses zero)
+    stride = max(1, n >> 16)
+    got = f(x[::stride]).get()
     with b200.host_arrays():
-        want = f(x_host[:k].copy())
+        want = f(x_host[::stride].copy())
     err = float(onp.max(onp.abs(got - want)) / onp.max(onp.abs(want)))
 
     line = {
