@@ -1,0 +1,142 @@
+"""Generate tests/golden/*.npz from the REAL reference: /root/reference/autograd + /root/reference/examples.
+
+TEST INFRASTRUCTURE (oracle).  Run in the authoring container only (where /root/reference is mounted):
+
+    python oracle/make_golden.py
+
+The example scripts are imported unmodified; because they import matplotlib / download MNIST at module
+level, `matplotlib*` and `data_mnist` are stubbed in sys.modules first.  Inputs are
+seeded exactly like examples/workloads.py builds them, so the fixtures pin (a) that our restated workload
+functions compute the same thing as the reference's example code, bit for bit, on NumPy, and (b) golden
+outputs the GPU path is compared against on the GPU box, where /root/reference does not exist.
+"""
+
+from __future__ import annotations
+
+import os
+import sys
+import types
+
+REFERENCE = "/root/reference"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+class _Stub(types.ModuleType):
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        child = _Stub(f"{self.__name__}.{name}")
+        setattr(self, name, child)
+        return child
+
+    def __call__(self, *a, **k):
+        return _Stub("call")
+
+    def __iter__(self):
+        return iter(())
+
+
+def _install_stubs():
+    for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.image", "matplotlib.cm", "data_mnist"):
+        sys.modules[name] = _Stub(name)
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    sys.modules["matplotlib"].image = sys.modules["matplotlib.image"]
+
+
+def main():
+    if not os.path.isdir(REFERENCE):
+        print("make_golden: /root/reference is not mounted; keeping the committed fixtures")
+        return 0
+    sys.path[:0] = [REFERENCE, os.path.join(REFERENCE, "examples"), os.path.join(REFERENCE, "examples", "fluidsim"), ROOT]
+    _install_stubs()
+    import numpy as onp
+
+    import autograd.numpy as np  # noqa: F401
+    from autograd import elementwise_grad as egrad
+    from autograd import grad, value_and_grad
+
+    assert os.path.realpath(sys.modules["autograd"].__file__).startswith(REFERENCE)
+    os.makedirs(OUT, exist_ok=True)
+
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("b200_workloads", os.path.join(ROOT, "examples", "workloads.py"))
+    w = importlib.util.module_from_spec(spec)  # only for the seeded input builders
+    spec.loader.exec_module(w)
+
+    # ---------------- C1 neural_net.py
+    import neural_net
+
+    def c1(batch, sizes):
+        params, X, T = w.mlp_data(batch=batch, layer_sizes=sizes)
+        ref_params = neural_net.init_random_params(0.1, list(sizes), onp.random.RandomState(0))
+        for (a, b), (c, d) in zip(params, ref_params):
+            assert onp.array_equal(a, c) and onp.array_equal(b, d)
+        g = grad(lambda p: -neural_net.log_posterior(p, X, T, 1.0))(ref_params)
+        val = -neural_net.log_posterior(ref_params, X, T, 1.0)
+        return val, g
+
+    val, g = c1(32, (20, 16, 12, 10))
+    onp.savez(os.path.join(OUT, "c1_mlp_small.npz"), value=val, **{f"g{i}_{j}": a for i, wb in enumerate(g) for j, a in enumerate(wb)})
+    val, g = c1(256, (784, 200, 100, 10))
+    flat = onp.concatenate([a.ravel() for wb in g for a in wb])
+    onp.savez(os.path.join(OUT, "c1_mlp_full_summary.npz"), value=val, n=flat.size, sum=flat.sum(), sumsq=(flat * flat).sum(),
+              sample=flat[::997].copy())
+
+    # ---------------- C2 tanh.py (module executes its plotting code against the stubs)
+    import tanh as tanh_example
+
+    x = onp.linspace(-7, 7, 4001)
+    f = tanh_example.tanh
+    outs = {}
+    for order in range(5):
+        outs[f"d{order}"] = f(x)
+        f = egrad(f)
+    onp.savez(os.path.join(OUT, "c2_tanh.npz"), x=x, **outs)
+
+    # ---------------- C3 lstm.py
+    import lstm as lstm_example
+
+    params, X, Y = w.lstm_data(seq_len=3, batch=8, hidden=16, chars=12)
+    ref = lstm_example.init_lstm_params(12, 16, 12, param_scale=0.01, rs=onp.random.RandomState(0))
+    # workloads.lstm_data draws params first, then the inputs, from ONE RandomState(0) stream
+    for k in ref:
+        assert onp.array_equal(ref[k].astype(onp.float32), params[k]), k
+    g = grad(lambda p: -lstm_example.lstm_log_likelihood(p, X, Y))(params)
+    val = -lstm_example.lstm_log_likelihood(params, X, Y)
+    onp.savez(os.path.join(OUT, "c3_lstm_small.npz"), value=val, **{k.replace(" ", "_"): v for k, v in g.items()})
+
+    # ---------------- C4 fluidsim.py
+    import fluidsim as fluid_example
+
+    fluid_example.print = lambda *a, **k: None
+    rows = cols = 16
+    p, s0, tg = w.fluid_data(rows, cols)
+
+    def objective(params):
+        vx = np.reshape(params[: rows * cols], (rows, cols))
+        vy = np.reshape(params[rows * cols:], (rows, cols))
+        final = fluid_example.simulate(vx, vy, s0, 2)
+        return np.mean((tg - final) ** 2)
+
+    val, g = value_and_grad(objective)(p)
+    smoke = fluid_example.simulate(p[: rows * cols].reshape(rows, cols), p[rows * cols:].reshape(rows, cols), s0, 2)
+    onp.savez(os.path.join(OUT, "c4_fluid_small.npz"), value=val, grad=g, smoke=smoke)
+
+    # ---------------- C5 convnet.py
+    import convnet as conv_example
+
+    layer_specs = [conv_example.conv_layer((5, 5), 6), conv_example.maxpool_layer((2, 2)),
+                   conv_example.conv_layer((5, 5), 16), conv_example.maxpool_layer((2, 2)),
+                   conv_example.tanh_layer(120), conv_example.tanh_layer(84), conv_example.softmax_layer(10)]
+    N, pred, loss, _ = conv_example.make_nn_funs((1, 28, 28), layer_specs, 1.0)
+    W, X, T = w.convnet_data(6, N)
+    g = grad(loss)(W, X, T)
+    onp.savez(os.path.join(OUT, "c5_convnet_small.npz"), n_weights=N, value=loss(W, X, T), grad=g)
+    print("make_golden: wrote", sorted(os.listdir(OUT)))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,99 @@
+"""Golden vectors generated from the REAL reference examples (oracle/make_golden.py, run where
+/root/reference is mounted).
+
+* CPU (`-m "not gpu"`): the restated workloads in examples/workloads.py, run through unmodified
+  autograd on NumPy, reproduce the golden outputs BIT FOR BIT — this pins the oracle used everywhere
+  else (reference autograd on NumPy + these workload functions) to the reference's own example code.
+* GPU (`-m gpu`): the device path reproduces the same golden outputs within the north_star tolerances.
+"""
+
+import os
+
+import numpy as onp
+import pytest
+
+import cases
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _load(name):
+    return onp.load(os.path.join(GOLD, name))
+
+
+def _run_all(asarray, getter, exact):
+    """Evaluate every golden case; `asarray` lifts host inputs, `getter` lowers results."""
+    import autograd_b200 as b200
+    from autograd import grad, value_and_grad
+
+    from examples import workloads as w
+
+    tol_e = 0 if exact else cases.TOL_ELEMENTWISE
+    tol_r = 0 if exact else cases.TOL_REDUCE
+    tol_f = 0 if exact else cases.TOL_F32
+    lift = lambda t: cases.to_dev(t) if asarray else t
+
+    # C1 small + full-size summary
+    gold = _load("c1_mlp_small.npz")
+    params, X, T = w.mlp_data(batch=32, layer_sizes=(20, 16, 12, 10))
+    g = getter(grad(w.mlp_objective)(lift(params), lift(X), lift(T), 1.0))
+    for i, wb in enumerate(g):
+        for j, a in enumerate(wb):
+            cases.assert_close(a, gold[f"g{i}_{j}"], tol_r, f"C1 g{i}_{j}")
+    gold = _load("c1_mlp_full_summary.npz")
+    params, X, T = w.mlp_data()
+    val, g = value_and_grad(w.mlp_objective)(lift(params), lift(X), lift(T), 1.0)
+    flat = onp.concatenate([onp.asarray(a).ravel() for wb in getter(g) for a in wb])
+    assert flat.size == int(gold["n"])
+    cases.assert_close(flat[::997], gold["sample"], tol_r, "C1 full-size gradient sample")
+    assert abs(flat.sum() - float(gold["sum"])) <= max(tol_r, 1e-15) * onp.abs(flat).sum()
+    assert abs((flat * flat).sum() - float(gold["sumsq"])) <= max(tol_r, 1e-15) * float(gold["sumsq"])
+    assert abs(float(getter(val)) - float(gold["value"])) <= max(tol_r, 1e-15) * abs(float(gold["value"]))
+
+    # C2 orders 0..4
+    gold = _load("c2_tanh.npz")
+    x = gold["x"]
+    for order in range(5):
+        f = w.tanh_nth_derivative(order)
+        cases.assert_close(getter(f(lift(x))), gold[f"d{order}"], tol_e, f"C2 order {order}")
+
+    # C3
+    gold = _load("c3_lstm_small.npz")
+    params, X, Y = w.lstm_data(seq_len=3, batch=8, hidden=16, chars=12)
+    g = getter(grad(w.lstm_objective)(lift(params), lift(X), lift(Y)))
+    for k, v in g.items():
+        cases.assert_close(v, gold[k.replace(" ", "_")], tol_f, f"C3 {k}")
+
+    # C4: gradient within tolerance, forward smoke field bit-exact even on the device
+    gold = _load("c4_fluid_small.npz")
+    rows = cols = 16
+    p, s0, tg = w.fluid_data(rows, cols)
+    val, g = value_and_grad(w.fluid_objective)(lift(p), lift(s0), lift(tg), rows, cols, 2)
+    cases.assert_close(getter(g), gold["grad"], tol_r, "C4 grad")
+    cases.assert_close(onp.asarray(getter(val)), gold["value"], tol_r, "C4 value")
+    dp = lift(p)
+    smoke = w.fluid_simulate(dp[: rows * cols].reshape(rows, cols), dp[rows * cols:].reshape(rows, cols), lift(s0), 2)
+    cases.assert_close(getter(smoke), gold["smoke"], 0, "C4 forward bit-exact")
+
+    # C5
+    gold = _load("c5_convnet_small.npz")
+    n, _pred, loss = w.convnet_make()
+    assert n == int(gold["n_weights"])
+    W, X, T = w.convnet_data(6, n)
+    cases.assert_close(getter(grad(loss)(lift(W), lift(X), lift(T))), gold["grad"], tol_r, "C5 grad")
+
+
+def test_oracle_restated_workloads_match_reference_examples_bit_for_bit(fake_dev):
+    import autograd_b200 as b200
+
+    with b200.host_arrays(), onp.errstate(all="ignore"):
+        _run_all(False, lambda t: t, exact=True)
+
+
+def test_host_logic_matches_golden(fake_dev):
+    _run_all(True, cases.to_host, exact=False)
+
+
+@pytest.mark.gpu
+def test_device_matches_golden(cuda_dev):
+    _run_all(True, cases.to_host, exact=False)
