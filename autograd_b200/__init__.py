@@ -14,6 +14,7 @@ without the built library raises.
 
 from . import array, backend, lazy
 from .array import DeviceArray, asarray, to_device
+from .graph import capture
 from .install import host_arrays, install, is_installed
 
 
@@ -25,5 +26,5 @@ def to_host(x):
     return x.get() if isinstance(x, DeviceArray) else x
 
 
-__all__ = ["host_arrays", "DeviceArray", "asarray", "to_device", "to_host", "install", "is_installed", "synchronize", "array",
+__all__ = ["capture", "host_arrays", "DeviceArray", "asarray", "to_device", "to_host", "install", "is_installed", "synchronize", "array",
            "backend", "lazy"]

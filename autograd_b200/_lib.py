@@ -28,6 +28,7 @@ PROTOTYPES = {
     "b200ag_synchronize": [],
     "b200ag_launch_count": [C.POINTER(C.c_uint64)],
     "b200ag_malloc": [C.c_size_t, c_void_pp],
+    "b200ag_malloc_upload": [C.c_size_t, c_void_pp],
     "b200ag_free": [C.c_void_p],
     "b200ag_empty_cache": [],
     "b200ag_mem_stats": [c_size_p, c_size_p, c_size_p],

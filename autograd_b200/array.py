@@ -443,7 +443,7 @@ def _upload(host: np.ndarray) -> DeviceArray:
         else:
             backend.dtype_code(host.dtype)
     host = np.ascontiguousarray(host)
-    m = Mat.empty(host.shape, host.dtype)
+    m = Mat.empty(host.shape, host.dtype, upload=True)
     if host.size:
         backend.get().h2d(m.ptr, host)
     return DeviceArray(lazy.leaf(m))

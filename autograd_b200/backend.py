@@ -65,6 +65,11 @@ class CudaBackend:
         self._check(self._lib.b200ag_malloc(nbytes, C.byref(p)))
         return p.value or 0
 
+    def malloc_upload(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        self._check(self._lib.b200ag_malloc_upload(nbytes, C.byref(p)))
+        return p.value or 0
+
     def free(self, ptr: int) -> None:
         self._lib.b200ag_free(ptr)
 

@@ -7,6 +7,7 @@
 #include <map>
 #include <mutex>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 #include "common.cuh"
@@ -16,6 +17,8 @@ namespace b200ag {
 static thread_local std::string g_error;
 static std::string g_rtc_log;
 static cudaStream_t g_stream = nullptr;
+static cudaStream_t g_side_stream = nullptr;  // uploads issued while g_stream is being captured
+static bool g_capturing = false;
 static int g_device = -1;
 static int g_sm_count = 148;
 static std::atomic<uint64_t> g_launches{0};
@@ -47,6 +50,7 @@ static Arena g_main_arena;
 static Arena* g_capture_arena = nullptr;
 static std::unordered_map<void*, std::pair<size_t, Arena*>> g_live;  // ptr -> (binned size, arena)
 static size_t g_in_use = 0, g_cached = 0, g_peak = 0;
+static std::unordered_set<void*> g_norecycle;  // graph constants: never handed out again while the graph lives
 
 static size_t bin_size(size_t n) {
   if (n == 0) n = 1;
@@ -86,6 +90,7 @@ int b200ag_init(int device) {
   if (prop.major < 10) B200AG_FAIL("b200ag_init: this library is built for sm_100a (B200) only");
   g_sm_count = prop.multiProcessorCount;
   B200AG_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+  B200AG_CUDA(cudaStreamCreateWithFlags(&g_side_stream, cudaStreamNonBlocking));
   g_device = device;
   return 0;
 }
@@ -124,6 +129,7 @@ int b200ag_stream(void** s) {
 
 int b200ag_synchronize(void) {
   B200AG_CHECK_INIT();
+  if (g_capturing) B200AG_FAIL("synchronize() while a CUDA graph is being captured");
   B200AG_CUDA(cudaStreamSynchronize(g_stream));
   return 0;
 }
@@ -150,7 +156,7 @@ int b200ag_malloc(size_t nbytes, void** ptr) {
     if (e != cudaSuccess) {
       cudaGetLastError();
       // give cached blocks back to the driver and retry once
-      cudaStreamSynchronize(g_stream);
+      if (!g_capturing) cudaStreamSynchronize(g_stream);
       release_bins(g_main_arena);
       e = cudaMalloc(&p, sz);
       if (e != cudaSuccess) {
@@ -169,6 +175,26 @@ int b200ag_malloc(size_t nbytes, void** ptr) {
   return 0;
 }
 
+// Destination of a host upload.  Outside a capture this is a plain malloc.  While a graph is being
+// captured the upload happens once, at capture time (b200ag_memcpy_h2d), so the block holds a CONSTANT of
+// the graph: it must be a block no captured kernel has written or will ever write, i.e. it is allocated
+// fresh and never goes back to the arena's free bins.
+int b200ag_malloc_upload(size_t nbytes, void** ptr) {
+  B200AG_CHECK_INIT();
+  if (!g_capturing) return b200ag_malloc(nbytes, ptr);
+  size_t sz = bin_size(nbytes);
+  void* p = nullptr;
+  B200AG_CUDA(cudaMalloc(&p, sz));
+  std::lock_guard<std::mutex> lock(g_mem_mutex);
+  g_capture_arena->owned.push_back(p);
+  g_live[p] = {sz, g_capture_arena};
+  g_norecycle.insert(p);
+  g_in_use += sz;
+  if (g_in_use > g_peak) g_peak = g_in_use;
+  *ptr = p;
+  return 0;
+}
+
 int b200ag_free(void* ptr) {
   if (!ptr) return 0;
   std::lock_guard<std::mutex> lock(g_mem_mutex);
@@ -178,6 +204,13 @@ int b200ag_free(void* ptr) {
   Arena* arena = it->second.second;
   g_live.erase(it);
   g_in_use -= sz;
+  if (g_norecycle.count(ptr)) {
+    if (arena == nullptr) {  // its graph is gone: release now
+      g_norecycle.erase(ptr);
+      cudaFree(ptr);
+    }
+    return 0;  // otherwise the block stays reserved until the owning graph is destroyed
+  }
   if (arena == nullptr) {  // block outlived the graph whose arena owned it
     cudaFree(ptr);
     return 0;
@@ -218,12 +251,22 @@ int b200ag_host_free(void* ptr) {
 int b200ag_memcpy_h2d(void* dst, const void* src, size_t nbytes) {
   B200AG_CHECK_INIT();
   if (!nbytes) return 0;
+  if (g_capturing) {
+    // A host pointer must not be baked into a graph (the ndarray is gone at replay time): upload now,
+    // on a side stream, into the graph-owned block; the data is then a constant of the graph.
+    B200AG_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyHostToDevice, g_side_stream));
+    B200AG_CUDA(cudaStreamSynchronize(g_side_stream));
+    return 0;
+  }
   B200AG_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyHostToDevice, g_stream));
   return 0;
 }
 
 int b200ag_memcpy_d2h(void* dst, const void* src, size_t nbytes) {
   B200AG_CHECK_INIT();
+  if (g_capturing)
+    B200AG_FAIL("device->host read while a CUDA graph is being captured: the traced function depends on array "
+                "VALUES (float(x), bool(x), .get()); such functions cannot be replayed as a graph");
   if (nbytes) B200AG_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToHost, g_stream));
   B200AG_CUDA(cudaStreamSynchronize(g_stream));
   return 0;
@@ -351,10 +394,13 @@ int b200ag_graph_begin(void) {
     g_capture_arena = nullptr;
     B200AG_FAIL(std::string("cudaStreamBeginCapture: ") + cudaGetErrorString(e));
   }
+  g_capturing = true;
   return 0;
 }
 
 int b200ag_graph_end(void** out) {
+  if (!g_capturing) B200AG_FAIL("b200ag_graph_end: no capture in progress");
+  g_capturing = false;
   Graph* g = new Graph();
   cudaError_t e = cudaStreamEndCapture(g_stream, &g->graph);
   {
@@ -410,7 +456,10 @@ int b200ag_graph_destroy(void* graph) {
       }
     for (auto& kv : g->arena->free_bins) g_cached -= kv.first * kv.second.size();
     for (void* p : g->arena->owned)
-      if (!live_in_arena.count(p)) cudaFree(p);
+      if (!live_in_arena.count(p)) {
+        g_norecycle.erase(p);
+        cudaFree(p);
+      }
     delete g->arena;
   }
   delete g;

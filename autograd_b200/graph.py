@@ -1,0 +1,148 @@
+"""Tape replay as a CUDA graph.
+
+autograd re-traces the user function on every ``grad(f)(x)`` call: a Python loop over the tape
+(``backward_pass``, autograd/core.py:26-33; 64 / 10,252 / 35,003 nodes for BASELINE configs C1 / C3 / C4).
+Once the kernels are on the GPU that loop *is* the run time.  ``capture(fn)`` runs the traced call once
+under CUDA stream capture — every kernel the tape launches, fused elementwise programs, GEMMs, reductions,
+gathers and scatter-adds alike, becomes a graph node — and afterwards replays the recorded forward+backward
+tape with one ``cudaGraphLaunch``: no Python per op, no per-kernel launch latency.
+
+Validity is the usual one for traced programs: the recorded tape must not depend on array *values*
+(a device→host read during capture raises) and is keyed on the argument structure, shapes and dtypes;
+a call with a new signature is captured afresh.  Python scalars are constants of the recording and are
+part of the key.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from . import backend, lazy
+from .array import DeviceArray, asarray
+
+
+def _flatten(tree, leaves, spec):
+    if isinstance(tree, DeviceArray) or isinstance(tree, np.ndarray):
+        spec.append(("a", tuple(tree.shape), np.dtype(tree.dtype).char))
+        leaves.append(tree)
+    elif isinstance(tree, (list, tuple)):
+        spec.append(("seq", type(tree).__name__, len(tree)))
+        for t in tree:
+            _flatten(t, leaves, spec)
+    elif isinstance(tree, dict):
+        keys = sorted(tree)
+        spec.append(("dict", tuple(keys)))
+        for k in keys:
+            _flatten(tree[k], leaves, spec)
+    else:
+        spec.append(("const", type(tree).__name__, tree if isinstance(tree, (int, float, bool, str, type(None))) else id(tree)))
+
+
+def _rebuild(tree, it):
+    if isinstance(tree, DeviceArray) or isinstance(tree, np.ndarray):
+        return next(it)
+    if isinstance(tree, (list, tuple)):
+        return type(tree)(_rebuild(t, it) for t in tree)
+    if isinstance(tree, dict):
+        return {k: _rebuild(tree[k], it) for k in sorted(tree)}
+    return tree
+
+
+def _out_leaves(tree, acc):
+    if isinstance(tree, DeviceArray):
+        acc.append(tree)
+    elif isinstance(tree, (list, tuple)):
+        for t in tree:
+            _out_leaves(t, acc)
+    elif isinstance(tree, dict):
+        for k in sorted(tree):
+            _out_leaves(tree[k], acc)
+
+
+class _Recording:
+    __slots__ = ("graph", "static_inputs", "outputs", "nodes", "__weakref__")
+
+    def __init__(self, graph, static_inputs, outputs, nodes):
+        self.graph, self.static_inputs, self.outputs, self.nodes = graph, static_inputs, outputs, nodes
+
+    def __del__(self):
+        try:
+            backend.get().graph_destroy(self.graph)
+        except Exception:
+            pass
+
+
+class CapturedFunction:
+    """``fn`` replayed as a CUDA graph.  Returned arrays are owned by the recording and are overwritten by
+    the next call with the same signature (copy them if they must survive)."""
+
+    def __init__(self, fn):
+        self.fn = fn
+        self._recordings = {}
+
+    def __call__(self, *args):
+        be = backend.get()
+        leaves, spec = [], []
+        _flatten(args, leaves, spec)
+        key = tuple(spec)
+        rec = self._recordings.get(key)
+        if rec is None:
+            rec = self._record(be, args, leaves)
+            self._recordings[key] = rec
+        else:
+            for dst, src in zip(rec.static_inputs, leaves):
+                self._refresh(be, dst, src)
+        be.graph_launch(rec.graph)
+        return rec.outputs
+
+    @staticmethod
+    def _refresh(be, dst: DeviceArray, src):
+        dm = dst._node.mat
+        if isinstance(src, DeviceArray):
+            sm = src._cmat()
+            if sm.ptr != dm.ptr:
+                be.d2d(dm.ptr, sm.ptr, src.nbytes)
+        else:
+            be.h2d(dm.ptr, np.ascontiguousarray(src, dtype=dm.dtype))
+
+    def _record(self, be, args, leaves):
+        # 1. eager warm-up: compiles/loads every kernel the tape needs, sizes the caches
+        out = self.fn(*args)
+        acc = []
+        _out_leaves(out, acc)
+        for a in acc:
+            a.materialize()
+        be.synchronize()
+        del out, acc
+        # 2. private copies of the inputs: their addresses are what the graph bakes in
+        static = []
+        for leaf in leaves:
+            d = asarray(leaf)
+            static.append(d.copy() if isinstance(leaf, DeviceArray) else d)
+        be.synchronize()
+        static_args = _rebuild(args, iter(static))
+        # 3. capture the same call
+        be.graph_begin()
+        try:
+            out = self.fn(*static_args)
+            acc = []
+            _out_leaves(out, acc)
+            for a in acc:
+                a.materialize()
+        except BaseException:
+            try:
+                g = be.graph_end()
+                be.graph_destroy(g)
+            except Exception:
+                pass
+            raise
+        graph = be.graph_end()
+        return _Recording(graph, static, out, be.graph_num_nodes(graph))
+
+    def num_nodes(self):
+        return {k: r.nodes for k, r in self._recordings.items()}
+
+
+def capture(fn):
+    """Wrap ``fn`` (typically ``grad(f)`` / ``value_and_grad(f)``) so that repeated calls replay a CUDA graph."""
+    return CapturedFunction(fn)

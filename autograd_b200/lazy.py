@@ -54,9 +54,10 @@ class Buffer:
 
     __slots__ = ("ptr", "nbytes", "__weakref__")
 
-    def __init__(self, nbytes: int):
+    def __init__(self, nbytes: int, upload: bool = False):
         self.nbytes = int(nbytes)
-        self.ptr = backend.get().malloc(self.nbytes)
+        be = backend.get()
+        self.ptr = be.malloc_upload(self.nbytes) if upload else be.malloc(self.nbytes)
 
     def __del__(self):
         ptr, self.ptr = self.ptr, 0
@@ -111,9 +112,9 @@ class Mat:
         return True
 
     @staticmethod
-    def empty(shape, dtype):
+    def empty(shape, dtype, upload=False):
         shape = tuple(int(s) for s in shape)
-        return Mat(Buffer(prod(shape) * dtype.itemsize), shape, c_strides(shape), 0, dtype)
+        return Mat(Buffer(prod(shape) * dtype.itemsize, upload), shape, c_strides(shape), 0, dtype)
 
 
 class Const:

@@ -57,6 +57,7 @@ int b200ag_launch_count(uint64_t* n);       /* kernels launched by this library 
  * Replaces numpy's allocator for array payloads (np.zeros/np.empty results,
  * ufunc outputs).  Caching, stream-ordered on the library stream. */
 int b200ag_malloc(size_t nbytes, void** ptr);
+int b200ag_malloc_upload(size_t nbytes, void** ptr);  /* destination of a host upload (graph-constant safe) */
 int b200ag_free(void* ptr);
 int b200ag_empty_cache(void);
 int b200ag_mem_stats(size_t* in_use, size_t* cached, size_t* peak_in_use);

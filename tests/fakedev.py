@@ -66,6 +66,9 @@ class FakeBackend:
         self.peak = max(self.peak, self.in_use)
         return base
 
+    def malloc_upload(self, nbytes):
+        return self.malloc(nbytes)
+
     def free(self, ptr):
         buf = self._bufs.pop(ptr, None)
         if buf is not None:

@@ -1,0 +1,88 @@
+"""CUDA-graph tape replay (autograd_b200.capture) — GPU only."""
+
+import numpy as onp
+import pytest
+
+import cases
+
+pytestmark = pytest.mark.gpu
+
+
+def test_replayed_mlp_grad_matches_eager_and_reference(cuda_dev):
+    import autograd_b200 as b200
+    from autograd import grad
+
+    from examples import workloads as w
+
+    params, X, T = w.mlp_data(batch=32, layer_sizes=(20, 16, 12, 10))
+    g = grad(w.mlp_objective)
+    with b200.host_arrays():
+        want = g(params, X, T, 1.0)
+    fast = b200.capture(g)
+    dp, dX, dT = cases.to_dev(params), b200.asarray(X), b200.asarray(T)
+    n0 = cuda_dev.launch_count()
+    for _ in range(3):
+        got = cases.to_host(fast(dp, dX, dT, 1.0))
+        for a, r in zip(cases.leaves(got), cases.leaves(want)):
+            cases.assert_close(a, r, cases.TOL_REDUCE, "replayed C1 grad")
+    assert cuda_dev.launch_count() > n0
+    # new input VALUES, same signature: the recording is replayed on refreshed inputs
+    params2, X2, T2 = w.mlp_data(batch=32, layer_sizes=(20, 16, 12, 10), seed=7)
+    with b200.host_arrays():
+        want2 = g(params2, X2, T2, 1.0)
+    got2 = cases.to_host(fast(cases.to_dev(params2), b200.asarray(X2), b200.asarray(T2), 1.0))
+    for a, r in zip(cases.leaves(got2), cases.leaves(want2)):
+        cases.assert_close(a, r, cases.TOL_REDUCE, "replayed C1 grad, new inputs")
+    assert len(fast.num_nodes()) == 1
+    # a different batch size is a new signature -> second recording
+    params3, X3, T3 = w.mlp_data(batch=16, layer_sizes=(20, 16, 12, 10), seed=3)
+    with b200.host_arrays():
+        want3 = g(params3, X3, T3, 1.0)
+    got3 = cases.to_host(fast(cases.to_dev(params3), b200.asarray(X3), b200.asarray(T3), 1.0))
+    for a, r in zip(cases.leaves(got3), cases.leaves(want3)):
+        cases.assert_close(a, r, cases.TOL_REDUCE, "replayed C1 grad, new signature")
+    assert len(fast.num_nodes()) == 2
+
+
+def test_replayed_lstm_and_fluid(cuda_dev):
+    import autograd_b200 as b200
+    from autograd import grad, value_and_grad
+
+    from examples import workloads as w
+
+    params, X, Y = w.lstm_data(seq_len=3, batch=8, hidden=16, chars=12)
+    g = grad(w.lstm_objective)
+    with b200.host_arrays():
+        want = g(params, X, Y)
+    fast = b200.capture(g)
+    for _ in range(2):
+        got = cases.to_host(fast(cases.to_dev(params), b200.asarray(X), b200.asarray(Y)))
+        for k in want:
+            cases.assert_close(got[k], want[k], cases.TOL_F32, f"replayed C3 {k}")
+
+    rows = cols = 16
+    p, s0, tg = w.fluid_data(rows, cols)
+    vg = value_and_grad(w.fluid_objective)
+    with b200.host_arrays():
+        vw, gw = vg(p, s0, tg, rows, cols, 2)
+    fastf = b200.capture(vg)
+    for _ in range(2):
+        v, gg = fastf(b200.asarray(p), b200.asarray(s0), b200.asarray(tg), rows, cols, 2)
+        cases.assert_close(gg.get(), gw, cases.TOL_REDUCE, "replayed C4 grad")
+        cases.assert_close(v.get(), onp.asarray(vw), cases.TOL_REDUCE, "replayed C4 value")
+
+
+def test_value_dependent_control_flow_is_rejected(cuda_dev):
+    import autograd.numpy as np
+    import autograd_b200 as b200
+
+    def f(x):
+        if float(np.sum(x)) > 0:  # reads a device value on the host
+            return x * 2
+        return x * 3
+
+    fast = b200.capture(f)
+    with pytest.raises(RuntimeError, match="captured"):
+        fast(b200.asarray(onp.ones(8)))
+    # the backend must be usable again afterwards
+    assert float((b200.asarray(onp.ones(4)) * 2).get().sum()) == 8.0
