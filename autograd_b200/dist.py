@@ -1,0 +1,138 @@
+"""Batch-sharded gradients across GPUs (one process per GPU, torch.distributed for the plumbing).
+
+The reference has no distributed layer; BASELINE.json's north_star asks for exactly one
+thing: batch-separable objectives (minibatch losses such as examples/neural_net.py:45-48 and
+examples/convnet.py:61-64) are sharded by batch, every rank runs the unchanged ``grad(objective)`` on its
+shard, and the gradient leaves are summed with ONE allreduce over NVLink.  Tape-serial workloads stay on one
+GPU.  The collective runs on NCCL tensors that alias our HBM buffers (no staging copy); on the CPU test
+suite the same code runs over gloo.
+"""
+
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from . import backend, lazy
+from .array import DeviceArray, concatenate, ravel, reshape
+
+_pg = None
+
+
+def init(backend_name: str | None = None):
+    """Join the torch.distributed job described by RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT."""
+    global _pg
+    import torch
+    import torch.distributed as dist
+
+    if dist.is_initialized():
+        _pg = dist
+        return dist
+    be = backend.get()
+    if backend_name is None:
+        backend_name = "nccl" if be.name == "cuda" else "gloo"
+    if backend_name == "nccl":
+        torch.cuda.set_device(be.device)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", be.device))
+    else:
+        dist.init_process_group(backend_name)
+    _pg = dist
+    return dist
+
+
+def world_size() -> int:
+    return int(os.environ.get("WORLD_SIZE", "1")) if _pg is None else _pg.get_world_size()
+
+
+def rank() -> int:
+    return int(os.environ.get("RANK", "0")) if _pg is None else _pg.get_rank()
+
+
+def _as_torch(x: DeviceArray):
+    """A torch tensor aliasing the payload of a contiguous DeviceArray."""
+    import torch
+
+    be = backend.get()
+    m = x._mat()
+    if not m.is_contiguous:
+        raise ValueError("allreduce needs a contiguous array")
+    if be.name == "cuda":
+        return torch.as_tensor(x, device=torch.device("cuda", be.device))
+    el, e0 = be._elems(m.ptr, m.dtype)  # host emulation used by the CPU test-suite
+    return torch.from_numpy(el[e0: e0 + x.size]).reshape(m.shape)
+
+
+def allreduce_sum_(x: DeviceArray) -> DeviceArray:
+    """In-place sum over ranks of a materialised, contiguous array (ncclAllReduce on the library stream)."""
+    if _pg is None or _pg.get_world_size() == 1:
+        return x
+    import torch
+
+    x._own_buffer()
+    be = backend.get()
+    if be.name == "cuda":
+        stream = torch.cuda.ExternalStream(be.stream_handle(), device=torch.device("cuda", be.device))
+        with torch.cuda.stream(stream):
+            t = _as_torch(x)
+            _pg.all_reduce(t, op=_pg.ReduceOp.SUM)
+    else:
+        _pg.all_reduce(_as_torch(x), op=_pg.ReduceOp.SUM)
+    return x
+
+
+def _leaves(tree, acc):
+    if isinstance(tree, DeviceArray):
+        acc.append(tree)
+    elif isinstance(tree, (list, tuple)):
+        for t in tree:
+            _leaves(t, acc)
+    elif isinstance(tree, dict):
+        for k in sorted(tree):
+            _leaves(tree[k], acc)
+    else:
+        raise TypeError(f"gradient leaf of type {type(tree).__name__} is not a DeviceArray")
+
+
+def _rebuild(tree, it):
+    if isinstance(tree, DeviceArray):
+        return next(it)
+    if isinstance(tree, (list, tuple)):
+        return type(tree)(_rebuild(t, it) for t in tree)
+    return {k: _rebuild(tree[k], it) for k in sorted(tree)}
+
+
+def flatten_tree(tree) -> DeviceArray:
+    """All gradient leaves raveled into ONE contiguous vector (one message instead of one per leaf)."""
+    acc = []
+    _leaves(tree, acc)
+    dt = np.result_type(*[a.dtype for a in acc])
+    return concatenate([ravel(a) if a.dtype == dt else ravel(a).astype(dt) for a in acc])
+
+
+def unflatten_like(flat: DeviceArray, tree):
+    acc = []
+    _leaves(tree, acc)
+    out, pos = [], 0
+    for a in acc:
+        piece = reshape(flat[pos: pos + a.size], a.shape)
+        out.append(piece if piece.dtype == a.dtype else piece.astype(a.dtype))
+        pos += a.size
+    return _rebuild(tree, iter(out))
+
+
+def allreduce_grads(grads):
+    """Sum a gradient tree over ranks with a single collective; returns a tree of the same structure."""
+    if _pg is None or _pg.get_world_size() == 1:
+        return grads
+    flat = flatten_tree(grads)
+    allreduce_sum_(flat)
+    return unflatten_like(flat, grads)
+
+
+def shard_batch(n_total: int):
+    """This rank's contiguous slice of a batch of ``n_total`` examples (even split, remainder to low ranks)."""
+    w, r = world_size(), rank()
+    base, extra = divmod(n_total, w)
+    lo = r * base + min(r, extra)
+    return slice(lo, lo + base + (1 if r < extra else 0))

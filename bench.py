@@ -259,7 +259,31 @@ def run_b200(args):
     e2e = {"value": world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(x_host.nbytes),
            "d2h_bytes_per_step": int(y_host.nbytes), "ms_per_step": e2e_ms}
 
+    # parity spot check on the bench inputs themselves: 2^16 points strided across the whole resident vector,
+    # error relative to the max-norm of the reference result (SURVEY.md §7: the derivative crosses zero)
+    stride = max(1, n >> 16)
+    got = f(x[::stride]).get()
+    with b200.host_arrays():
+        want = f(x_host[::stride].copy())
+    err = float(onp.max(onp.abs(got - want)) / onp.max(onp.abs(want)))
+    mem = be.mem_stats()
+
+    # ---- batch-sharded configs (C1 weak, C5 strong) with the NCCL gradient allreduce: every rank takes part
+    dp_results = None
+    if not args.no_extras:
+        del x, x_host, y_host, got, want
+        be.synchronize()
+        be.empty_cache()
+        from autograd_b200 import dist as bdist
+        from benchmarks import extras
+
+        if world > 1:
+            bdist.init("nccl")
+        dp_results = extras.run_dp(be, world, rank)
+
     if rank != 0:
+        if dist is not None:
+            dist.barrier()
         return 0
 
     # ---- reference CPU path timed beside it on this box's host cores (bounded sample)
@@ -268,26 +292,22 @@ def run_b200(args):
     cpu = {"value": cpu_value, "unit": UNIT, "cores": 1, "kind": "reference", "sample": sample,
            "host_cpu_count": os.cpu_count()}
 
-    # parity spot check on the bench inputs themselves: 2^16 points strided across the whole resident vector,
-    # error relative to the max-norm of the reference result (SURVEY.md §7: the derivative crosses zero)
-    stride = max(1, n >> 16)
-    got = f(x[::stride]).get()
-    with b200.host_arrays():
-        want = f(x_host[::stride].copy())
-    err = float(onp.max(onp.abs(got - want)) / onp.max(onp.abs(want)))
-
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": _config(n, world), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": launches, "clocks": clocks.summary(),
-        "parity_max_rel_err_vs_reference": err, "mem": be.mem_stats(),
+        "parity_max_rel_err_vs_reference": err, "mem": mem,
     }
-    if args.extras:
+    if dp_results is not None:
+        line["other_configs"] = dp_results
+    if not args.no_extras and world == 1:
         from benchmarks import extras
 
-        line["other_configs"] = extras.run(be, dist)
+        line["other_configs"] = {**extras.run(be), **(dp_results or {})}
     print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
     return 0
 
 
@@ -298,7 +318,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=1 << 28, help="points per GPU")
-    ap.add_argument("--extras", action="store_true", help="also time configs C1/C3/C4/C5 (reported under other_configs)")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the secondary measurements (configs C1/C3/C4/C5, kernel rates) reported under other_configs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
