@@ -1125,6 +1125,10 @@ def getitem(a: DeviceArray, idx):
     idx_arrays, idx_shape, n_lead = info
     m = a._cmat()
     inner_shape = a.shape[n_lead:]
+    if not inner_shape and prod(idx_shape) > 1:
+        # every axis is indexed: a pure element lookup, kept symbolic and fused into its consumers
+        table = a._node if a._node.mat is m else lazy.leaf(m)
+        return DeviceArray(lazy.make_gather(table, [i._node for i in idx_arrays]))
     out = Mat.empty(tuple(idx_shape) + tuple(inner_shape), a.dtype)
     mats = [i._cmat() for i in idx_arrays]
     backend.get().gather(out.ptr, m.ptr, a.dtype, [p.ptr for p in mats], list(a.shape[:n_lead]), prod(idx_shape),

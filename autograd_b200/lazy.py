@@ -36,14 +36,14 @@ _COST = {
     "equal": 1, "not_equal": 1, "less": 1, "less_equal": 1, "greater": 1, "greater_equal": 1,
     "logical_and": 1, "logical_or": 1, "logical_not": 1, "logical_xor": 1,
     "isfinite": 1, "isnan": 1, "isinf": 1, "floor": 1, "ceil": 1, "trunc": 1, "rint": 1,
-    "divide": 6, "reciprocal": 6, "sqrt": 6, "remainder": 8, "floor_divide": 8,
+    "divide": 6, "reciprocal": 6, "sqrt": 6, "remainder": 4, "floor_divide": 4, "gather": 4,
 }
 _DEFAULT_COST = 12  # transcendental functions
 
 # An interior node that Python can still see (a VJP closure holds it) is written
 # out as an extra output of the fused kernel once recomputing it would cost more
 # than this; cheaper ones are simply recomputed by whoever needs them later.
-KEEP_COST = 12
+KEEP_COST = 48
 # Hard caps that force a flush while a graph is still being built.
 MAX_NODES = 1500
 MAX_LEAVES = 48
@@ -256,6 +256,16 @@ def make_full(value, shape, dtype):
     return Node("full", (Const(value, dtype),), (dtype,), tuple(shape), dtype)
 
 
+def make_gather(table: Node, idx_nodes):
+    """Lazy ``table[idx0, idx1, ...]`` for integer index expressions covering EVERY axis of a materialised,
+    contiguous table: the lookup is folded into whatever fused kernel consumes it (and is simply redone by
+    the backward kernels that need the value again, instead of being kept in HBM)."""
+    shape = broadcast_shapes([i.shape for i in idx_nodes])
+    node = Node("gather", (table,) + tuple(idx_nodes), (table.dtype,) + (I64,) * len(idx_nodes), shape, table.dtype)
+    _maybe_flush_growing(node)
+    return node
+
+
 def _maybe_flush_growing(node):
     if len(node.leafset) > MAX_LEAVES:
         materialize(node)
@@ -271,9 +281,9 @@ def _maybe_flush_growing(node):
 class Program:
     """Structural description of one fused kernel; ``key`` identifies the generated code."""
 
-    __slots__ = ("instrs", "leaves", "consts", "outputs", "ndim", "idx64", "vec", "key", "cost")
+    __slots__ = ("instrs", "leaves", "consts", "outputs", "ndim", "idx64", "vec", "key", "cost", "tables")
 
-    def __init__(self, instrs, leaves, consts, outputs, ndim, idx64, vec, cost):
+    def __init__(self, instrs, leaves, consts, outputs, ndim, idx64, vec, cost, tables=()):
         self.instrs = instrs      # tuple of (op, in_dtype chars, out dtype char, arg refs)
         self.leaves = leaves      # tuple of (dtype char, layout class 'C'|'S'|'G', has_shift)
         self.consts = consts      # tuple of C scalar kinds: 'd' | 'q' | '?'
@@ -282,7 +292,8 @@ class Program:
         self.idx64 = idx64
         self.vec = vec            # elements per thread per step on the vector path
         self.cost = cost
-        self.key = (instrs, leaves, consts, outputs, ndim, idx64, vec)
+        self.tables = tables      # gather sources: tuple of (dtype char, number of indexed dims)
+        self.key = (instrs, leaves, consts, outputs, ndim, idx64, vec, tables)
 
     def launch_config(self, sm_count):
         block = 256
@@ -363,10 +374,25 @@ def materialize(root: Node) -> Mat:
         if nd_ is not root and nd_.nhandles > 0 and nd_.cost >= KEEP_COST and nd_.shape == root_shape:
             outs.append(nd_)
 
+    # ---- gather sources ("tables") are addressed by computed indices, not by the iteration index
+    table_index, table_descs, table_rt, elementwise_leaf = {}, [], [], set()
+    for nd_ in order:
+        for k, a in enumerate(nd_.args):
+            if type(a) is Node and a.mat is not None:
+                if nd_.op == "gather" and k == 0:
+                    if a.nid not in table_index:
+                        table_index[a.nid] = len(table_descs)
+                        table_descs.append((a.mat.dtype.char, len(a.mat.shape)))
+                        table_rt.append((a.mat.ptr, a.mat.shape))
+                else:
+                    elementwise_leaf.add(a.nid)
+
     # ---- leaves: classify layout relative to the iteration space
     leaf_index, leaf_descs, leaf_ptrs, g_layouts, g_slots = {}, [], [], [], []
     dedup = {}
     for ln in leaf_nodes:
+        if ln.nid not in elementwise_leaf:
+            continue
         m = ln.mat
         strides, shifts = _aligned_strides(m, root_shape)
         sig = (m.buf.ptr, m.offset, m.dtype.char, tuple(strides), tuple(shifts))
@@ -403,9 +429,11 @@ def materialize(root: Node) -> Mat:
     instr_index, instrs = {}, []
     for nd_ in order:
         refs = []
-        for a, in_dt in zip(nd_.args, nd_.in_dtypes):
+        for k, (a, in_dt) in enumerate(zip(nd_.args, nd_.in_dtypes)):
             if type(a) is Node:
-                if a.mat is not None:
+                if nd_.op == "gather" and k == 0:
+                    refs.append(("t", table_index[a.nid]))
+                elif a.mat is not None:
                     refs.append(("l", leaf_index[a.nid]))
                 else:
                     refs.append(("n", instr_index[a.nid]))
@@ -419,8 +447,8 @@ def materialize(root: Node) -> Mat:
                 else:
                     v = bool(v)
                 if (kind == "d" and v in _BAKED and not (v == 0.0 and math.copysign(1.0, v) < 0)) or (
-                    kind == "q" and -4 <= v <= 4
-                ) or kind == "?":
+                    kind == "q" and (-4 <= v <= 4 or (k == 1 and nd_.op in ("remainder", "floor_divide") and abs(v) < 1 << 31))
+                ) or kind == "?":  # a baked integer divisor lets the compiler strength-reduce `%` and `/`
                     refs.append(("k", v if kind != "d" else float(v)))
                 else:
                     ck = (kind, v)
@@ -438,6 +466,8 @@ def materialize(root: Node) -> Mat:
 
     # ---- vector width: 16-byte accesses on every contiguous leaf and output when alignment allows
     max_item = max([o.dtype.itemsize for o in outs] + [np.dtype(c).itemsize for c, cls, _ in leaf_descs if cls == "C"])
+    if table_descs:
+        max_item = 16  # gathers are latency-bound scalar loads: no vector path
     vec = max(1, 16 // max_item)
     total_cost = sum(_COST.get(nd_.op, _DEFAULT_COST) for nd_ in order)
     if total_cost > 400 or n < 4096:
@@ -454,10 +484,11 @@ def materialize(root: Node) -> Mat:
             max_extent = max(max_extent, ext)
     idx64 = max_extent >= (1 << 31) - (1 << 24)
 
-    program = Program(tuple(instrs), tuple(leaf_descs), tuple(const_kinds), outputs, ndim, idx64, vec, total_cost)
+    program = Program(tuple(instrs), tuple(leaf_descs), tuple(const_kinds), outputs, ndim, idx64, vec, total_cost,
+                      tuple(table_descs))
 
     out_mats = [Mat.empty(root_shape, o.dtype) for o in outs]
-    backend.get().run_program(program, (leaf_ptrs, dims), const_values, [m.ptr for m in out_mats], n)
+    backend.get().run_program(program, (leaf_ptrs, dims, table_rt), const_values, [m.ptr for m in out_mats], n)
     for o, m in zip(outs, out_mats):
         o.mat = m
     # drop the graph behind everything that is now materialised or no longer needed

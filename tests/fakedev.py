@@ -175,7 +175,8 @@ class FakeBackend:
             self._compiled.add(program.key)
         if n == 0:
             return
-        leaf_ptrs, dims = leaf_info
+        leaf_ptrs, dims = leaf_info[0], leaf_info[1]
+        tables = leaf_info[2] if len(leaf_info) > 2 else ()
         i = np.arange(n, dtype=np.int64)
         coords = None
         if program.ndim:
@@ -206,6 +207,9 @@ class FakeBackend:
                 args = []
                 for (kind, v), ich in zip(refs, in_chars):
                     dt = np.dtype(ich)
+                    if kind == "t":
+                        args.append(v)
+                        continue
                     if kind == "n":
                         a = vals[v]
                     elif kind == "l":
@@ -216,6 +220,17 @@ class FakeBackend:
                         a = v
                     args.append(np.asarray(a).astype(dt))
                 out_dt = np.dtype(out_ch)
+                if op == "gather":
+                    tptr, tdims = tables[args[0]]
+                    el, e0 = self._elems(tptr, out_dt)
+                    lin = np.zeros(n, dtype=np.int64)
+                    for d, size in enumerate(tdims):
+                        g = np.broadcast_to(args[1 + d], (n,)).astype(np.int64)
+                        g = np.where(g < 0, g + size, g)
+                        assert (g >= 0).all() and (g < size).all(), "gather index out of bounds"
+                        lin = lin * size + g
+                    vals.append(el[e0 + lin])
+                    continue
                 if op == "where":
                     r = np.where(args[0], args[1], args[2])
                 elif op in ("cast", "full"):
