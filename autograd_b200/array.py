@@ -425,6 +425,10 @@ class DeviceArray:
         v = asarray(values)
         if v.dtype != self.dtype:
             v = v.astype(self.dtype)
+        if not inner_shape and self.dtype.kind in "fi" and self.dtype.itemsize >= 4 and \
+                lazy.broadcast_shapes([tuple(idx_shape), v.shape]) == tuple(idx_shape):
+            lazy.scatter_add(m, [i._node for i in idx_arrays], v._node)
+            return
         v = broadcast_to(v, tuple(idx_shape) + tuple(inner_shape))
         vm = v._cmat()
         ptrs = [a._cmat() for a in idx_arrays]

@@ -114,6 +114,7 @@ class CapturedFunction:
             a.materialize()
         be.synchronize()
         del out, acc
+        be.empty_cache()  # the recording allocates from its own arena: give the warm-up's blocks back first
         # 2. private copies of the inputs: their addresses are what the graph bakes in
         static = []
         for leaf in leaves:

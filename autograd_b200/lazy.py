@@ -43,7 +43,7 @@ _DEFAULT_COST = 12  # transcendental functions
 # An interior node that Python can still see (a VJP closure holds it) is written
 # out as an extra output of the fused kernel once recomputing it would cost more
 # than this; cheaper ones are simply recomputed by whoever needs them later.
-KEEP_COST = 48
+KEEP_COST = 96
 # Hard caps that force a flush while a graph is still being built.
 MAX_NODES = 1500
 MAX_LEAVES = 48
@@ -266,6 +266,18 @@ def make_gather(table: Node, idx_nodes):
     return node
 
 
+def scatter_add(target: Mat, idx_nodes, value):
+    """``np.add.at(target, (idx0, idx1, ...), value)`` with every axis indexed, as ONE generated kernel: index
+    and value expressions are evaluated in registers and accumulated with FP64 atomics (RED.ADD in L2), so
+    neither the index arrays nor the cotangent being scattered are ever written to HBM
+    (VJP of integer-array ``__getitem__``, autograd/numpy/numpy_vjps.py:941-954)."""
+    args = (leaf(target),) + tuple(idx_nodes) + (value,)
+    shapes = [a.shape for a in args[1:] if type(a) is Node]
+    shape = broadcast_shapes(shapes) if shapes else ()
+    root = Node("scatter", args, (target.dtype,) + (I64,) * len(idx_nodes) + (target.dtype,), shape, target.dtype)
+    materialize(root, store_root=False)
+
+
 def _maybe_flush_growing(node):
     if len(node.leafset) > MAX_LEAVES:
         materialize(node)
@@ -360,7 +372,7 @@ def _collapse_dims(root_shape, leaf_layouts):
     return dims, lay
 
 
-def materialize(root: Node) -> Mat:
+def materialize(root: Node, store_root: bool = True) -> Mat:
     """Compute ``root`` (and any still-visible expensive interior node) with one fused kernel."""
     if root.mat is not None:
         return root.mat
@@ -369,7 +381,7 @@ def materialize(root: Node) -> Mat:
     n = prod(root_shape)
 
     # interior nodes that Python still holds and that are costly to recompute become extra outputs
-    outs = [root]
+    outs = [root] if store_root else []
     for nd_ in order:
         if nd_ is not root and nd_.nhandles > 0 and nd_.cost >= KEEP_COST and nd_.shape == root_shape:
             outs.append(nd_)
@@ -379,7 +391,7 @@ def materialize(root: Node) -> Mat:
     for nd_ in order:
         for k, a in enumerate(nd_.args):
             if type(a) is Node and a.mat is not None:
-                if nd_.op == "gather" and k == 0:
+                if nd_.op in ("gather", "scatter") and k == 0:
                     if a.nid not in table_index:
                         table_index[a.nid] = len(table_descs)
                         table_descs.append((a.mat.dtype.char, len(a.mat.shape)))
@@ -431,7 +443,7 @@ def materialize(root: Node) -> Mat:
         refs = []
         for k, (a, in_dt) in enumerate(zip(nd_.args, nd_.in_dtypes)):
             if type(a) is Node:
-                if nd_.op == "gather" and k == 0:
+                if nd_.op in ("gather", "scatter") and k == 0:
                     refs.append(("t", table_index[a.nid]))
                 elif a.mat is not None:
                     refs.append(("l", leaf_index[a.nid]))
@@ -491,6 +503,8 @@ def materialize(root: Node) -> Mat:
     backend.get().run_program(program, (leaf_ptrs, dims, table_rt), const_values, [m.ptr for m in out_mats], n)
     for o, m in zip(outs, out_mats):
         o.mat = m
+    if not store_root:
+        root.args = ()
     # drop the graph behind everything that is now materialised or no longer needed
     for nd_ in order:
         if nd_.mat is not None:

@@ -231,6 +231,18 @@ class FakeBackend:
                         lin = lin * size + g
                     vals.append(el[e0 + lin])
                     continue
+                if op == "scatter":
+                    tptr, tdims = tables[args[0]]
+                    el, e0 = self._elems(tptr, out_dt)
+                    lin = np.zeros(n, dtype=np.int64)
+                    for d, size in enumerate(tdims):
+                        g = np.broadcast_to(args[1 + d], (n,)).astype(np.int64)
+                        g = np.where(g < 0, g + size, g)
+                        assert (g >= 0).all() and (g < size).all(), "scatter index out of bounds"
+                        lin = lin * size + g
+                    np.add.at(el, e0 + lin, np.broadcast_to(args[1 + len(tdims)], (n,)).astype(out_dt))
+                    vals.append(np.zeros((), out_dt))
+                    continue
                 if op == "where":
                     r = np.where(args[0], args[1], args[2])
                 elif op in ("cast", "full"):
