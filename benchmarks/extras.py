@@ -352,9 +352,7 @@ def run_dp(be, world, rank):
 def run(be, dist=None, which=("kernels", "c1", "c5", "c3", "c4")):
     res = {}
     table = {"kernels": kernels, "c1": c1_mlp, "c3": c3_lstm, "c5": c5_convnet,
-             # the 200-step tape of the named 2048^2 grid does not fit 180 GB yet (1.18 GB retained per step):
-             # run the named grid for as many steps as the bench budget allows and say so
-             "c4": lambda be: c4_fluid(be, rows=2048, cols=2048, steps=16, cpu_rows=256)}
+             "c4": c4_fluid}
     for name in which:
         try:
             res[name] = table[name](be)
