@@ -183,11 +183,11 @@ class CudaBackend:
             handle, image = self.compile(source, name)
             rec = (handle, image, packer, program.launch_config(self.sm_count))
             self._kernels[program.key] = rec
-        handle, _image, packer, (block, elems_per_block, max_grid) = rec
+        handle, _image, packer, (block, _elems_per_block, _max_grid) = rec
         if n == 0:
             return
         params = packer(n, leaf_ptrs, const_values, out_ptrs, program)
-        grid = min((n + elems_per_block - 1) // elems_per_block, max_grid)
+        grid = program.grid(n, leaf_ptrs[1], self.sm_count)
         if self.profile is None:
             self._check(self._lib.b200ag_kernel_launch(handle, grid, block, 0, params, len(params)))
         else:

@@ -29,6 +29,8 @@ struct GemmArgs {
   int64_t b_rs, b_cs, b_bs;
   int64_t M, N, K;
   int c_is_f32;
+  int splits;        // split-K factor: blockIdx.z = batch * splits + split
+  int64_t k_chunk;   // K range per split (multiple of BK)
 };
 
 template <typename TA, typename TB, int BM, int BN, int WM, int WN, bool A_KMAJOR, bool B_KMAJOR>
@@ -46,8 +48,11 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32) gemm_dmma_kernel(G
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp / (BN / WN), wn = warp % (BN / WN);
   const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
-  const TA* A = (const TA*)g.A + (int64_t)blockIdx.z * g.a_bs;
-  const TB* B = (const TB*)g.B + (int64_t)blockIdx.z * g.b_bs;
+  const int64_t bz = blockIdx.z / g.splits, kz = blockIdx.z % g.splits;
+  const int64_t k_lo = kz * g.k_chunk;
+  const int64_t k_hi = (k_lo + g.k_chunk < g.K) ? k_lo + g.k_chunk : g.K;
+  const TA* A = (const TA*)g.A + bz * g.a_bs;
+  const TB* B = (const TB*)g.B + bz * g.b_bs;
 
   double acc[TM][TN][2];
 #pragma unroll
@@ -64,7 +69,7 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32) gemm_dmma_kernel(G
       int m = A_KMAJOR ? e / BK : e % BM;
       int k = A_KMAJOR ? e % BK : e / BM;
       int64_t gm = m0 + m, gk = k0 + k;
-      ra[i] = (gm < g.M && gk < g.K) ? (double)A[gm * g.a_rs + gk * g.a_cs] : 0.0;
+      ra[i] = (gm < g.M && gk < k_hi) ? (double)A[gm * g.a_rs + gk * g.a_cs] : 0.0;
     }
 #pragma unroll
     for (int i = 0; i < LB; ++i) {
@@ -72,7 +77,7 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32) gemm_dmma_kernel(G
       int n = B_KMAJOR ? e / BK : e % BN;
       int k = B_KMAJOR ? e % BK : e / BN;
       int64_t gn = n0 + n, gk = k0 + k;
-      rb[i] = (gn < g.N && gk < g.K) ? (double)B[gk * g.b_rs + gn * g.b_cs] : 0.0;
+      rb[i] = (gn < g.N && gk < k_hi) ? (double)B[gk * g.b_rs + gn * g.b_cs] : 0.0;
     }
   };
   auto store_shared = [&](int buf) {
@@ -94,14 +99,14 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32) gemm_dmma_kernel(G
     }
   };
 
-  const int64_t ktiles = (g.K + BK - 1) / BK;
-  load_global(0);
+  const int64_t ktiles = (k_hi - k_lo + BK - 1) / BK;
+  load_global(k_lo);
   store_shared(0);
   __syncthreads();
 
   for (int64_t kt = 0; kt < ktiles; ++kt) {
     const int buf = kt & 1;
-    if (kt + 1 < ktiles) load_global((kt + 1) * BK);
+    if (kt + 1 < ktiles) load_global(k_lo + (kt + 1) * BK);
     const double* as = As + buf * BM * LDS + (wm * WM + (lane >> 2)) * LDS + (lane & 3);
     const double* bs = Bs + buf * BN * LDS + (wn * WN + (lane >> 2)) * LDS + (lane & 3);
 #pragma unroll
@@ -122,8 +127,8 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32) gemm_dmma_kernel(G
     }
   }
 
-  // epilogue: one rounding to the output dtype
-  const int64_t cb = (int64_t)blockIdx.z * g.c_bs;
+  // epilogue: one rounding to the output dtype (split-K partials are accumulated with FP64 atomics instead)
+  const int64_t cb = bz * g.c_bs;
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
     int64_t row = m0 + wm * WM + i * 8 + (lane >> 2);
@@ -135,7 +140,8 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32) gemm_dmma_kernel(G
       for (int t = 0; t < 2; ++t) {
         if (col + t < g.N) {
           int64_t off = cb + row * g.c_rs + (col + t) * g.c_cs;
-          if (g.c_is_f32) ((float*)g.C)[off] = (float)acc[i][j][t];
+          if (g.splits > 1) atomicAdd((double*)g.C + off, acc[i][j][t]);
+          else if (g.c_is_f32) ((float*)g.C)[off] = (float)acc[i][j][t];
           else ((double*)g.C)[off] = acc[i][j][t];
         }
       }
@@ -153,7 +159,7 @@ static int launch_gemm(const GemmArgs& g, int64_t batch) {
     B200AG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  dim3 grid((unsigned)((g.N + BN - 1) / BN), (unsigned)((g.M + BM - 1) / BM), (unsigned)batch);
+  dim3 grid((unsigned)((g.N + BN - 1) / BN), (unsigned)((g.M + BM - 1) / BM), (unsigned)(batch * g.splits));
   kern<<<grid, NT, smem, stream()>>>(g);
   B200AG_LAUNCH_CHECK();
   return 0;
@@ -192,10 +198,43 @@ extern "C" int b200ag_gemm(void* C, int c_dtype, int64_t c_rs, int64_t c_cs, int
   if (M == 0 || N == 0 || batch == 0) return 0;
   if (c_dtype != B200AG_F64 && c_dtype != B200AG_F32) B200AG_FAIL("gemm: output dtype must be float64 or float32");
   if (batch > 65535) B200AG_FAIL("gemm: batch too large");
-  GemmArgs g{C, A, B, c_rs, c_cs, c_bs, a_rs, a_cs, a_bs, b_rs, b_cs, b_bs, M, N, K, c_dtype == B200AG_F32};
-  if (a_dtype == B200AG_F64 && b_dtype == B200AG_F64) return pick_layout<double, double>(g, batch);
-  if (a_dtype == B200AG_F64 && b_dtype == B200AG_F32) return pick_layout<double, float>(g, batch);
-  if (a_dtype == B200AG_F32 && b_dtype == B200AG_F64) return pick_layout<float, double>(g, batch);
-  if (a_dtype == B200AG_F32 && b_dtype == B200AG_F32) return pick_layout<float, float>(g, batch);
-  B200AG_FAIL("gemm: operand dtypes must be float64 or float32");
+  GemmArgs g{C, A, B, c_rs, c_cs, c_bs, a_rs, a_cs, a_bs, b_rs, b_cs, b_bs, M, N, K, c_dtype == B200AG_F32, 1, K};
+  // Split-K: when the output has too few tiles to occupy 148 SMs (weight gradients: small M x N, long K), slices of
+  // K go to different CTAs and are combined with FP64 atomics into a zeroed float64 accumulator.
+  int64_t tiles = ((M + 63) / 64) * ((N + 63) / 64) * batch;
+  int64_t want = (3 * (int64_t)sm_count() + tiles - 1) / tiles;
+  int64_t max_by_k = K / 128;
+  int64_t splits = want < max_by_k ? want : max_by_k;
+  if (splits > 64) splits = 64;
+  void* scratch = nullptr;
+  void* real_c = C;
+  bool dense_c = (c_cs == 1 && c_rs == N && (batch == 1 || c_bs == M * N));
+  if (tiles < 2 * (int64_t)sm_count() && splits >= 2 && dense_c && batch * splits <= 65535) {
+    int64_t chunk = (K + splits - 1) / splits;
+    chunk = (chunk + BK - 1) / BK * BK;
+    splits = (K + chunk - 1) / chunk;
+    g.splits = (int)splits;
+    g.k_chunk = chunk;
+    size_t bytes = (size_t)(M * N * batch) * sizeof(double);
+    if (g.c_is_f32) {
+      if (b200ag_malloc(bytes, &scratch)) return 1;
+      g.C = scratch;
+      g.c_is_f32 = 0;
+    }
+    if (b200ag_memset(g.C, 0, bytes)) return 1;
+  }
+  int rc;
+  if (a_dtype == B200AG_F64 && b_dtype == B200AG_F64) rc = pick_layout<double, double>(g, batch);
+  else if (a_dtype == B200AG_F64 && b_dtype == B200AG_F32) rc = pick_layout<double, float>(g, batch);
+  else if (a_dtype == B200AG_F32 && b_dtype == B200AG_F64) rc = pick_layout<float, double>(g, batch);
+  else if (a_dtype == B200AG_F32 && b_dtype == B200AG_F32) rc = pick_layout<float, float>(g, batch);
+  else B200AG_FAIL("gemm: operand dtypes must be float64 or float32");
+  if (scratch) {
+    if (rc == 0) {
+      int64_t shape[1] = {M * N * batch}, one[1] = {1};
+      rc = b200ag_copy_strided(real_c, B200AG_F32, one, scratch, B200AG_F64, one, shape, 1);
+    }
+    b200ag_free(scratch);
+  }
+  return rc;
 }

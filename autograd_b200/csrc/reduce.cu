@@ -143,6 +143,22 @@ __global__ void __launch_bounds__(256) col_reduce_kernel(T* __restrict__ dst, co
   }
 }
 
+// ---- inner > 1 and a SHORT reduced axis (pooling windows, small channel counts): one thread per output,
+// consecutive threads on consecutive `inner` positions, so every 32-byte sector that is fetched is used.
+template <typename T, typename A, int OP>
+__global__ void __launch_bounds__(256) col_reduce_small_kernel(T* __restrict__ dst, const T* __restrict__ src,
+                                                                int64_t outer, int64_t reduce, int64_t inner) {
+  int64_t total = outer * inner;
+  int64_t step = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += step) {
+    int64_t o = idx / inner, c = idx - o * inner;
+    const T* p = src + o * reduce * inner + c;
+    A acc = Red<OP, A>::identity();
+    for (int64_t r = 0; r < reduce; ++r) acc = Red<OP, A>::apply(acc, (A)p[r * inner]);
+    dst[idx] = (T)acc;
+  }
+}
+
 template <typename T, typename A, int OP>
 static int reduce_impl(T* dst, const T* src, int64_t outer, int64_t reduce, int64_t inner) {
   const int64_t target_ctas = (int64_t)sm_count() * 4;
@@ -179,6 +195,11 @@ static int reduce_impl(T* dst, const T* src, int64_t outer, int64_t reduce, int6
     int rc = reduce_impl<T, A, OP>(dst, (const T*)scratch, outer, split, 1);
     b200ag_free(scratch);
     return rc;
+  }
+  if (reduce <= 16 && outer * inner >= 32768) {
+    col_reduce_small_kernel<T, A, OP><<<grid_for(outer * inner, 256, 8), 256, 0, stream()>>>(dst, src, outer, reduce, inner);
+    B200AG_LAUNCH_CHECK();
+    return 0;
   }
   int64_t col_tiles = (inner + 31) / 32;
   int64_t base = outer * col_tiles;

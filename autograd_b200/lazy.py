@@ -293,9 +293,9 @@ def _maybe_flush_growing(node):
 class Program:
     """Structural description of one fused kernel; ``key`` identifies the generated code."""
 
-    __slots__ = ("instrs", "leaves", "consts", "outputs", "ndim", "idx64", "vec", "key", "cost", "tables")
+    __slots__ = ("instrs", "leaves", "consts", "outputs", "ndim", "idx64", "vec", "key", "cost", "tables", "mode")
 
-    def __init__(self, instrs, leaves, consts, outputs, ndim, idx64, vec, cost, tables=()):
+    def __init__(self, instrs, leaves, consts, outputs, ndim, idx64, vec, cost, tables=(), mode="flat"):
         self.instrs = instrs      # tuple of (op, in_dtype chars, out dtype char, arg refs)
         self.leaves = leaves      # tuple of (dtype char, layout class 'C'|'S'|'G', has_shift)
         self.consts = consts      # tuple of C scalar kinds: 'd' | 'q' | '?'
@@ -305,11 +305,22 @@ class Program:
         self.vec = vec            # elements per thread per step on the vector path
         self.cost = cost
         self.tables = tables      # gather sources: tuple of (dtype char, number of indexed dims)
-        self.key = (instrs, leaves, consts, outputs, ndim, idx64, vec, tables)
+        self.mode = mode          # "flat": one flattened index; "row": rows x inner loop (general-layout operands)
+        self.key = (instrs, leaves, consts, outputs, ndim, idx64, vec, tables, mode)
 
     def launch_config(self, sm_count):
         block = 256
         return block, block * self.vec, sm_count * 16
+
+    def grid(self, n, dims, sm_count):
+        per_block = 256 * self.vec
+        max_grid = sm_count * 16
+        if self.mode == "row":
+            inner = dims[-1]
+            gx = (inner + per_block - 1) // per_block
+            gy = max(1, min(n // inner, max_grid // gx))
+            return gx * gy
+        return max(1, min((n + per_block - 1) // per_block, max_grid))
 
 
 # small exact constants are baked into the source (lets the compiler fold x*1, x**2 ...)
@@ -495,9 +506,12 @@ def materialize(root: Node, store_root: bool = True) -> Mat:
             ext = sum(abs(s) * (d - 1) for s, d in zip(lp[1], dims)) + 1
             max_extent = max(max_extent, ext)
     idx64 = max_extent >= (1 << 31) - (1 << 24)
+    mode = "row" if g_layouts and dims[-1] >= 128 else "flat"
+    if mode == "row" and vec > 1 and dims[-1] % vec:
+        vec = 1
 
     program = Program(tuple(instrs), tuple(leaf_descs), tuple(const_kinds), outputs, ndim, idx64, vec, total_cost,
-                      tuple(table_descs))
+                      tuple(table_descs), mode)
 
     out_mats = [Mat.empty(root_shape, o.dtype) for o in outs]
     backend.get().run_program(program, (leaf_ptrs, dims, table_rt), const_values, [m.ptr for m in out_mats], n)

@@ -227,6 +227,33 @@ def case_roll():
     check(lambda a: onp.roll(a, 1, axis=0)[2:5], a, tol=0, what="slice of rolled")
 
 
+def case_row_mode_layouts():
+    """General-layout operands with a long inner dim: exercises the row-structured generated kernels."""
+    r = rs(30)
+    a = r.randn(48, 384)
+    b = r.randn(384)
+    c = r.randn(48, 1)
+    check(lambda a, b, c: a * b + c, a, b, c, tol=0, what="row/col broadcast, inner 384")
+    check(lambda a: onp.roll(a, 1, axis=0) + onp.roll(a, -1, axis=0) + onp.roll(a, 1, axis=1) + onp.roll(a, -1, axis=1),
+          a, tol=0, what="4-point stencil, inner 384")
+    check(lambda a: (a + onp.roll(a, 7, axis=1)) / 4.0 - onp.roll(a, -5, axis=0), a, tol=0, what="rolls + contiguous")
+    sq = r.randn(256, 256)
+    check(lambda s: s.T * 2.0 + s, sq, tol=0, what="transposed operand, inner 256")
+    check(lambda s: s[::2, ::-1] + 1.0, sq, tol=0, what="strided/negative-stride view")
+    t3 = r.randn(6, 10, 130)
+    check(lambda t: onp.roll(t, 1, axis=1) - t + onp.roll(t, -3, axis=2) * onp.roll(t, 2, axis=0), t3, tol=0,
+          what="3-D rolls (outer coords decomposed per row)")
+    check(lambda t, v: t * v[:130] + onp.swapaxes(t, 0, 1)[:6, :6, :].sum(), t3, b, tol=TOL_REDUCE, what="3-D broadcast")
+    odd = r.randn(33, 131)
+    check(lambda o: onp.roll(o, 1, axis=1) * 2.0 + o, odd, tol=0, what="odd inner size (no vector path)")
+    f32 = r.randn(40, 512).astype(onp.float32)
+    check(lambda x: onp.roll(x, -1, axis=1) + x * 2, f32, tol=0, what="f32 row mode (4-wide vectors)")
+    idx = onp.arange(2048)
+    cx, cy = onp.meshgrid(idx[:40], idx[:160])
+    v = r.randn(160, 40)
+    check(lambda cx, v: (cx - v, onp.floor(cx - v).astype(int) % 40), cx, v, tol=0, what="meshgrid broadcast views")
+
+
 def case_concat_repeat_pad():
     r = rs(10)
     a, b, c = r.randn(4, 5), r.randn(3, 5), r.randn(4, 2)
@@ -321,6 +348,9 @@ def case_big_reductions():
     check(lambda m: onp.sum(m, axis=1), m, tol=TOL_REDUCE, what="row sum")
     w = r.randn(33, 6, 12, 2, 12, 2)
     check(lambda w: onp.max(onp.max(w, axis=3), axis=4), w, tol=0, what="maxpool-style double max")
+    w2 = r.randn(300, 6, 12, 2, 12, 2)
+    check(lambda w: (onp.max(w, axis=3), onp.sum(w > 0.5, axis=3, keepdims=True), onp.sum(w, axis=(3, 5))), w2,
+          tol=TOL_REDUCE, what="short reduced axis, many outputs (pooling windows)")
     check(lambda m: onp.sum(m * m), m, tol=TOL_REDUCE, what="sum of squares")
     check(lambda v: onp.dot(v, v), v, tol=TOL_REDUCE, what="dot 1-D 1M")
 
@@ -393,6 +423,7 @@ OP_CASES = {
     "vector_tail": case_large_vector_tail,
     "views": case_views,
     "roll": case_roll,
+    "row_mode_layouts": case_row_mode_layouts,
     "concat_repeat_pad": case_concat_repeat_pad,
     "indexing": case_indexing,
     "reductions": case_reductions,
@@ -605,3 +636,20 @@ GRAD_CASES = {
     "check_grads": grad_case_check_grads,
     "vspace_axioms": grad_case_vspace_axioms,
 }
+
+
+def case_gemm_split_k():
+    """Few output tiles, long K: the split-K path (FP64 atomics) incl. f32 outputs and batched operands."""
+    r = rs(40)
+    a, b = r.randn(96, 4100), r.randn(4100, 40)
+    check(lambda a, b: onp.dot(a, b), a, b, tol=TOL_REDUCE, what="split-K 96x40x4100")
+    check(lambda a, b: onp.dot(a.T[:1000].T.T, b[:, :1].T.T) if False else onp.dot(a[:, :1000], b[:1000]), a, b,
+          tol=TOL_REDUCE, what="split-K strided A")
+    check(lambda a, b: onp.dot(a.astype(onp.float32), b.astype(onp.float32)), a, b, tol=TOL_F32, what="split-K f32 out")
+    g, x = r.randn(3000, 24), r.randn(3000, 50)
+    check(lambda g, x: onp.dot(x.T, g), g, x, tol=TOL_REDUCE, what="weight-gradient shape (A^T G)")
+    ba, bb = r.randn(3, 20, 1500), r.randn(3, 1500, 30)
+    check(lambda a, b: onp.matmul(a, b), ba, bb, tol=TOL_REDUCE, what="batched split-K")
+
+
+OP_CASES["gemm_split_k"] = case_gemm_split_k
