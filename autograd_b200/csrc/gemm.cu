@@ -14,7 +14,6 @@
 namespace b200ag {
 
 constexpr int BK = 16;
-constexpr int LDS = BK + 4;  // row pitch in doubles: (r*20 + k) mod 16 is a bijection on r<4,k<4
 
 __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -33,17 +32,31 @@ struct GemmArgs {
   int64_t k_chunk;   // K range per split (multiple of BK)
 };
 
+// Shared-memory layouts (doubles).  An operand that is contiguous along k in global memory is staged as
+// [row][k] with pitch BK+4; one that is contiguous along m/n is staged as [k][row] with pitch ROWS+4.  In both,
+// consecutive threads of the loader write consecutive addresses, and the 64-bit fragment reads of a half-warp
+// (row = lane/4 in 0..3, k = lane%4) hit 16 distinct bank pairs because the pitch is 4 mod 16.
+template <int ROWS, bool KMAJOR>
+struct Tile {
+  static constexpr int PITCH = KMAJOR ? BK + 4 : ROWS + 4;
+  static constexpr int SIZE = KMAJOR ? ROWS * PITCH : BK * PITCH;
+  __device__ static int at(int row, int k) { return KMAJOR ? row * PITCH + k : k * PITCH + row; }
+};
+
 template <typename TA, typename TB, int BM, int BN, int WM, int WN, bool A_KMAJOR, bool B_KMAJOR>
 __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32) gemm_dmma_kernel(GemmArgs g) {
   constexpr int NT = (BM / WM) * (BN / WN) * 32;
   constexpr int LA = BM * BK / NT;
   constexpr int LB = BN * BK / NT;
   constexpr int TM = WM / 8, TN = WN / 8;
+  using TileA = Tile<BM, A_KMAJOR>;
+  using TileB = Tile<BN, B_KMAJOR>;
   static_assert(BM * BK % NT == 0 && BN * BK % NT == 0, "tile/threads mismatch");
+  static_assert(NT % BK == 0 && NT % BM == 0 && NT % BN == 0 || NT >= BM, "loader mapping");
 
   extern __shared__ double smem[];
-  double* As = smem;                    // [2][BM][LDS]
-  double* Bs = smem + 2 * BM * LDS;     // [2][BN][LDS]
+  double* As = smem;                       // [2][TileA::SIZE]
+  double* Bs = smem + 2 * TileA::SIZE;     // [2][TileB::SIZE]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp / (BN / WN), wn = warp % (BN / WN);
@@ -51,8 +64,24 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32) gemm_dmma_kernel(G
   const int64_t bz = blockIdx.z / g.splits, kz = blockIdx.z % g.splits;
   const int64_t k_lo = kz * g.k_chunk;
   const int64_t k_hi = (k_lo + g.k_chunk < g.K) ? k_lo + g.k_chunk : g.K;
-  const TA* A = (const TA*)g.A + bz * g.a_bs;
-  const TB* B = (const TB*)g.B + bz * g.b_bs;
+
+  // ---- loader mapping: element e = tid + i*NT of a ROWS x BK slab.
+  //   k-major:  row = e / BK, k = e % BK   -> per thread: k fixed, row = row0 + i * (NT / BK)
+  //   row-major: row = e % ROWS, k = e / ROWS -> per thread: row fixed, k = k0 + i * (NT / ROWS)
+  constexpr int A_RSTEP = A_KMAJOR ? NT / BK : 0, A_KSTEP = A_KMAJOR ? 0 : NT / BM;
+  constexpr int B_RSTEP = B_KMAJOR ? NT / BK : 0, B_KSTEP = B_KMAJOR ? 0 : NT / BN;
+  const int a_row0 = A_KMAJOR ? tid / BK : tid % BM, a_k0 = A_KMAJOR ? tid % BK : tid / BM;
+  const int b_row0 = B_KMAJOR ? tid / BK : tid % BN, b_k0 = B_KMAJOR ? tid % BK : tid / BN;
+  const TA* pa = (const TA*)g.A + bz * g.a_bs + (m0 + a_row0) * g.a_rs + (k_lo + a_k0) * g.a_cs;
+  const TB* pb = (const TB*)g.B + bz * g.b_bs + (n0 + b_row0) * g.b_cs + (k_lo + b_k0) * g.b_rs;
+  const int64_t a_istep = (int64_t)A_RSTEP * g.a_rs + (int64_t)A_KSTEP * g.a_cs;
+  const int64_t b_istep = (int64_t)B_RSTEP * g.b_cs + (int64_t)B_KSTEP * g.b_rs;
+  const int64_t a_kadv = (int64_t)BK * g.a_cs, b_kadv = (int64_t)BK * g.b_rs;
+  unsigned a_rowok = 0, b_rowok = 0;  // bit i: row of element i is inside the matrix
+#pragma unroll
+  for (int i = 0; i < LA; ++i) a_rowok |= (m0 + a_row0 + i * A_RSTEP < g.M) ? (1u << i) : 0u;
+#pragma unroll
+  for (int i = 0; i < LB; ++i) b_rowok |= (n0 + b_row0 + i * B_RSTEP < g.N) ? (1u << i) : 0u;
 
   double acc[TM][TN][2];
 #pragma unroll
@@ -60,43 +89,32 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32) gemm_dmma_kernel(G
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  double ra[LA], rb[LB];
+  // staging registers keep the operand's own type: the f32 -> f64 widening happens when the slab is written to
+  // shared memory, i.e. AFTER the multiply of the previous slab, so the global loads stay in flight behind it
+  TA ra[LA];
+  TB rb[LB];
 
-  auto load_global = [&](int64_t k0) {
+  auto load_global = [&](int64_t kbase) {
 #pragma unroll
     for (int i = 0; i < LA; ++i) {
-      int e = tid + i * NT;
-      int m = A_KMAJOR ? e / BK : e % BM;
-      int k = A_KMAJOR ? e % BK : e / BM;
-      int64_t gm = m0 + m, gk = k0 + k;
-      ra[i] = (gm < g.M && gk < k_hi) ? (double)A[gm * g.a_rs + gk * g.a_cs] : 0.0;
+      bool ok = ((a_rowok >> i) & 1u) && (kbase + a_k0 + i * A_KSTEP < k_hi);
+      ra[i] = ok ? pa[i * a_istep] : (TA)0;
     }
 #pragma unroll
     for (int i = 0; i < LB; ++i) {
-      int e = tid + i * NT;
-      int n = B_KMAJOR ? e / BK : e % BN;
-      int k = B_KMAJOR ? e % BK : e / BN;
-      int64_t gn = n0 + n, gk = k0 + k;
-      rb[i] = (gn < g.N && gk < k_hi) ? (double)B[gk * g.b_rs + gn * g.b_cs] : 0.0;
+      bool ok = ((b_rowok >> i) & 1u) && (kbase + b_k0 + i * B_KSTEP < k_hi);
+      rb[i] = ok ? pb[i * b_istep] : (TB)0;
     }
+    pa += a_kadv;
+    pb += b_kadv;
   };
   auto store_shared = [&](int buf) {
-    double* as = As + buf * BM * LDS;
-    double* bs = Bs + buf * BN * LDS;
+    double* as = As + buf * TileA::SIZE;
+    double* bs = Bs + buf * TileB::SIZE;
 #pragma unroll
-    for (int i = 0; i < LA; ++i) {
-      int e = tid + i * NT;
-      int m = A_KMAJOR ? e / BK : e % BM;
-      int k = A_KMAJOR ? e % BK : e / BM;
-      as[m * LDS + k] = ra[i];
-    }
+    for (int i = 0; i < LA; ++i) as[TileA::at(a_row0 + i * A_RSTEP, a_k0 + i * A_KSTEP)] = (double)ra[i];
 #pragma unroll
-    for (int i = 0; i < LB; ++i) {
-      int e = tid + i * NT;
-      int n = B_KMAJOR ? e / BK : e % BN;
-      int k = B_KMAJOR ? e % BK : e / BN;
-      bs[n * LDS + k] = rb[i];
-    }
+    for (int i = 0; i < LB; ++i) bs[TileB::at(b_row0 + i * B_RSTEP, b_k0 + i * B_KSTEP)] = (double)rb[i];
   };
 
   const int64_t ktiles = (k_hi - k_lo + BK - 1) / BK;
@@ -104,18 +122,23 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32) gemm_dmma_kernel(G
   store_shared(0);
   __syncthreads();
 
+  const int a_frag = TileA::at(wm * WM + (lane >> 2), lane & 3);
+  const int b_frag = TileB::at(wn * WN + (lane >> 2), lane & 3);
+  constexpr int A_ROW8 = A_KMAJOR ? 8 * TileA::PITCH : 8, A_K4 = A_KMAJOR ? 4 : 4 * TileA::PITCH;
+  constexpr int B_ROW8 = B_KMAJOR ? 8 * TileB::PITCH : 8, B_K4 = B_KMAJOR ? 4 : 4 * TileB::PITCH;
+
   for (int64_t kt = 0; kt < ktiles; ++kt) {
     const int buf = kt & 1;
     if (kt + 1 < ktiles) load_global(k_lo + (kt + 1) * BK);
-    const double* as = As + buf * BM * LDS + (wm * WM + (lane >> 2)) * LDS + (lane & 3);
-    const double* bs = Bs + buf * BN * LDS + (wn * WN + (lane >> 2)) * LDS + (lane & 3);
+    const double* as = As + buf * TileA::SIZE + a_frag;
+    const double* bs = Bs + buf * TileB::SIZE + b_frag;
 #pragma unroll
     for (int k4 = 0; k4 < BK / 4; ++k4) {
       double af[TM], bf[TN];
 #pragma unroll
-      for (int i = 0; i < TM; ++i) af[i] = as[i * 8 * LDS + k4 * 4];
+      for (int i = 0; i < TM; ++i) af[i] = as[i * A_ROW8 + k4 * A_K4];
 #pragma unroll
-      for (int j = 0; j < TN; ++j) bf[j] = bs[j * 8 * LDS + k4 * 4];
+      for (int j = 0; j < TN; ++j) bf[j] = bs[j * B_ROW8 + k4 * B_K4];
 #pragma unroll
       for (int i = 0; i < TM; ++i)
 #pragma unroll
@@ -152,7 +175,7 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32) gemm_dmma_kernel(G
 template <typename TA, typename TB, int BM, int BN, int WM, int WN, bool AK, bool BKM>
 static int launch_gemm(const GemmArgs& g, int64_t batch) {
   constexpr int NT = (BM / WM) * (BN / WN) * 32;
-  size_t smem = (size_t)2 * (BM + BN) * LDS * sizeof(double);
+  size_t smem = (size_t)2 * (Tile<BM, AK>::SIZE + Tile<BN, BKM>::SIZE) * sizeof(double);
   auto kern = gemm_dmma_kernel<TA, TB, BM, BN, WM, WN, AK, BKM>;
   static bool configured = false;
   if (!configured) {
