@@ -44,6 +44,7 @@ _DEFAULT_COST = 12  # transcendental functions
 # out as an extra output of the fused kernel once recomputing it would cost more
 # than this; cheaper ones are simply recomputed by whoever needs them later.
 KEEP_COST = 96
+REUSE_LIMIT = 2
 # Hard caps that force a flush while a graph is still being built.
 MAX_NODES = 1500
 MAX_LEAVES = 48
@@ -132,7 +133,7 @@ _EMPTY = frozenset()
 
 class Node:
     __slots__ = ("op", "args", "in_dtypes", "shape", "dtype", "mat", "nid", "lo", "cost", "leafset", "nhandles",
-                 "__weakref__")
+                 "uses", "__weakref__")
 
     def __init__(self, op, args, in_dtypes, shape, dtype, mat=None):
         self.op = op
@@ -143,6 +144,7 @@ class Node:
         self.mat = mat
         self.nid = next(_ids)
         self.nhandles = 0
+        self.uses = 0  # times this node was recomputed as an interior node of somebody else's kernel
         if mat is None:
             lo, cost, leafset = self.nid, _COST.get(op, _DEFAULT_COST), _EMPTY
             for a in args:
@@ -392,10 +394,15 @@ def materialize(root: Node, store_root: bool = True) -> Mat:
     n = prod(root_shape)
 
     # interior nodes that Python still holds and that are costly to recompute become extra outputs
+    # (b) or that have already been recomputed REUSE_LIMIT times (a loop keeps coming back to them: the
+    #     Jacobi right-hand side of fluidsim.py:21-30 is read by all ten sweeps)
     outs = [root] if store_root else []
     for nd_ in order:
-        if nd_ is not root and nd_.nhandles > 0 and nd_.cost >= KEEP_COST and nd_.shape == root_shape:
-            outs.append(nd_)
+        if nd_ is not root and nd_.nhandles > 0 and nd_.shape == root_shape and nd_.op not in ("full", "scatter"):
+            if nd_.cost >= KEEP_COST or (nd_.uses >= REUSE_LIMIT and len(nd_.leafset) > 1):
+                outs.append(nd_)
+            else:
+                nd_.uses += 1
 
     # ---- gather sources ("tables") are addressed by computed indices, not by the iteration index
     table_index, table_descs, table_rt, elementwise_leaf = {}, [], [], set()
@@ -443,9 +450,23 @@ def materialize(root: Node, store_root: bool = True) -> Mat:
         for slot, (s, sh) in zip(g_slots, lay):
             leaf_ptrs[slot][1] = s
             leaf_ptrs[slot][2] = sh
+            # specialise the common inner-dim patterns: "u" = unit inner stride, "R" = additionally no inner
+            # shift and every row start 16-byte aligned, so the row can be read with vector loads
+            ch, _cls, has_shift = leaf_descs[slot]
+            item = np.dtype(ch).itemsize
+            vecw = max(1, 16 // item)
+            if s[-1] == 1:
+                aligned = leaf_ptrs[slot][0] % 16 == 0 and all(st % vecw == 0 for st in s[:-1])
+                if not sh[-1] and aligned:
+                    leaf_descs[slot] = (ch, "G", has_shift, "R")
+                else:
+                    leaf_descs[slot] = (ch, "G", has_shift, "u")
+            else:
+                leaf_descs[slot] = (ch, "G", has_shift, "")
         ndim = len(dims)
     else:
         dims, ndim = [], 0
+    leaf_descs = [d if len(d) == 4 else d + ("",) for d in leaf_descs]
 
     # ---- instructions
     const_kinds, const_values, const_dedup = [], [], {}
@@ -488,7 +509,7 @@ def materialize(root: Node, store_root: bool = True) -> Mat:
     outputs = tuple((instr_index[o.nid], o.dtype.char) for o in outs)
 
     # ---- vector width: 16-byte accesses on every contiguous leaf and output when alignment allows
-    max_item = max([o.dtype.itemsize for o in outs] + [np.dtype(c).itemsize for c, cls, _ in leaf_descs if cls == "C"])
+    max_item = max([o.dtype.itemsize for o in outs] + [np.dtype(d[0]).itemsize for d in leaf_descs if d[1] == "C" or d[3] == "R"])
     if table_descs:
         max_item = 16  # gathers are latency-bound scalar loads: no vector path
     vec = max(1, 16 // max_item)
@@ -496,7 +517,7 @@ def materialize(root: Node, store_root: bool = True) -> Mat:
     if total_cost > 400 or n < 4096:
         vec = 1  # heavy bodies are ALU-bound: keep the code size down
     if vec > 1:
-        for (ch, cls, _), lp in zip(leaf_descs, leaf_ptrs):
+        for (ch, cls, _, _f), lp in zip(leaf_descs, leaf_ptrs):
             if cls == "C" and lp[0] % (np.dtype(ch).itemsize * vec):
                 vec = 1
                 break

@@ -186,7 +186,7 @@ class FakeBackend:
                 rem = rem // dims[d]
             coords[0] = rem
         leaves = []
-        for (ch, cls, has_shift), (ptr, strides, shifts) in zip(program.leaves, leaf_ptrs):
+        for (ch, cls, has_shift, _flag), (ptr, strides, shifts) in zip(program.leaves, leaf_ptrs):
             el, e0 = self._elems(ptr, np.dtype(ch))
             if cls == "S":
                 leaves.append(el[e0])
