@@ -133,15 +133,17 @@ static bool try_transpose(void* dst, const void* src, const StridedDesc& d) {
   // pattern: 2 or 3 collapsed dims, one of the two inner dims unit-stride in src and the other in dst
   if (d.ndim != 2 && d.ndim != 3) return false;
   int o = d.ndim - 2;
-  int64_t rows = d.shape[o], cols = d.shape[o + 1];
+  int r = o, c = o + 1;  // the kernel wants src contiguous along "cols" and dst contiguous along "rows"
+  if (d.src_strides[o] == 1 && d.dst_strides[o + 1] == 1) { r = o + 1; c = o; }
+  else if (!(d.src_strides[o + 1] == 1 && d.dst_strides[o] == 1)) return false;
+  int64_t rows = d.shape[r], cols = d.shape[c];
   if (rows < 16 || cols < 16) return false;
-  if (!(d.src_strides[o + 1] == 1 && d.dst_strides[o] == 1)) return false;
   int64_t batch = d.ndim == 3 ? d.shape[0] : 1;
   int64_t ntiles = ((rows + 31) / 32) * ((cols + 31) / 32) * batch;
   unsigned grid = (unsigned)(ntiles < (int64_t)sm_count() * 16 ? ntiles : (int64_t)sm_count() * 16);
   transpose_tile_kernel<T><<<grid, 256, 0, stream()>>>(
-      (T*)dst, (const T*)src, rows, cols, d.dst_strides[o], d.dst_strides[o + 1], d.src_strides[o],
-      d.src_strides[o + 1], batch, d.ndim == 3 ? d.dst_strides[0] : 0, d.ndim == 3 ? d.src_strides[0] : 0);
+      (T*)dst, (const T*)src, rows, cols, d.dst_strides[r], d.dst_strides[c], d.src_strides[r],
+      d.src_strides[c], batch, d.ndim == 3 ? d.dst_strides[0] : 0, d.ndim == 3 ? d.src_strides[0] : 0);
   return true;
 }
 

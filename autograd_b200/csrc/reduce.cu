@@ -301,25 +301,27 @@ __global__ void __launch_bounds__(256) logsumexp_kernel(T* __restrict__ dst, con
     for (int64_t r = lane; r < reduce; r += 32) mx = max_nan(mx, (double)p[r * inner]);
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) mx = max_nan(mx, __shfl_xor_sync(0xffffffffu, mx, d));
-    double m = 0.0, s = 0.0, direct = 0.0;
+    double m = 0.0, s = 0.0;
     for (int64_t r = lane; r < reduce; r += 32) {
       double a = (double)p[r * inner];
       if (a == mx) m += 1.0;
       else s += exp(a - mx);
-      direct += exp(a);
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
       m += __shfl_xor_sync(0xffffffffu, m, d);
       s += __shfl_xor_sync(0xffffffffu, s, d);
-      direct += __shfl_xor_sync(0xffffffffu, direct, d);
     }
-    if (lane == 0) {
-      double sm = (s == 0.0) ? s : s / m;
-      double out = log1p(sm) + log(m) + mx;
-      if (!isfinite(out)) out = log(direct);
-      dst[w] = (T)out;
+    double sm = (s == 0.0) ? s : s / m;
+    double out = log1p(sm) + log(m) + mx;
+    if (!isfinite(out)) {  // rare (inf / nan / empty-ish rows): SciPy falls back to the direct formula
+      double direct = 0.0;
+      for (int64_t r = lane; r < reduce; r += 32) direct += exp((double)p[r * inner]);
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) direct += __shfl_xor_sync(0xffffffffu, direct, d);
+      out = log(direct);
     }
+    if (lane == 0) dst[w] = (T)out;
   }
 }
 
