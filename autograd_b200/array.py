@@ -1456,6 +1456,106 @@ def outer(a, b, out=None):
 
 
 
+
+# =================================================================== einsum (pairwise contraction on the GEMM kernel)
+def _einsum_parse(subscripts, shapes):
+    """Explicit input/output subscript lists for ``subscripts`` (ellipsis expanded to upper-case letters)."""
+    subscripts = subscripts.replace(" ", "")
+    if "->" in subscripts:
+        lhs, out = subscripts.split("->")
+    else:
+        lhs, out = subscripts, None
+    ins = lhs.split(",")
+    if len(ins) != len(shapes):
+        raise ValueError("more operands provided to einstein sum function than specified in the subscripts string")
+    ell = "ABCDEFGHIJKLMNOPQRSTUVWXYZ"
+    max_ell = 0
+    ex = []
+    for sub, shp in zip(ins, shapes):
+        if "..." in sub:
+            n = len(shp) - (len(sub) - 3)
+            if n < 0:
+                raise ValueError("einsum: ellipsis does not match operand rank")
+            max_ell = max(max_ell, n)
+            sub = sub.replace("...", ell[len(ell) - n:] if n else "")
+        if len(sub) != len(shp):
+            raise ValueError(f"einsum: operand has {len(shp)} dims but subscripts {sub!r}")
+        ex.append(sub)
+    if out is None:
+        counts = {}
+        for sub in ex:
+            for ch in sub:
+                counts[ch] = counts.get(ch, 0) + 1
+        out = "".join(sorted(ch for ch in counts if ch in ell)) + "".join(sorted(ch for ch, c in counts.items() if c == 1 and ch not in ell))
+    else:
+        out = out.replace("...", ell[len(ell) - max_ell:] if max_ell else "")
+    return ex, out
+
+
+def einsum(*operands, **kwargs):
+    """np.einsum for device operands: every pairwise step is transposes + one (batched) DMMA GEMM."""
+    if kwargs.get("out") is not None:
+        raise NotImplementedError("autograd_b200: einsum(out=...) is not supported")
+    if not isinstance(operands[0], str):
+        # (op0, sublist0, op1, sublist1, ..., [sublistout]) convention -> subscript string
+        letters = "abcdefghijklmnopqrstuvwxyz"
+        ops, subs = [], []
+        rest = list(operands)
+        while len(rest) >= 2:
+            ops.append(rest.pop(0))
+            sl = rest.pop(0)
+            subs.append("".join("..." if x is Ellipsis else letters[x] for x in sl))
+        spec = ",".join(subs)
+        if rest:
+            spec += "->" + "".join("..." if x is Ellipsis else letters[x] for x in rest[0])
+        return einsum(spec, *ops)
+    spec, ops = operands[0], [asarray(o) for o in operands[1:]]
+    ins, out = _einsum_parse(spec, [o.shape for o in ops])
+    for sub in ins:
+        if len(set(sub)) != len(sub):
+            raise NotImplementedError("autograd_b200: einsum with a repeated index inside one operand (diagonal) is not implemented")
+    sizes = {}
+    for sub, o in zip(ins, ops):
+        for ch, n in zip(sub, o.shape):
+            if n != 1:
+                if sizes.get(ch, n) != n:
+                    raise ValueError(f"einsum: size mismatch for index {ch!r}")
+                sizes[ch] = n
+            sizes.setdefault(ch, n)
+    # broadcast size-1 dims that pair with larger ones
+    ops = [broadcast_to(o, tuple(sizes[ch] for ch in sub)) if o.shape != tuple(sizes[ch] for ch in sub) else o
+           for sub, o in zip(ins, ops)]
+
+    def reduce_unneeded(sub, o, needed):
+        drop = [i for i, ch in enumerate(sub) if ch not in needed]
+        if drop:
+            o = reduce_(o, "sum", tuple(drop), False)
+            sub = "".join(ch for ch in sub if ch in needed)
+        return sub, o
+
+    cur_sub, cur = ins[0], ops[0]
+    for k in range(1, len(ops)):
+        later = set(out).union(*ins[k + 1:]) if k + 1 < len(ops) else set(out)
+        cur_sub, cur = reduce_unneeded(cur_sub, cur, later | set(ins[k]))
+        b_sub, b = reduce_unneeded(ins[k], ops[k], later | set(cur_sub))
+        batch = [ch for ch in cur_sub if ch in b_sub and ch in later]
+        contr = [ch for ch in cur_sub if ch in b_sub and ch not in later]
+        free_a = [ch for ch in cur_sub if ch not in b_sub]
+        free_b = [ch for ch in b_sub if ch not in cur_sub]
+        a_t = transpose(cur, [cur_sub.index(ch) for ch in batch + free_a + contr])
+        b_t = transpose(b, [b_sub.index(ch) for ch in batch + contr + free_b])
+        nb = prod(sizes[ch] for ch in batch)
+        M, K, N = prod(sizes[ch] for ch in free_a), prod(sizes[ch] for ch in contr), prod(sizes[ch] for ch in free_b)
+        res = matmul(reshape(a_t, (nb, M, K)), reshape(b_t, (nb, K, N))) if nb != 1 or batch else \
+            _gemm2d(reshape(a_t, (M, K)), reshape(b_t, (K, N)))
+        cur_sub = "".join(batch + free_a + free_b)
+        cur = reshape(res, tuple(sizes[ch] for ch in cur_sub))
+    cur_sub, cur = reduce_unneeded(cur_sub, cur, set(out))
+    if cur_sub != out:
+        cur = transpose(cur, [cur_sub.index(ch) for ch in out])
+    return cur
+
+
 # =================================================================== convolution (NCHW, tiny channel counts)
 def _conv_operands(x, w):
     x, w = asarray(x), asarray(w)
@@ -1550,7 +1650,7 @@ FUNCTIONS = {
     np.sum: sum_, np.prod: prod_, np.max: amax, np.amax: amax, np.min: amin, np.amin: amin, np.mean: mean,
     np.var: var, np.std: std, np.all: all_, np.any: any_, np.count_nonzero: count_nonzero,
     np.argmax: argmax, np.argmin: argmin,
-    np.dot: dot, np.matmul: matmul, np.tensordot: tensordot, np.inner: inner, np.outer: outer,
+    np.dot: dot, np.matmul: matmul, np.tensordot: tensordot, np.inner: inner, np.outer: outer, np.einsum: einsum,
     np.where: where, np.clip: clip, np.round: round_, np.around: round_, np.nan_to_num: nan_to_num,
     np.real: real, np.imag: imag, np.isclose: isclose, np.allclose: allclose, np.array_equal: array_equal,
     np.zeros_like: zeros_like, np.ones_like: ones_like, np.empty_like: empty_like, np.full_like: full_like,
@@ -1559,4 +1659,5 @@ FUNCTIONS = {
     np.meshgrid: meshgrid, np.linspace: linspace,
 }
 # NumPy's own pure-Python implementations of these only call other dispatched functions.
-DECOMPOSE = {np.hstack, np.vstack, np.dstack, np.column_stack, np.atleast_3d, np.rot90, np.kron}
+DECOMPOSE = {np.hstack, np.vstack, np.dstack, np.column_stack, np.atleast_3d, np.rot90, np.kron,
+             np.split, np.array_split, np.hsplit, np.vsplit, np.dsplit}

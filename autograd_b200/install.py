@@ -194,6 +194,11 @@ def install(creation: bool = True):
         lambda ans, A_, g, An, Bn: lambda B: nv.match_complex(g, anp.dot(A_, B)),
     )
 
+    from autograd.core import def_linear
+
+    def_linear(dev_dot_adjoint_0)  # numpy_jvps.py:232-233: the adjoints are linear in every argument
+    def_linear(dev_dot_adjoint_1)
+
     # ------------------------------------------------------------ logsumexp (scipy/special.py:120-147)
     ref_logsumexp = aspecial.logsumexp
 
@@ -286,6 +291,21 @@ def install(creation: bool = True):
     nw.array_from_args = from_args
     anp._array_from_scalar_or_array = from_scalar
     anp.array_from_args = from_args
+
+    # ------------------------------------------------------------ einsum VJP: subscript parsing without coercion
+    # numpy_wrapper.py:192-195: parse_einsum_input hands the operands to NumPy's parser, which calls asanyarray on
+    # them.  Only shapes matter there, so device operands are swapped for zero-stride host stand-ins.
+    from autograd.extend import notrace_primitive
+
+    ref_parse = nw._parse_einsum_input
+
+    def _parse_raw(*args):
+        stand_ins = [onp.broadcast_to(onp.zeros((), a.dtype), a.shape) if isinstance(a, DeviceArray) else a for a in args]
+        return ref_parse(stand_ins)
+
+    parse_einsum_input = notrace_primitive(_parse_raw)
+    nw.parse_einsum_input = parse_einsum_input
+    anp.parse_einsum_input = parse_einsum_input
 
     # ------------------------------------------------------------ creation functions
     if creation:

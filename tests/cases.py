@@ -402,6 +402,24 @@ def case_gemm():
           what="inner/outer")
 
 
+def case_einsum():
+    r = rs(50)
+    a, b, c = r.randn(5, 7), r.randn(7, 4), r.randn(4, 6)
+    t3, t4 = r.randn(3, 5, 7), r.randn(3, 7, 2)
+    check(lambda a, b: onp.einsum("ij,jk->ik", a, b), a, b, tol=TOL_REDUCE, what="einsum matmul")
+    check(lambda a, b: onp.einsum("ij,jk", a, b), a, b, tol=TOL_REDUCE, what="einsum implicit output")
+    check(lambda a, b, c: onp.einsum("ij,jk,kl->il", a, b, c), a, b, c, tol=TOL_REDUCE, what="einsum 3 operands")
+    check(lambda x, y: onp.einsum("bij,bjk->bik", x, y), t3, t4, tol=TOL_REDUCE, what="einsum batched")
+    check(lambda x, y: onp.einsum("bij,bjk->kb", x, y), t3, t4, tol=TOL_REDUCE, what="einsum batched + sum + transpose")
+    check(lambda a: onp.einsum("ij->ji", a), a, tol=0, what="einsum transpose")
+    check(lambda a: onp.einsum("ij->", a), a, tol=TOL_REDUCE, what="einsum total sum")
+    check(lambda a, b: onp.einsum("ij,jk->", a, b), a, b, tol=TOL_REDUCE, what="einsum full contraction")
+    check(lambda x, a: onp.einsum("...ij,kj->...ik", x, a), t3, a, tol=TOL_REDUCE, what="einsum ellipsis")
+    check(lambda a: onp.einsum("ij,ij->i", a, a), a, tol=TOL_REDUCE, what="einsum row dots")
+    check(lambda a, v: onp.einsum("ij,j", a, v), a, r.randn(7), tol=TOL_REDUCE, what="einsum mat-vec")
+    check(lambda a, b: onp.einsum(a, [0, 1], b, [1, 2], [0, 2]), a, b, tol=TOL_REDUCE, what="einsum sublist form")
+
+
 def case_conv2d():
     from autograd.scipy.signal import convolve
 
@@ -430,6 +448,7 @@ OP_CASES = {
     "big_reductions": case_big_reductions,
     "logsumexp": case_logsumexp,
     "gemm": case_gemm,
+    "einsum": case_einsum,
     "conv2d": case_conv2d,
 }
 
@@ -574,6 +593,8 @@ def grad_case_vjp_rules():
         "tensordot": (lambda a: np.sum(np.tensordot(a, a, [[0], [0]]) ** 2), (a,)),
         "matmul": (lambda a: np.sum((a @ a.T) ** 2), (a,)),
         "repeat": (lambda c: np.sum(np.repeat(c, 4, axis=1) * np.arange(4.0)), (c,)),
+        "einsum": (lambda a, b: np.sum(np.einsum("ij,j->i", a, b) ** 2) + np.sum(np.einsum("ij,kj->ik", a, a)), (a, b)),
+        "einsum naked sum": (lambda a: np.sum(np.einsum("ij->j", a) ** 2), (a,)),
         "astype f32": (lambda a: np.sum(a.astype(onp.float32) ** 2), (a,)),
         "var/std": (lambda a: np.sum(np.var(a, axis=0)) + np.sum(np.std(a, axis=1)), (a,)),
     }
@@ -653,3 +674,45 @@ def case_gemm_split_k():
 
 
 OP_CASES["gemm_split_k"] = case_gemm_split_k
+
+
+def grad_case_systematic_ufuncs():
+    """Finite-difference checks (reference autograd/test_util.check_grads, rev + fwd mode, 2nd order) of the
+    elementwise rule table on the device type — the analogue of reference tests/test_systematic.py:51-243."""
+    import autograd.numpy as np
+    from autograd.test_util import check_grads
+
+    r = rs(60)
+    x = b200.asarray(r.randn(3, 4))
+    pos = b200.asarray(onp.abs(r.randn(3, 4)) + 0.5)
+    unit = b200.asarray(r.rand(3, 4) * 1.6 - 0.8)
+    y = b200.asarray(r.randn(4) + 3.0)
+    unary_any = [np.negative, np.exp, np.tanh, np.sinh, np.cosh, np.sin, np.cos, np.square, np.arctan, np.arcsinh,
+                 np.expm1, np.exp2, np.abs, lambda v: v ** 3, lambda v: np.where(v > 0, v, 0.5 * v)]
+    unary_pos = [np.log, np.log1p, np.log2, np.log10, np.sqrt, np.reciprocal, lambda v: v ** 0.5, lambda v: v ** -1.5,
+                 lambda v: 2.0 ** v, lambda v: np.mean(v, axis=0) * np.max(v, axis=1, keepdims=True)[:3, 0].sum()]
+    unary_unit = [np.arcsin, np.arccos, np.arctanh, np.tan]
+    for f in unary_any:
+        check_grads(f, modes=["rev", "fwd"], order=2)(x)
+    for f in unary_pos:
+        check_grads(f, modes=["rev", "fwd"], order=2)(pos)
+    for f in unary_unit:
+        check_grads(f, modes=["rev", "fwd"], order=2)(unit)
+    for f in (np.hypot, np.logaddexp):  # the reference defines no JVP for these (numpy_jvps.py): reverse mode only
+        check_grads(f, modes=["rev"], order=2)(pos, y)
+    binary = [np.add, np.subtract, np.multiply, np.true_divide, np.maximum, np.minimum, np.arctan2,
+              lambda a, b: a ** 2.0 * b, lambda a, b: np.dot(a, b), lambda a, b: np.sum(a * b, axis=1),
+              lambda a, b: np.einsum("ij,j->i", a, b), lambda a, b: np.tensordot(a, b, [[1], [0]])]
+    for f in binary:
+        check_grads(f, modes=["rev", "fwd"], order=2)(pos, y)
+    check_grads(np.power, modes=["rev", "fwd"], order=2)(pos, y / 3.0)
+    shape_fns = [lambda v: np.reshape(v, (4, 3)), lambda v: np.ravel(v), lambda v: v.T, lambda v: np.swapaxes(v, 0, 1),
+                 lambda v: np.roll(v, 2, axis=1), lambda v: np.concatenate([v, 2 * v], axis=0), lambda v: v[1:, ::2],
+                 lambda v: np.repeat(v, 2, axis=0), lambda v: np.expand_dims(v, 1), lambda v: np.sum(v, axis=(0, 1)),
+                 lambda v: np.pad(v, ((1, 0), (0, 2)), mode="constant"), lambda v: np.tile(v, (2, 1)),
+                 lambda v: np.hstack((v, v * v)), lambda v: np.broadcast_to(v[:1], (5, 4)), lambda v: np.clip(v, -0.5, 0.5)]
+    for f in shape_fns:
+        check_grads(f, modes=["rev", "fwd"], order=2)(x)
+
+
+GRAD_CASES["systematic_ufuncs"] = grad_case_systematic_ufuncs
