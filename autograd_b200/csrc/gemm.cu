@@ -225,7 +225,9 @@ extern "C" int b200ag_gemm(void* C, int c_dtype, int64_t c_rs, int64_t c_cs, int
   // Split-K: when the output has too few tiles to occupy 148 SMs (weight gradients: small M x N, long K), slices of
   // K go to different CTAs and are combined with FP64 atomics into a zeroed float64 accumulator.
   int64_t tiles = ((M + 63) / 64) * ((N + 63) / 64) * batch;
-  int64_t want = (3 * (int64_t)sm_count() + tiles - 1) / tiles;
+  // aim for ONE full wave: 3 CTAs of the 64x64 kernel are resident per SM (register-limited)
+  int64_t slots = 3 * (int64_t)sm_count();
+  int64_t want = slots / tiles;
   int64_t max_by_k = K / 128;
   int64_t splits = want < max_by_k ? want : max_by_k;
   if (splits > 64) splits = 64;
