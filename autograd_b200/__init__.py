@@ -16,6 +16,7 @@ from . import array, backend, lazy
 from .array import DeviceArray, asarray, to_device
 from .graph import capture
 from .install import host_arrays, install, is_installed
+from .pipeline import map_elementwise
 
 
 def synchronize() -> None:
@@ -26,5 +27,5 @@ def to_host(x):
     return x.get() if isinstance(x, DeviceArray) else x
 
 
-__all__ = ["capture", "host_arrays", "DeviceArray", "asarray", "to_device", "to_host", "install", "is_installed", "synchronize", "array",
+__all__ = ["map_elementwise", "capture", "host_arrays", "DeviceArray", "asarray", "to_device", "to_host", "install", "is_installed", "synchronize", "array",
            "backend", "lazy"]

@@ -43,6 +43,13 @@ PROTOTYPES = {
     "b200ag_event_synchronize": [C.c_void_p],
     "b200ag_event_elapsed_ms": [C.c_void_p, C.c_void_p, C.POINTER(C.c_float)],
     "b200ag_event_destroy": [C.c_void_p],
+    "b200ag_stream_create": [c_void_pp],
+    "b200ag_stream_destroy": [C.c_void_p],
+    "b200ag_stream_synchronize": [C.c_void_p],
+    "b200ag_event_record_on": [C.c_void_p, C.c_void_p],
+    "b200ag_stream_wait_event": [C.c_void_p, C.c_void_p],
+    "b200ag_memcpy_h2d_on": [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p],
+    "b200ag_memcpy_d2h_on": [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p],
     "b200ag_rtc_compile": [C.c_char_p, C.c_char_p, c_void_pp, c_size_p],
     "b200ag_rtc_free": [C.c_void_p],
     "b200ag_rtc_log": [C.POINTER(C.c_char_p)],

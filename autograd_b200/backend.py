@@ -136,6 +136,32 @@ class CudaBackend:
     def event_destroy(self, ev: int) -> None:
         self._check(self._lib.b200ag_event_destroy(ev))
 
+    # ------------------------------------------------------------ copy streams
+    def stream_create(self) -> int:
+        p = C.c_void_p()
+        self._check(self._lib.b200ag_stream_create(C.byref(p)))
+        return p.value
+
+    def stream_destroy(self, s: int) -> None:
+        self._check(self._lib.b200ag_stream_destroy(s))
+
+    def stream_synchronize(self, s) -> None:
+        self._check(self._lib.b200ag_stream_synchronize(s))
+
+    def event_record_on(self, ev: int, s) -> None:
+        self._check(self._lib.b200ag_event_record_on(ev, s))
+
+    def stream_wait_event(self, s, ev: int) -> None:
+        self._check(self._lib.b200ag_stream_wait_event(s, ev))
+
+    def h2d_on(self, ptr: int, host: np.ndarray, s) -> None:
+        assert host.flags.c_contiguous
+        self._check(self._lib.b200ag_memcpy_h2d_on(ptr, host.ctypes.data, host.nbytes, s))
+
+    def d2h_on(self, host: np.ndarray, ptr: int, s) -> None:
+        assert host.flags.c_contiguous
+        self._check(self._lib.b200ag_memcpy_d2h_on(host.ctypes.data, ptr, host.nbytes, s))
+
     # ------------------------------------------------------------ CUDA graphs
     def graph_begin(self) -> None:
         self._check(self._lib.b200ag_graph_begin())

@@ -311,6 +311,44 @@ int b200ag_event_destroy(void* ev) {
   return 0;
 }
 
+// ---------------------------------------------------------------- auxiliary copy streams (host<->device pipelining)
+int b200ag_stream_create(void** s) {
+  B200AG_CHECK_INIT();
+  cudaStream_t st;
+  B200AG_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  *s = (void*)st;
+  return 0;
+}
+int b200ag_stream_destroy(void* s) {
+  B200AG_CUDA(cudaStreamDestroy((cudaStream_t)s));
+  return 0;
+}
+int b200ag_stream_synchronize(void* s) {
+  B200AG_CUDA(cudaStreamSynchronize(s ? (cudaStream_t)s : g_stream));
+  return 0;
+}
+// s == NULL means the library's compute stream
+int b200ag_event_record_on(void* ev, void* s) {
+  B200AG_CUDA(cudaEventRecord((cudaEvent_t)ev, s ? (cudaStream_t)s : g_stream));
+  return 0;
+}
+int b200ag_stream_wait_event(void* s, void* ev) {
+  B200AG_CUDA(cudaStreamWaitEvent(s ? (cudaStream_t)s : g_stream, (cudaEvent_t)ev, 0));
+  return 0;
+}
+int b200ag_memcpy_h2d_on(void* dst, const void* src, size_t nbytes, void* s) {
+  B200AG_CHECK_INIT();
+  if (!nbytes) return 0;
+  B200AG_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyHostToDevice, s ? (cudaStream_t)s : g_stream));
+  return 0;
+}
+int b200ag_memcpy_d2h_on(void* dst, const void* src, size_t nbytes, void* s) {
+  B200AG_CHECK_INIT();
+  if (!nbytes) return 0;
+  B200AG_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToHost, s ? (cudaStream_t)s : g_stream));
+  return 0;
+}
+
 // ---------------------------------------------------------------- NVRTC
 int b200ag_rtc_compile(const char* src, const char* name, void** cubin, size_t* cubin_size) {
   nvrtcProgram prog;

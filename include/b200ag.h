@@ -75,6 +75,17 @@ int b200ag_event_synchronize(void* ev);
 int b200ag_event_elapsed_ms(void* start, void* stop, float* ms);
 int b200ag_event_destroy(void* ev);
 
+/* ---------------------------------------------------------------- copy streams
+ * Host<->device copies that overlap the compute stream (np.asarray uploads / .get() downloads of chunked
+ * elementwise workloads).  A NULL stream argument means the library's compute stream. */
+int b200ag_stream_create(void** stream);
+int b200ag_stream_destroy(void* stream);
+int b200ag_stream_synchronize(void* stream);
+int b200ag_event_record_on(void* ev, void* stream);
+int b200ag_stream_wait_event(void* stream, void* ev);
+int b200ag_memcpy_h2d_on(void* dst, const void* src, size_t nbytes, void* stream);  /* async; src should be pinned */
+int b200ag_memcpy_d2h_on(void* dst, const void* src, size_t nbytes, void* stream);  /* async; dst should be pinned */
+
 /* ---------------------------------------------------------------- generated elementwise kernels
  * Replaces NumPy ufunc inner loops (tracer.py:94 → numpy add/multiply/exp/...)
  * and the operator chains inside VJP closures (numpy_vjps.py:76-191).  The

@@ -163,6 +163,27 @@ class FakeBackend:
     def event_destroy(self, ev):
         pass
 
+    def stream_create(self):
+        return 1
+
+    def stream_destroy(self, s):
+        pass
+
+    def stream_synchronize(self, s):
+        pass
+
+    def event_record_on(self, ev, s):
+        self.event_record(ev)
+
+    def stream_wait_event(self, s, ev):
+        pass
+
+    def h2d_on(self, ptr, host, s):
+        self.h2d(ptr, host)
+
+    def d2h_on(self, host, ptr, s):
+        self.d2h(host, ptr)
+
     def graph_begin(self):
         raise RuntimeError("fake device: CUDA graphs need a GPU")
 
