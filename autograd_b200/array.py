@@ -468,33 +468,28 @@ to_device = asarray
 
 
 def pinned_empty(shape, dtype=float) -> np.ndarray:
-    """A numpy array backed by page-locked host memory (full-rate, truly asynchronous H2D/D2H copies)."""
+    """A numpy array backed by page-locked host memory (full-rate, truly asynchronous H2D/D2H copies).
+    The block lives until ``free_pinned(arr)`` (or process exit): views handed to NumPy must never dangle."""
     import ctypes
 
     shape = _shape_tuple(shape)
     dtype = np.dtype(dtype)
     nbytes = max(prod(shape) * dtype.itemsize, 1)
-    be = backend.get()
-    ptr = be.host_alloc(nbytes)
+    ptr = backend.get().host_alloc(nbytes)
     buf = (ctypes.c_char * nbytes).from_address(ptr)
     arr = np.frombuffer(buf, dtype=dtype, count=prod(shape)).reshape(shape)
-    _PINNED[id(buf)] = (buf, ptr)
-    import weakref
-
-    weakref.finalize(arr.base if arr.base is not None else arr, _release_pinned, id(buf), be)
+    _PINNED[ptr] = buf
     return arr
 
 
 _PINNED = {}
 
 
-def _release_pinned(key, be):
-    rec = _PINNED.pop(key, None)
-    if rec is not None:
-        try:
-            be.host_free(rec[1])
-        except Exception:
-            pass
+def free_pinned(arr: np.ndarray) -> None:
+    """Release a block obtained from ``pinned_empty`` (the caller guarantees no view of it is used afterwards)."""
+    ptr = arr.ctypes.data
+    if _PINNED.pop(ptr, None) is not None:
+        backend.get().host_free(ptr)
 
 
 def _shape_tuple(shape):

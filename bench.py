@@ -219,6 +219,7 @@ def run_b200(args):
         be.event_record(ev1)
         be.synchronize()
         _barrier(dist)
+        launches = be.launch_count() - l0
         if clocks.samples is not None and len(clocks.samples) < 3:
             # a short timed region can fall between two nvidia-smi polls: keep the same kernel running (untimed)
             # until a few samples under load exist
@@ -227,7 +228,6 @@ def run_b200(args):
                 f(x).materialize()
                 be.synchronize()
     ms = be.event_elapsed_ms(ev0, ev1)
-    launches = be.launch_count() - l0
     ms_per_step = _max_over_ranks(ms / args.steps, dist)
     value = world / (ms_per_step * 1e-3)
 
