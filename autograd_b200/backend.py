@@ -162,6 +162,27 @@ class CudaBackend:
         assert host.flags.c_contiguous
         self._check(self._lib.b200ag_memcpy_d2h_on(host.ctypes.data, ptr, host.nbytes, s))
 
+    # ------------------------------------------------------------ peer-memory allreduce
+    def comm_create(self, rank: int, world: int, slot_bytes: int) -> bytes:
+        h = C.create_string_buffer(64)
+        self._check(self._lib.b200ag_comm_create(rank, world, slot_bytes, h))
+        return h.raw
+
+    def comm_connect(self, handles: bytes) -> None:
+        buf = C.create_string_buffer(handles, len(handles))
+        self._check(self._lib.b200ag_comm_connect(buf))
+
+    def comm_allreduce_sum_f64(self, out: int, src: int, n: int) -> None:
+        self._check(self._lib.b200ag_comm_allreduce_sum_f64(out, src, n))
+
+    def comm_status(self) -> int:
+        v = C.c_int()
+        self._check(self._lib.b200ag_comm_status(C.byref(v)))
+        return v.value
+
+    def comm_destroy(self) -> None:
+        self._lib.b200ag_comm_destroy()
+
     # ------------------------------------------------------------ CUDA graphs
     def graph_begin(self) -> None:
         self._check(self._lib.b200ag_graph_begin())

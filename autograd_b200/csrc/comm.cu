@@ -1,0 +1,196 @@
+// One-shot sum-allreduce of small gradient vectors over NVLink peer memory (one process per GPU).
+//
+// The reference has no communication layer; BASELINE.json's north_star adds exactly one collective: the sum of
+// the batch-sharded gradient leaves (1.42 MB for the MLP, 355 KB for the convnet).  At that size an allreduce is
+// pure latency, so instead of a ring it is done in ONE kernel per rank: every rank publishes its vector in a
+// CUDA-IPC buffer, raises a flag in every peer, waits for the peers' flags, then READS all peer vectors through
+// NVLink (NVSwitch gives full bandwidth to every peer) and adds them in rank order — identical bits on all ranks.
+// The kernel carries its own epoch counter in device memory, so it can sit inside a replayed CUDA graph right
+// behind the last weight-gradient kernel.
+#include "common.cuh"
+
+namespace b200ag {
+
+struct PeerComm {
+  int rank = 0, world = 1;
+  size_t slot_bytes = 0;
+  unsigned char* local = nullptr;      // [2 slots][slot_bytes] data, then flags [2][world] u32, then epoch u32, status u32
+  unsigned char* peers[16] = {nullptr};
+  uint32_t* flags_of[16] = {nullptr};  // flags array inside each peer's block
+  size_t flags_off = 0;
+};
+static PeerComm g_comm;
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+struct AllreduceArgs {
+  double* out;
+  const double* peer_data[16];   // slot base of every rank's buffer (index = rank), as mapped in THIS process
+  uint32_t* peer_flags[16];      // flags array of every rank
+  uint32_t* my_flags;
+  uint32_t* epoch;               // device-resident call counter of this rank
+  uint32_t* status;              // set to 1 when a wait timed out
+  int64_t n;
+  int64_t slot_elems;
+  int rank, world;
+};
+
+// Copy this rank's vector into the slot the CURRENT epoch selects (epoch lives on the device: graph-replay safe).
+__global__ void __launch_bounds__(256) peer_publish_kernel(double* slots, const double* __restrict__ src, int64_t n,
+                                                            int64_t slot_elems, const uint32_t* epoch) {
+  double* dst = slots + (int64_t)(*epoch & 1) * slot_elems;
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) dst[i] = src[i];
+}
+
+__global__ void __launch_bounds__(256) peer_allreduce_kernel(AllreduceArgs a) {
+  __shared__ int ok;
+  const uint32_t epoch = *a.epoch;           // same value on every rank: each call advances every counter once
+  const int slot = epoch & 1;
+  if (threadIdx.x == 0) {
+    if (blockIdx.x == 0) {
+      __threadfence_system();                // this rank's vector (written by earlier kernels) is visible system-wide
+      for (int p = 0; p < a.world; ++p) st_release_sys(a.peer_flags[p] + slot * a.world + a.rank, epoch);
+    }
+    int good = 1;
+    for (int p = 0; p < a.world && good; ++p) {
+      const uint32_t* f = a.my_flags + slot * a.world + p;
+      long long spins = 0;
+      while (ld_acquire_sys(f) != epoch) {
+        if (++spins > 20000000LL) { good = 0; *a.status = 1; break; }   // ~ 2 s: a peer died; do not hang the GPU
+        __nanosleep(64);
+      }
+    }
+    ok = good;
+  }
+  __syncthreads();
+  if (ok) {
+    const int64_t off = (int64_t)slot * a.slot_elems;
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += step) {
+      double acc = 0.0;
+      for (int p = 0; p < a.world; ++p) acc += __ldcv(a.peer_data[p] + off + i);   // rank order: same bits everywhere
+      a.out[i] = acc;
+    }
+  }
+  // last block to finish advances the epoch (device-resident, so a replayed graph keeps counting)
+  __shared__ unsigned last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned done = atomicAdd(a.epoch + 2, 1u);   // epoch[2] = arrival counter
+    last = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    a.epoch[2] = 0;
+    a.epoch[0] = epoch + 1;
+  }
+}
+
+}  // namespace b200ag
+
+using namespace b200ag;
+
+extern "C" {
+
+// Allocate this rank's comm block (2 data slots + flags + counters) and return its 64-byte CUDA IPC handle.
+int b200ag_comm_create(int rank, int world, size_t slot_bytes, void* ipc_handle_out) {
+  B200AG_CHECK_INIT();
+  if (world < 1 || world > 16 || rank < 0 || rank >= world) B200AG_FAIL("comm_create: bad rank/world (max 16 ranks)");
+  if (g_comm.local) B200AG_FAIL("comm_create: already created");
+  slot_bytes = (slot_bytes + 255) & ~size_t(255);
+  size_t flags_off = 2 * slot_bytes;
+  size_t total = flags_off + 4096;
+  void* p = nullptr;
+  B200AG_CUDA(cudaMalloc(&p, total));
+  B200AG_CUDA(cudaMemset(p, 0, total));
+  g_comm.rank = rank; g_comm.world = world; g_comm.slot_bytes = slot_bytes; g_comm.flags_off = flags_off;
+  g_comm.local = (unsigned char*)p;
+  uint32_t one = 1;   // epoch starts at 1 so that zeroed flags never match
+  B200AG_CUDA(cudaMemcpy(g_comm.local + flags_off + 2048, &one, 4, cudaMemcpyHostToDevice));
+  cudaIpcMemHandle_t h;
+  B200AG_CUDA(cudaIpcGetMemHandle(&h, p));
+  memcpy(ipc_handle_out, &h, sizeof(h));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  return 0;
+}
+
+// Map every rank's comm block (handles = world x 64 bytes, in rank order).
+int b200ag_comm_connect(const void* handles) {
+  B200AG_CHECK_INIT();
+  if (!g_comm.local) B200AG_FAIL("comm_connect: call comm_create first");
+  for (int p = 0; p < g_comm.world; ++p) {
+    if (p == g_comm.rank) {
+      g_comm.peers[p] = g_comm.local;
+    } else {
+      cudaIpcMemHandle_t h;
+      memcpy(&h, (const unsigned char*)handles + 64 * p, 64);
+      void* q = nullptr;
+      B200AG_CUDA(cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess));
+      g_comm.peers[p] = (unsigned char*)q;
+    }
+    g_comm.flags_of[p] = (uint32_t*)(g_comm.peers[p] + g_comm.flags_off);
+  }
+  return 0;
+}
+
+// out[0:n] = sum over ranks of src[0:n] (float64).  src is first copied into this rank's published slot.
+int b200ag_comm_allreduce_sum_f64(void* out, const void* src, int64_t n) {
+  B200AG_CHECK_INIT();
+  if (!g_comm.local || !g_comm.peers[g_comm.world - 1]) B200AG_FAIL("comm_allreduce: communicator is not connected");
+  if ((size_t)n * 8 > g_comm.slot_bytes) B200AG_FAIL("comm_allreduce: message larger than the comm slot");
+  if (n == 0) return 0;
+  AllreduceArgs a;
+  a.out = (double*)out;
+  for (int p = 0; p < g_comm.world; ++p) {
+    a.peer_data[p] = (const double*)g_comm.peers[p];
+    a.peer_flags[p] = g_comm.flags_of[p];
+  }
+  a.my_flags = g_comm.flags_of[g_comm.rank];
+  a.epoch = (uint32_t*)(g_comm.local + g_comm.flags_off + 2048);
+  a.status = a.epoch + 1;
+  a.n = n;
+  a.slot_elems = (int64_t)(g_comm.slot_bytes / 8);
+  a.rank = g_comm.rank;
+  a.world = g_comm.world;
+  unsigned pgrid = (unsigned)((n + 1023) / 1024);
+  if (pgrid > 148) pgrid = 148;
+  peer_publish_kernel<<<pgrid, 256, 0, stream()>>>((double*)g_comm.local, (const double*)src, n, a.slot_elems, a.epoch);
+  B200AG_LAUNCH_CHECK();
+  unsigned grid = (unsigned)((n + 256 * 4 - 1) / (256 * 4));
+  if (grid > 64) grid = 64;
+  if (grid < 1) grid = 1;
+  peer_allreduce_kernel<<<grid, 256, 0, stream()>>>(a);
+  B200AG_LAUNCH_CHECK();
+  return 0;
+}
+
+int b200ag_comm_status(int* timed_out) {
+  B200AG_CHECK_INIT();
+  *timed_out = 0;
+  if (!g_comm.local) return 0;
+  uint32_t v = 0;
+  B200AG_CUDA(cudaMemcpy(&v, g_comm.local + g_comm.flags_off + 2048 + 4, 4, cudaMemcpyDeviceToHost));
+  *timed_out = (int)v;
+  return 0;
+}
+
+int b200ag_comm_destroy(void) {
+  if (!g_comm.local) return 0;
+  cudaStreamSynchronize(stream());
+  for (int p = 0; p < g_comm.world; ++p)
+    if (p != g_comm.rank && g_comm.peers[p]) cudaIpcCloseMemHandle(g_comm.peers[p]);
+  cudaFree(g_comm.local);
+  g_comm = PeerComm();
+  return 0;
+}
+
+}  // extern "C"

@@ -63,14 +63,41 @@ def _as_torch(x: DeviceArray):
     return torch.from_numpy(el[e0: e0 + x.size]).reshape(m.shape)
 
 
+_peer = {"ready": False, "slot_bytes": 0}
+
+
+def enable_peer_allreduce(max_bytes: int = 4 << 20) -> bool:
+    """Set up the one-kernel NVLink allreduce (csrc/comm.cu) for float64 vectors up to ``max_bytes``: every rank
+    allocates its comm block and the CUDA-IPC handles are exchanged through torch.distributed."""
+    if _pg is None or _pg.get_world_size() == 1 or backend.get().name != "cuda":
+        return False
+    if _peer["ready"]:
+        return True
+    be = backend.get()
+    world, r = _pg.get_world_size(), _pg.get_rank()
+    handle = be.comm_create(r, world, max_bytes)
+    gathered = [None] * world
+    _pg.all_gather_object(gathered, handle)
+    be.comm_connect(b"".join(gathered))
+    _pg.barrier()
+    _peer["ready"], _peer["slot_bytes"] = True, max_bytes
+    return True
+
+
 def allreduce_sum_(x: DeviceArray) -> DeviceArray:
-    """In-place sum over ranks of a materialised, contiguous array (ncclAllReduce on the library stream)."""
+    """In-place sum over ranks of a materialised, contiguous array: the one-kernel peer-memory allreduce when it is
+    enabled and the vector fits, otherwise ncclAllReduce on the library stream."""
     if _pg is None or _pg.get_world_size() == 1:
         return x
     import torch
 
     x._own_buffer()
     be = backend.get()
+    if _peer["ready"] and x.dtype == lazy.F64 and x.nbytes <= _peer["slot_bytes"]:
+        m = x._mat()
+        if m.is_contiguous:
+            be.comm_allreduce_sum_f64(m.ptr, m.ptr, x.size)
+            return x
     if be.name == "cuda":
         stream = torch.cuda.ExternalStream(be.stream_handle(), device=torch.device("cuda", be.device))
         with torch.cuda.stream(stream):

@@ -172,6 +172,16 @@ int b200ag_conv2d_wgrad(void* dB, const void* A, const void* G, int dtype,
                         int64_t N, int64_t C, int64_t H, int64_t W,
                         int64_t F, int64_t kh, int64_t kw);
 
+/* ---------------------------------------------------------------- gradient allreduce over NVLink peer memory
+ * Not in the reference (single process).  Sum of batch-sharded gradient vectors, one process per GPU: every rank
+ * publishes its vector in a CUDA-IPC buffer and one kernel per rank reads all peers through NVLink and adds them
+ * in rank order.  handles = world x 64-byte cudaIpcMemHandle_t, exchanged by the caller (torch.distributed). */
+int b200ag_comm_create(int rank, int world, size_t slot_bytes, void* ipc_handle_out);
+int b200ag_comm_connect(const void* handles);
+int b200ag_comm_allreduce_sum_f64(void* out, const void* src, int64_t n);
+int b200ag_comm_status(int* timed_out);
+int b200ag_comm_destroy(void);
+
 /* ---------------------------------------------------------------- CUDA graphs
  * Capture everything the library enqueues between begin and end (a recorded
  * forward+backward tape) and replay it with one launch (core.py:26-33 is the
