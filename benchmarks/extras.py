@@ -293,15 +293,35 @@ def c1_dp(be, world=1, rank=0):
     g = grad(w.mlp_objective)
     local = b200.capture(lambda p, x, t: bdist.flatten_tree(g(p, x, t, 1.0 / world)))
 
-    def step():
+    def step_nccl():
         flat = local(dp, dX, dT)
         bdist.allreduce_sum_(flat)
         return flat
 
+    peer = world > 1 and bdist.enable_peer_allreduce(4 << 20)
+    nccl_ms = None
+    if peer:
+        # baseline for comparison: the same step with the collective issued through NCCL after the graph
+        bdist._peer["ready"] = False
+        nccl_ms, _ = _dp_time(be, step_nccl, 50, world)
+        bdist._peer["ready"] = True
+
+        # product path: forward + backward + flatten + the one-kernel NVLink allreduce in ONE CUDA graph
+        def fused(p, x, t):
+            flat = bdist.flatten_tree(g(p, x, t, 1.0 / world)).materialize()
+            return bdist.allreduce_sum_(flat)
+
+        whole = b200.capture(fused)
+        step = lambda: whole(dp, dX, dT)
+    else:
+        step = step_nccl
     ms, launches = _dp_time(be, step, 50, world)
-    res = {"workload": f"C1 MLP grad, 256 rows per GPU x {world} GPUs, graph replay + 1 NCCL allreduce (1.42 MB f64)",
+    res = {"workload": f"C1 MLP grad, 256 rows per GPU x {world} GPUs, 1.42 MB f64 gradient allreduce per step",
+           "collective": "one-kernel NVLink peer-memory allreduce inside the replayed CUDA graph" if peer else
+                         ("ncclAllReduce after the replayed graph" if world > 1 else "none (1 GPU)"),
            "scaling": "weak", "ms_per_step": ms, "grad_evals_per_sec": world * 1e3 / ms,
-           "rows_per_sec": world * 256 * 1e3 / ms, "launches_per_step": launches}
+           "rows_per_sec": world * 256 * 1e3 / ms, "launches_per_step": launches,
+           "nccl_variant_ms_per_step": nccl_ms}
     # parity: the summed gradient equals the reference gradient of the concatenated batch
     flat = step().get()
     if rank == 0:
@@ -324,16 +344,25 @@ def c5_dp(be, world=1, rank=0, N=65536):
     _, X, T = w.convnet_data(per, n, seed=100 + rank)
     dW, dX, dT = b200.asarray(W), b200.asarray(X), b200.asarray(T)
     g = grad(loss)
-    local = b200.capture(lambda wv, x, t: g(wv, x, t, 1.0 / world))
+    peer = world > 1 and bdist.enable_peer_allreduce(4 << 20)
+
+    def fused(wv, x, t):
+        flat = g(wv, x, t, 1.0 / world).materialize()
+        return bdist.allreduce_sum_(flat) if peer else flat
+
+    local = b200.capture(fused)
 
     def step():
         flat = local(dW, dX, dT)
-        bdist.allreduce_sum_(flat)
+        if world > 1 and not peer:
+            bdist.allreduce_sum_(flat)
         return flat
 
     ms, launches = _dp_time(be, step, 5, world)
-    return {"workload": f"C5 convnet grad, {N} images split over {world} GPUs ({per} each), graph replay + 1 NCCL "
-                        f"allreduce (355 KB f64)", "scaling": "strong", "ms_per_step": ms,
+    return {"workload": f"C5 convnet grad, {N} images split over {world} GPUs ({per} each), 355 KB f64 gradient "
+                        f"allreduce per step", "collective": "one-kernel NVLink peer-memory allreduce inside the replayed "
+                        "CUDA graph" if peer else ("ncclAllReduce" if world > 1 else "none (1 GPU)"),
+            "scaling": "strong", "ms_per_step": ms,
             "grad_evals_per_sec": 1e3 / ms, "images_per_sec": per * world * 1e3 / ms, "launches_per_step": launches}
 
 

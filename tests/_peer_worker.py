@@ -29,7 +29,14 @@ for it in range(20):
     x = b200.asarray(all_vecs[rank] * (it + 1))
     dist.allreduce_sum_(x)
     got = x.get()
-    assert onp.array_equal(got, want * (it + 1)) or onp.allclose(got, want * (it + 1), rtol=1e-15, atol=0), f"iter {it}"
+    exp = onp.zeros(178110)
+    for v in all_vecs:
+        exp = exp + v * (it + 1)                              # same order, same roundings as the kernel
+    if not onp.array_equal(got, exp):
+        # diagnose: which multiple of each rank's vector did we actually sum?
+        A = onp.stack(all_vecs, axis=1)
+        coef = onp.linalg.lstsq(A[:2000], got[:2000], rcond=None)[0]
+        raise AssertionError(f"rank {rank} iter {it}: summed coefficients {coef} (expected {it + 1} each), status {be.comm_status()}")
 assert be.comm_status() == 0
 
 # 2. bit-identical across ranks
