@@ -72,12 +72,26 @@ __global__ void __launch_bounds__(256) peer_allreduce_kernel(AllreduceArgs a) {
   }
   __syncthreads();
   if (ok) {
+    // every thread owns ONE pair of doubles (grid sized to the vector): a single NVLink round trip, all peer loads
+    // of a thread issued back to back, summed in rank order so every rank produces the same bits
     const int64_t off = (int64_t)slot * a.slot_elems;
     const int64_t step = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += step) {
+    const int64_t npairs = a.n >> 1;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += step) {
+      double2 v[16];
+#pragma unroll
+      for (int p = 0; p < 16; ++p)
+        if (p < a.world) v[p] = __ldcv(reinterpret_cast<const double2*>(a.peer_data[p] + off) + i);
+      double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+      for (int p = 0; p < 16; ++p)
+        if (p < a.world) { acc.x += v[p].x; acc.y += v[p].y; }
+      reinterpret_cast<double2*>(a.out)[i] = acc;
+    }
+    if ((a.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
       double acc = 0.0;
-      for (int p = 0; p < a.world; ++p) acc += __ldcv(a.peer_data[p] + off + i);   // rank order: same bits everywhere
-      a.out[i] = acc;
+      for (int p = 0; p < a.world; ++p) acc += __ldcv(a.peer_data[p] + off + a.n - 1);
+      a.out[a.n - 1] = acc;
     }
   }
   // last block to finish advances the epoch (device-resident, so a replayed graph keeps counting)
@@ -165,8 +179,10 @@ int b200ag_comm_allreduce_sum_f64(void* out, const void* src, int64_t n) {
   if (pgrid > 148) pgrid = 148;
   peer_publish_kernel<<<pgrid, 256, 0, stream()>>>((double*)g_comm.local, (const double*)src, n, a.slot_elems, a.epoch);
   B200AG_LAUNCH_CHECK();
-  unsigned grid = (unsigned)((n + 256 * 4 - 1) / (256 * 4));
-  if (grid > 64) grid = 64;
+  if (((uintptr_t)out & 15) != 0) B200AG_FAIL("comm_allreduce: output must be 16-byte aligned");
+  unsigned grid = (unsigned)((n / 2 + 255) / 256);
+  unsigned cap = (unsigned)sm_count() * 4;   // all CTAs are resident: they only wait on remote flags, never on each other
+  if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
   peer_allreduce_kernel<<<grid, 256, 0, stream()>>>(a);
   B200AG_LAUNCH_CHECK();

@@ -168,7 +168,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
     return 0
 
 
@@ -341,13 +341,28 @@ def run_b200(args):
         from benchmarks import extras
 
         line["other_configs"] = {**extras.run(be), **(dp_results or {})}
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if dist is not None:
         dist.barrier()
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def _emit(line: dict) -> None:
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    # stdout must carry exactly ONE JSON line; native libraries (NCCL prints its version banner) write to fd 1
+    # directly, so everything else is sent to stderr and the JSON goes to a private duplicate of the real stdout
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
