@@ -446,7 +446,7 @@ def _upload(host: np.ndarray) -> DeviceArray:
             host = host.astype(np.int64)
         else:
             backend.dtype_code(host.dtype)
-    host = np.ascontiguousarray(host)
+    host = np.asarray(host, order="C")
     m = Mat.empty(host.shape, host.dtype, upload=True)
     if host.size:
         backend.get().h2d(m.ptr, host)

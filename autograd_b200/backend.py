@@ -74,7 +74,7 @@ class CudaBackend:
         self._lib.b200ag_free(ptr)
 
     def h2d(self, ptr: int, host: np.ndarray) -> None:
-        host = np.ascontiguousarray(host)
+        host = np.asarray(host, order="C")
         self._check(self._lib.b200ag_memcpy_h2d(ptr, host.ctypes.data, host.nbytes))
 
     def d2h(self, host: np.ndarray, ptr: int) -> None:

@@ -103,7 +103,7 @@ class CapturedFunction:
             if sm.ptr != dm.ptr:
                 be.d2d(dm.ptr, sm.ptr, src.nbytes)
         else:
-            be.h2d(dm.ptr, np.ascontiguousarray(src, dtype=dm.dtype))
+            be.h2d(dm.ptr, np.asarray(src, dtype=dm.dtype, order="C"))
 
     def _record(self, be, args, leaves):
         # 1. eager warm-up: compiles/loads every kernel the tape needs, sizes the caches

@@ -18,7 +18,7 @@ from .lazy import Mat
 
 def map_elementwise(fn, x_host: np.ndarray, out: np.ndarray | None = None, chunk: int = 1 << 25) -> np.ndarray:
     be = backend.get()
-    x_flat = np.ascontiguousarray(x_host).reshape(-1)
+    x_flat = np.asarray(x_host, order="C").reshape(-1)
     n = x_flat.size
     chunk = min(chunk, n)
     nchunks = (n + chunk - 1) // chunk

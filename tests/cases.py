@@ -190,6 +190,8 @@ def case_large_vector_tail():
 
 # =============================================================== layout
 def case_views():
+    assert b200.asarray(onp.float64(3.5)).shape == () and b200.asarray(onp.array(2.0)).get().shape == ()
+    assert b200.asarray(onp.zeros((0, 3))).shape == (0, 3) and b200.asarray(onp.zeros((0, 3))).get().shape == (0, 3)
     r = rs(8)
     a = r.randn(6, 8, 10)
     check(lambda a: a.T + 1.0, a, tol=0, what="T")
@@ -421,13 +423,25 @@ def case_einsum():
 
 
 def case_conv2d():
+    from autograd import grad
     from autograd.scipy.signal import convolve
 
+    import autograd.numpy as np
+
     r = rs(16)
-    A, B = r.randn(5, 3, 12, 10), r.randn(3, 4, 5, 3)
-    for mode in ("valid", "full"):
-        check(lambda A, B: convolve(A, B, axes=([2, 3], [2, 3]), dot_axes=([1], [0]), mode=mode), A, B,
-              tol=TOL_REDUCE, what=f"convolve {mode}")
+    shapes = [((5, 3, 12, 10), (3, 4, 5, 3)), ((9, 1, 28, 28), (1, 6, 5, 5)), ((17, 6, 12, 12), (6, 16, 5, 5)),
+              ((3, 2, 7, 9), (2, 8, 3, 3)), ((4, 5, 6, 6), (5, 3, 1, 1)), ((2, 3, 9, 8), (3, 20, 3, 2)),
+              ((33, 4, 11, 13), (4, 9, 4, 6)), ((1, 1, 5, 5), (1, 1, 5, 5))]
+    for a_shape, b_shape in shapes:
+        A, B = r.randn(*a_shape), r.randn(*b_shape)
+        for mode in ("valid", "full"):
+            check(lambda A, B: convolve(A, B, axes=([2, 3], [2, 3]), dot_axes=([1], [0]), mode=mode), A, B,
+                  tol=TOL_REDUCE, what=f"convolve {mode} {a_shape}*{b_shape}")
+        # both VJPs (input-gradient = full correlation, weight-gradient = batch-summed valid correlation)
+        Wt = r.randn(a_shape[0], b_shape[1], a_shape[2] - b_shape[2] + 1, a_shape[3] - b_shape[3] + 1)
+        loss = lambda A, B, Wt: np.sum(convolve(A, B, axes=([2, 3], [2, 3]), dot_axes=([1], [0]), mode="valid") * Wt)
+        for argnum in (0, 1):
+            check_grad(loss, (A, B, Wt), TOL_REDUCE, f"convolve vjp arg{argnum} {a_shape}*{b_shape}", argnum)
 
 
 # =============================================================== registries exposed to the test modules
@@ -716,3 +730,78 @@ def grad_case_systematic_ufuncs():
 
 
 GRAD_CASES["systematic_ufuncs"] = grad_case_systematic_ufuncs
+
+
+def grad_case_optimizers():
+    """autograd.misc.optimizers on device parameters — the Adam/SGD/RMSprop updates are plain
+    elementwise expressions, so each iteration's update is fused into the kernels that consume it."""
+    from autograd.misc.optimizers import adam, rmsprop, sgd
+
+    from examples import workloads as w
+
+    params, X, T = w.mlp_data(batch=16, layer_sizes=(12, 10, 8, 5))
+
+    def run(opt, to_dev_fn, **kw):
+        p0 = to_dev_fn(params)
+        Xd, Td = to_dev_fn(X), to_dev_fn(T)
+        from autograd import grad
+
+        g = grad(lambda p, i: w.mlp_objective(p, Xd, Td, 0.1))
+        return opt(g, p0, num_iters=5, **kw)
+
+    for opt, kw in ((adam, {"step_size": 0.01}), (sgd, {"step_size": 0.001, "mass": 0.9}), (rmsprop, {"step_size": 0.01})):
+        want = _ref(run, opt, lambda t: t, **kw)
+        got = to_host(run(opt, to_dev, **kw))
+        for a, r in zip(leaves(got), leaves(want)):
+            assert_close(a, r, 1e-9, f"{opt.__name__} after 5 iterations")
+
+
+def grad_case_forward_mode_operators():
+    """make_jvp / deriv / hessian-vector / Gauss-Newton products on the device type."""
+    import autograd.numpy as np
+    from autograd import deriv, hessian_tensor_product, make_ggnvp, make_jvp, tensor_jacobian_product
+    from autograd.differential_operators import make_jvp_reversemode
+
+    r = rs(70)
+    x, v = r.randn(6), r.randn(6)
+    A = r.randn(4, 6)
+    f = lambda x: np.tanh(np.dot(A_, x)) * np.sum(x ** 2)
+
+    def both(fn):
+        global A_
+        return None
+
+    def eval_pair(builder):
+        """builder(A, x, v) -> value; evaluated on host (reference) and on device."""
+        want = _ref(builder, A, x, v)
+        got = builder(b200.asarray(A), b200.asarray(x), b200.asarray(v))
+        return to_host(got), want
+
+    def jvp_case(A, x, v):
+        val, tangent = make_jvp(lambda x: np.tanh(np.dot(A, x)) * np.sum(x ** 2))(x)(v)
+        return [val, tangent]
+
+    def jvp_rev_case(A, x, v):
+        return make_jvp_reversemode(lambda x: np.tanh(np.dot(A, x)))(x)(v)
+
+    def hvp_case(A, x, v):
+        return hessian_tensor_product(lambda x: np.sum(np.tanh(np.dot(A, x)) ** 2))(x, v)
+
+    def ggnvp_case(A, x, v):
+        return make_ggnvp(lambda x: np.tanh(np.dot(A, x)))(x)(v)
+
+    def tjp_case(A, x, v):
+        return tensor_jacobian_product(lambda x: np.tanh(np.dot(A, x)))(x, np.dot(A, v))
+
+    def deriv_case(A, x, v):
+        return deriv(lambda t: np.sum(np.sin(t * x)))(0.7)
+
+    for name, case in (("make_jvp", jvp_case), ("make_jvp_reversemode", jvp_rev_case), ("hessian_tensor_product", hvp_case),
+                       ("make_ggnvp", ggnvp_case), ("tensor_jacobian_product", tjp_case), ("deriv", deriv_case)):
+        got, want = eval_pair(case)
+        for a, r_ in zip(leaves(got), leaves(want)):
+            assert_close(onp.asarray(a), onp.asarray(r_), TOL_REDUCE, name)
+
+
+GRAD_CASES["optimizers"] = grad_case_optimizers
+GRAD_CASES["forward_mode_operators"] = grad_case_forward_mode_operators

@@ -105,7 +105,7 @@ class FakeBackend:
         return el, idx
 
     def h2d(self, ptr, host):
-        host = np.ascontiguousarray(host)
+        host = np.asarray(host, order="C")
         buf, off = self._resolve(ptr)
         buf[off: off + host.nbytes] = host.reshape(-1).view(np.uint8)
 
