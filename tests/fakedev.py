@@ -54,6 +54,7 @@ class FakeBackend:
             os.path.join(os.path.dirname(__file__), "..", "autograd_b200", "libb200ag.so"))
         self.in_use = 0
         self.peak = 0
+        self._host = {}
 
     # ------------------------------------------------------------ memory
     def malloc(self, nbytes):
@@ -123,10 +124,12 @@ class FakeBackend:
         buf[off: off + nbytes] = byte
 
     def host_alloc(self, nbytes):
-        return self.malloc(nbytes)
+        arr = np.zeros(max(int(nbytes), 1), dtype=np.uint8)   # "pinned" memory must be REAL host memory
+        self._host[arr.ctypes.data] = arr
+        return arr.ctypes.data
 
     def host_free(self, ptr):
-        self.free(ptr)
+        self._host.pop(ptr, None)
 
     def mem_stats(self):
         s = {"in_use": self.in_use, "cached": 0, "peak_in_use": self.peak}
