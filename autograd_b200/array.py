@@ -1021,6 +1021,74 @@ def pad(array, pad_width, mode="constant", **kwargs):
     return out
 
 
+
+# =================================================================== triangular / diagonal helpers (views + masks)
+def _tri_mask(shape, k, lower):
+    n, m = shape[-2], shape[-1]
+    mask = np.tri(n, m, k=k, dtype=bool) if lower else ~np.tri(n, m, k=k - 1, dtype=bool)
+    return _upload(mask)
+
+
+def tril(m, k=0):
+    m = asarray(m)
+    return where(_tri_mask(m.shape, k, True), m, zeros((), m.dtype))
+
+
+def triu(m, k=0):
+    m = asarray(m)
+    return where(_tri_mask(m.shape, k, False), m, zeros((), m.dtype))
+
+
+def diagonal(a, offset=0, axis1=0, axis2=1):
+    a = asarray(a)
+    axis1, axis2 = _normalize_axis(axis1, a.ndim), _normalize_axis(axis2, a.ndim)
+    mt = a._mat()
+    if mt.shifts is not None:
+        mt = a._cmat()
+    n1, n2 = mt.shape[axis1], mt.shape[axis2]
+    s1, s2 = mt.strides[axis1], mt.strides[axis2]
+    if offset >= 0:
+        length, start = max(0, min(n1, n2 - offset)), offset * s2
+    else:
+        length, start = max(0, min(n1 + offset, n2)), -offset * s1
+    keep = [i for i in range(a.ndim) if i not in (axis1, axis2)]
+    shape = tuple(mt.shape[i] for i in keep) + (length,)
+    strides = tuple(mt.strides[i] for i in keep) + (s1 + s2,)
+    return DeviceArray(lazy.leaf(Mat(mt.buf, shape, strides, mt.offset + start, mt.dtype)))
+
+
+def diag(v, k=0):
+    v = asarray(v)
+    if v.ndim == 2:
+        return diagonal(v, k)
+    if v.ndim != 1:
+        raise ValueError("Input must be 1- or 2-d.")
+    n = v.shape[0] + abs(k)
+    out = zeros((n, n), v.dtype)
+    out._own_buffer()
+    dview = diagonal(out, k)
+    m, src = dview._mat(), v._mat() if v._node.mat is not None and v._mat().shifts is None else v._cmat()
+    backend.get().copy_strided(m.ptr, m.dtype, m.strides, src.ptr, src.dtype, src.strides, m.shape)
+    return out
+
+
+def trace(a, offset=0, axis1=0, axis2=1, dtype=None, out=None):
+    return reduce_(diagonal(a, offset, axis1, axis2), "sum", -1, False, dtype)
+
+
+def diff(a, n=1, axis=-1, prepend=None, append=None):
+    if prepend is not None or append is not None:
+        raise NotImplementedError("autograd_b200: np.diff prepend/append are not supported")
+    a = asarray(a)
+    axis = _normalize_axis(axis, a.ndim)
+    for _ in range(n):
+        hi = [slice(None)] * a.ndim
+        lo = [slice(None)] * a.ndim
+        hi[axis], lo[axis] = slice(1, None), slice(None, -1)
+        a = a[tuple(hi)] - a[tuple(lo)]
+    return a
+
+
 # =================================================================== indexing
 def _parse_index(shape, idx):
     """Classify ``idx``: ("basic", [(kind, ...)]) or ("adv", (index arrays, index shape, n leading dims))."""
@@ -1652,6 +1720,7 @@ FUNCTIONS = {
     np.copy: lambda a, **kw: asarray(a).copy(),
     np.astype: lambda a, dtype, copy=True, **kw: asarray(a).astype(dtype),
     np.meshgrid: meshgrid, np.linspace: linspace,
+    np.tril: tril, np.triu: triu, np.diag: diag, np.diagonal: diagonal, np.trace: trace, np.diff: diff,
 }
 # NumPy's own pure-Python implementations of these only call other dispatched functions.
 DECOMPOSE = {np.hstack, np.vstack, np.dstack, np.column_stack, np.atleast_3d, np.rot90, np.kron,

@@ -16,7 +16,7 @@ from .array import DeviceArray, pinned_empty
 from .lazy import Mat
 
 
-def map_elementwise(fn, x_host: np.ndarray, out: np.ndarray | None = None, chunk: int = 1 << 25) -> np.ndarray:
+def map_elementwise(fn, x_host: np.ndarray, out: np.ndarray | None = None, chunk: int = 1 << 23) -> np.ndarray:
     be = backend.get()
     x_flat = np.asarray(x_host, order="C").reshape(-1)
     n = x_flat.size

@@ -256,6 +256,18 @@ def case_row_mode_layouts():
     check(lambda cx, v: (cx - v, onp.floor(cx - v).astype(int) % 40), cx, v, tol=0, what="meshgrid broadcast views")
 
 
+def case_tri_diag():
+    r = rs(31)
+    a, v = r.randn(6, 7), r.randn(5)
+    check(lambda a: (onp.tril(a), onp.triu(a), onp.tril(a, -1), onp.triu(a, 2)), a, tol=0, what="tril/triu")
+    check(lambda a: (onp.diag(a), onp.diag(a, 1), onp.diag(a, -2), onp.diagonal(a.T, 1)), a, tol=0, what="diag of matrix")
+    check(lambda v: (onp.diag(v), onp.diag(v, 2), onp.diag(v, -1)), v, tol=0, what="diag of vector")
+    check(lambda a: (onp.trace(a), onp.trace(a, 1)), a, tol=TOL_REDUCE, what="trace")
+    check(lambda a: (onp.diff(a), onp.diff(a, axis=0), onp.diff(a, n=2, axis=1)), a, tol=0, what="diff")
+    t = r.randn(3, 4, 5)
+    check(lambda t: onp.diagonal(t, 0, 1, 2), t, tol=0, what="diagonal of 3-D")
+
+
 def case_concat_repeat_pad():
     r = rs(10)
     a, b, c = r.randn(4, 5), r.randn(3, 5), r.randn(4, 2)
@@ -455,6 +467,7 @@ OP_CASES = {
     "vector_tail": case_large_vector_tail,
     "views": case_views,
     "roll": case_roll,
+    "tri_diag": case_tri_diag,
     "row_mode_layouts": case_row_mode_layouts,
     "concat_repeat_pad": case_concat_repeat_pad,
     "indexing": case_indexing,
@@ -611,6 +624,9 @@ def grad_case_vjp_rules():
         "einsum naked sum": (lambda a: np.sum(np.einsum("ij->j", a) ** 2), (a,)),
         "astype f32": (lambda a: np.sum(a.astype(onp.float32) ** 2), (a,)),
         "var/std": (lambda a: np.sum(np.var(a, axis=0)) + np.sum(np.std(a, axis=1)), (a,)),
+        "triu/tril/diag/trace": (lambda a: np.sum(np.triu(a) ** 2) + np.sum(np.tril(a, -1) * 3) + np.sum(np.diag(a[:5, :5]) ** 3)
+                                 + np.trace(a[:5, :5]) ** 2, (a,)),
+        "diff": (lambda a: np.sum(np.diff(a, axis=0) ** 2), (a,)),
     }
     for name, (fn, args) in fns.items():
         for argnum in range(len(args)):
