@@ -76,8 +76,9 @@ class CapturedFunction:
     """``fn`` replayed as a CUDA graph.  Returned arrays are owned by the recording and are overwritten by
     the next call with the same signature (copy them if they must survive)."""
 
-    def __init__(self, fn):
+    def __init__(self, fn, copy_inputs: bool = True):
         self.fn = fn
+        self.copy_inputs = copy_inputs   # False: bake the caller's own input buffers into the graph (pipelines)
         self._recordings = {}
 
     def __call__(self, *args):
@@ -119,7 +120,7 @@ class CapturedFunction:
         static = []
         for leaf in leaves:
             d = asarray(leaf)
-            static.append(d.copy() if isinstance(leaf, DeviceArray) else d)
+            static.append(d.copy() if isinstance(leaf, DeviceArray) and self.copy_inputs else d)
         be.synchronize()
         static_args = _rebuild(args, iter(static))
         # 3. capture the same call
@@ -144,6 +145,6 @@ class CapturedFunction:
         return {k: r.nodes for k, r in self._recordings.items()}
 
 
-def capture(fn):
+def capture(fn, copy_inputs: bool = True):
     """Wrap ``fn`` (typically ``grad(f)`` / ``value_and_grad(f)``) so that repeated calls replay a CUDA graph."""
-    return CapturedFunction(fn)
+    return CapturedFunction(fn, copy_inputs)

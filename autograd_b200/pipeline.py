@@ -16,7 +16,12 @@ from .array import DeviceArray, pinned_empty
 from .lazy import Mat
 
 
-def map_elementwise(fn, x_host: np.ndarray, out: np.ndarray | None = None, chunk: int = 1 << 23) -> np.ndarray:
+def map_elementwise(fn, x_host: np.ndarray, out: np.ndarray | None = None, chunk: int = 1 << 23,
+                    replay: bool = True) -> np.ndarray:
+    """``replay=True`` records ``fn`` once per buffer slot as a CUDA graph (the trace must not depend on values),
+    so a chunk costs one graph launch instead of a re-trace through autograd and small chunks stay efficient."""
+    from .graph import CapturedFunction
+
     be = backend.get()
     x_flat = np.asarray(x_host, order="C").reshape(-1)
     n = x_flat.size
@@ -24,11 +29,14 @@ def map_elementwise(fn, x_host: np.ndarray, out: np.ndarray | None = None, chunk
     nchunks = (n + chunk - 1) // chunk
     up, down = be.stream_create(), be.stream_create()
     in_bufs = [Mat.empty((chunk,), x_flat.dtype) for _ in range(2)]
+    in_arrays = {}                                      # (slot, m) -> DeviceArray over the slot's first m elements
+    fast = [CapturedFunction(fn, copy_inputs=False) if replay else fn for _ in range(2)]
     ev_in = [be.event_create() for _ in range(2)]      # upload of slot finished
     ev_free = [be.event_create() for _ in range(2)]    # compute no longer reads slot
     ev_done = [be.event_create() for _ in range(2)]    # result of slot computed
     ev_out = [be.event_create() for _ in range(2)]     # download of slot finished
     results = [None, None]
+    busy = [False, False]
     out_flat = None
     try:
         for i in range(nchunks):
@@ -40,8 +48,16 @@ def map_elementwise(fn, x_host: np.ndarray, out: np.ndarray | None = None, chunk
             be.h2d_on(in_bufs[s].ptr, x_flat[lo:hi], up)
             be.event_record_on(ev_in[s], up)
             be.stream_wait_event(None, ev_in[s])
-            xin = DeviceArray(lazy.leaf(Mat(in_bufs[s].buf, (m,), (1,), 0, x_flat.dtype)))
-            y = fn(xin)
+            xin = in_arrays.get((s, m))
+            if xin is None:
+                xin = DeviceArray(lazy.leaf(Mat(in_bufs[s].buf, (m,), (1,), 0, x_flat.dtype)))
+                in_arrays[(s, m)] = xin
+            if busy[s]:
+                if replay:
+                    be.stream_wait_event(None, ev_out[s])       # the replay overwrites the slot's output buffer
+                else:
+                    be.event_synchronize(ev_out[s])             # its download is done: the buffer may be recycled
+            y = fast[s](xin)
             ym = y._cmat()
             be.event_record_on(ev_free[s], None)
             be.event_record_on(ev_done[s], None)
@@ -51,18 +67,19 @@ def map_elementwise(fn, x_host: np.ndarray, out: np.ndarray | None = None, chunk
                 out_flat = out.reshape(-1)
                 if out_flat.size != n or not out.flags.c_contiguous:
                     raise ValueError("map_elementwise: out must be a C-contiguous array with as many elements as x")
-            if results[s] is not None:
-                be.event_synchronize(ev_out[s])                 # its download is done: the buffer may be recycled
             results[s] = ym
+            busy[s] = True
             be.stream_wait_event(down, ev_done[s])
             be.d2h_on(out_flat[lo:hi], ym.ptr, down)
             be.event_record_on(ev_out[s], down)
-            del xin, y
+            del y
         be.stream_synchronize(down)
         be.stream_synchronize(up)
         be.synchronize()
     finally:
         results[:] = [None, None]
+        in_arrays.clear()
+        fast[:] = [None, None]
         for evs in (ev_in, ev_free, ev_done, ev_out):
             for e in evs:
                 be.event_destroy(e)

@@ -6,7 +6,7 @@ import pytest
 import cases
 
 
-def _check():
+def _check(replay):
     import autograd_b200 as b200
 
     from examples import workloads as w
@@ -16,17 +16,18 @@ def _check():
     with b200.host_arrays():
         want = f(x)
     for chunk in (1 << 14, 30000, 1 << 20):
-        got = b200.map_elementwise(f, x, chunk=chunk)
+        got = b200.map_elementwise(f, x, chunk=chunk, replay=replay)
         cases.assert_close(got, want, cases.TOL_ELEMENTWISE, f"map_elementwise chunk={chunk}")
     out = onp.empty_like(x)
-    res = b200.map_elementwise(lambda v: v * 2.0 + 1.0, x, out=out, chunk=4096)
+    res = b200.map_elementwise(lambda v: v * 2.0 + 1.0, x, out=out, chunk=4096, replay=replay)
     assert res is out and onp.array_equal(out, x * 2.0 + 1.0)
 
 
 def test_map_elementwise_host_logic(fake_dev):
-    _check()
+    _check(False)
 
 
 @pytest.mark.gpu
-def test_map_elementwise_gpu(cuda_dev):
-    _check()
+@pytest.mark.parametrize("replay", [False, True])
+def test_map_elementwise_gpu(cuda_dev, replay):
+    _check(replay)
