@@ -16,6 +16,9 @@ from .array import DeviceArray, pinned_empty
 from .lazy import Mat
 
 
+_STATE = {}
+
+
 def map_elementwise(fn, x_host: np.ndarray, out: np.ndarray | None = None, chunk: int = 1 << 23,
                     replay: bool = True) -> np.ndarray:
     """``replay=True`` records ``fn`` once per buffer slot as a CUDA graph (the trace must not depend on values),
@@ -28,9 +31,16 @@ def map_elementwise(fn, x_host: np.ndarray, out: np.ndarray | None = None, chunk
     chunk = min(chunk, n)
     nchunks = (n + chunk - 1) // chunk
     up, down = be.stream_create(), be.stream_create()
-    in_bufs = [Mat.empty((chunk,), x_flat.dtype) for _ in range(2)]
-    in_arrays = {}                                      # (slot, m) -> DeviceArray over the slot's first m elements
-    fast = [CapturedFunction(fn, copy_inputs=False) if replay else fn for _ in range(2)]
+    # staging buffers and recorded graphs are kept per (function, chunk, dtype): a second call replays immediately
+    key = (id(fn), chunk, x_flat.dtype.char, replay)
+    state = _STATE.get(key)
+    if state is None or state[0] is not fn:
+        state = (fn, [Mat.empty((chunk,), x_flat.dtype) for _ in range(2)], {},
+                 [CapturedFunction(fn, copy_inputs=False) if replay else fn for _ in range(2)])
+        if len(_STATE) >= 8:
+            _STATE.pop(next(iter(_STATE)))
+        _STATE[key] = state
+    _, in_bufs, in_arrays, fast = state   # in_arrays: (slot, m) -> DeviceArray over the slot's first m elements
     ev_in = [be.event_create() for _ in range(2)]      # upload of slot finished
     ev_free = [be.event_create() for _ in range(2)]    # compute no longer reads slot
     ev_done = [be.event_create() for _ in range(2)]    # result of slot computed
@@ -78,8 +88,6 @@ def map_elementwise(fn, x_host: np.ndarray, out: np.ndarray | None = None, chunk
         be.synchronize()
     finally:
         results[:] = [None, None]
-        in_arrays.clear()
-        fast[:] = [None, None]
         for evs in (ev_in, ev_free, ev_done, ev_out):
             for e in evs:
                 be.event_destroy(e)
