@@ -72,7 +72,7 @@ def test_copy_strided_transpose_and_cast(abi):
     a = rs.randn(37, 53)
     src = abi.put(a)
     dst = abi.empty(a.size * 8)
-    abi.ok(abi.lib.b200ag_copy_strided(dst, F64, i64(37, 1), src, F64, i64(53, 1), i64(37, 53), 2))  # dst = a.T laid out [53,37]
+    abi.ok(abi.lib.b200ag_copy_strided(dst, F64, i64(1, 37), src, F64, i64(53, 1), i64(37, 53), 2))  # element (r,c) -> dst[c*37 + r]: a.T laid out [53,37]
     assert np.array_equal(abi.get(dst, (53, 37), np.float64), a.T)
     dst32 = abi.empty(a.size * 4)
     abi.ok(abi.lib.b200ag_copy_strided(dst32, F32, i64(53, 1), src, F64, i64(53, 1), i64(37, 53), 2))
