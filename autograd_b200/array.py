@@ -122,7 +122,8 @@ class DeviceArray:
     def __array__(self, dtype=None, copy=None):
         raise TypeError(
             "autograd_b200.DeviceArray refuses implicit conversion to a host numpy array "
-            "(it would hide a device→host copy); call .get() explicitly."
+            "(it would hide a device→host copy); call .get() explicitly.  If this came from a SciPy/NumPy function that "
+            "autograd wraps, make sure autograd_b200.install() has run."
         )
 
     def __float__(self):

@@ -60,6 +60,16 @@ def _on_device(*xs) -> bool:
     return False
 
 
+def _swap_raw(prim, new_raw):
+    """Replace the raw function a ``primitive`` wrapper calls (tracer.py:94 ``f_raw``) IN PLACE, so that references to
+    the primitive taken before install() — ``from autograd.scipy.special import logsumexp`` at the top of
+    examples/neural_net.py:12 — dispatch to the device as well.  The primitive object, and therefore every VJP/JVP
+    registered for it, stays the same."""
+    idx = prim.__code__.co_freevars.index("f_raw")
+    prim.__closure__[idx].cell_contents = new_raw
+    prim.fun = new_raw
+
+
 def install(creation: bool = True):
     """Register DeviceArray with autograd.  Idempotent."""
     global _installed, DeviceArrayBox, DeviceVSpace
@@ -200,23 +210,20 @@ def install(creation: bool = True):
     def_linear(dev_dot_adjoint_1)
 
     # ------------------------------------------------------------ logsumexp (scipy/special.py:120-147)
-    ref_logsumexp = aspecial.logsumexp
+    scipy_logsumexp = aspecial.logsumexp.fun
 
     def _logsumexp_raw(x, axis=None, b=None, keepdims=False, return_sign=False):
         if isinstance(x, DeviceArray):
             if b is not None and not (isinstance(b, float) and b == 1.0):
                 raise NotImplementedError("autograd_b200: logsumexp with weights b is not implemented on device")
             return A.logsumexp(x, axis=axis, keepdims=keepdims, return_sign=return_sign)
-        return ref_logsumexp.fun(x, axis=axis, b=b, keepdims=keepdims, return_sign=return_sign)
+        return scipy_logsumexp(x, axis=axis, b=b, keepdims=keepdims, return_sign=return_sign)
 
-    logsumexp = primitive(_logsumexp_raw)
-    logsumexp.__name__ = "logsumexp"
-    defvjp(logsumexp, aspecial.make_grad_logsumexp)
-    defjvp(logsumexp, aspecial.fwd_grad_logsumexp)
-    aspecial.logsumexp = logsumexp
+    # same primitive object, new raw function: the reference's own VJP/JVP (special.py:123-147) keep applying
+    _swap_raw(aspecial.logsumexp, _logsumexp_raw)
 
     # ------------------------------------------------------------ convolve (scipy/signal.py:10-217)
-    ref_convolve = asignal.convolve
+    ref_convolve_raw = asignal.convolve.fun
 
     def _is_nchw(A_, B, axes, dot_axes):
         if axes is None or dot_axes is None:
@@ -234,10 +241,10 @@ def install(creation: bool = True):
                     "autograd_b200: device convolve supports A[N,C,H,W] * B[C,F,kh,kw] with "
                     "axes=([2,3],[2,3]), dot_axes=([1],[0]), mode 'valid' or 'full'")
             return A.conv2d(A.asarray(A_), A.asarray(B), mode=mode, flip=True)
-        return ref_convolve.fun(A_, B, axes=axes, dot_axes=dot_axes, mode=mode)
+        return ref_convolve_raw(A_, B, axes=axes, dot_axes=dot_axes, mode=mode)
 
-    convolve = primitive(_convolve_raw)
-    convolve.__name__ = "convolve"
+    convolve = asignal.convolve
+    _swap_raw(convolve, _convolve_raw)
     conv_input_grad = primitive(A.conv2d_input_grad)
     conv_filter_grad = primitive(A.conv2d_filter_grad)
 
@@ -250,7 +257,6 @@ def install(creation: bool = True):
         return lambda g: conv_filter_grad(g, A_, anp.shape(B), mode)
 
     defvjp(convolve, partial(convolve_vjp, 0), partial(convolve_vjp, 1))
-    asignal.convolve = convolve
 
     # ------------------------------------------------------------ np.array(...) on device values
     # numpy_wrapper.py:83-108: ``array`` funnels into two primitives that call ``_np.array`` (not NEP-18

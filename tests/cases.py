@@ -821,3 +821,22 @@ def grad_case_forward_mode_operators():
 
 GRAD_CASES["optimizers"] = grad_case_optimizers
 GRAD_CASES["forward_mode_operators"] = grad_case_forward_mode_operators
+
+
+def grad_case_primitives_imported_before_install():
+    """`from autograd.scipy.special import logsumexp` / `...signal import convolve` done at module import time (as the
+    reference examples do, neural_net.py:12, convnet.py:11) must reach the device too: install() swaps the raw
+    function inside the SAME primitive objects."""
+    import autograd.scipy.signal as asignal
+    import autograd.scipy.special as aspecial
+    import autograd_b200.install as inst
+    from autograd import grad
+
+    assert aspecial.logsumexp.fun.__name__ == "_logsumexp_raw" and asignal.convolve.fun.__name__ == "_convolve_raw"
+    r = rs(80)
+    x = r.randn(6, 5)
+    f = lambda x: aspecial.logsumexp(x, axis=1).sum() + aspecial.logsumexp(x * 2.0)
+    check_grad(lambda x: f(x), (x,), TOL_REDUCE, "logsumexp primitive object")
+
+
+GRAD_CASES["primitives_preimported"] = grad_case_primitives_imported_before_install
