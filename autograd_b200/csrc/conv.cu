@@ -10,6 +10,8 @@
 //   weight-gradient:           rows = taps (c,i,j), cols = f, k = (n,y,x) positions; every CTA reduces a chunk
 //                              of the batch in registers and adds its partial with FP64 atomics.
 // float32 keeps the simple CUDA-core kernels (no config uses it).
+#include <cuda_pipeline.h>
+
 #include "common.cuh"
 
 namespace b200ag {
@@ -28,6 +30,7 @@ struct ConvArgs {
   int K, K4;        // taps C*kh*kw and ceil(K/4)
   int P, TPI;       // positions per image Ho*Wo and 8-row tiles per image
   int G;            // images per CTA iteration
+  int NBUF;         // 2: double-buffered image staging (cp.async prefetch), 1: single buffer
 };
 
 // out[n,f,y,x] = sum_{c,i,j} Apad[n,c,y+i,x+j] * Bk[c,f,i,j], Bk = B flipped when flip=1 (true convolution,
@@ -58,25 +61,42 @@ __global__ void __launch_bounds__(256) conv2d_dmma_kernel(ConvArgs g) {
     int c = kk / khw, i = (kk % khw) / g.kw, j = kk % g.kw;
     koff[k] = (c * g.Hp + i) * g.Wp + j;
   }
-  for (int e = tid; e < g.G * img_elems; e += 256) imgs[e] = 0.0;   // borders stay zero for the whole kernel
+  for (int e = tid; e < g.NBUF * g.G * img_elems; e += 256) imgs[e] = 0.0;   // borders stay zero for the whole kernel
   __syncthreads();
 
   const int ipi = (g.TPI + MT - 1) / MT;               // work items per image
   const int64_t groups = (g.N + g.G - 1) / g.G;
   const int hw = g.H * g.W;
-  for (int64_t grp = blockIdx.x; grp < groups; grp += gridDim.x) {
+  // stage(buf, grp): asynchronous copy (cp.async, 8 B) of a group's images into the interior of buffer `buf`
+  auto stage = [&](int buf, int64_t grp) {
     const int64_t n0 = grp * g.G;
     const int ng = (int)((g.N - n0) < g.G ? (g.N - n0) : g.G);
-    // stage the group's images (interior only)
     const double* src = g.A + n0 * g.C * hw;
+    double* dst = imgs + (size_t)buf * g.G * img_elems;
     for (int e = tid; e < ng * g.C * hw; e += 256) {
       int x = e % g.W, y = (e / g.W) % g.H, ci = e / hw;     // ci = image*C + channel
-      imgs[(ci * g.Hp + y + g.py) * g.Wp + x + g.px] = src[e];
+      __pipeline_memcpy_async(dst + (ci * g.Hp + y + g.py) * g.Wp + x + g.px, src + e, 8);
+    }
+    __pipeline_commit();
+  };
+  int64_t grp = blockIdx.x;
+  if (grp < groups) stage(0, grp);
+  for (int it = 0; grp < groups; grp += gridDim.x, ++it) {
+    const int buf = g.NBUF == 2 ? (it & 1) : 0;
+    const int64_t next = grp + gridDim.x;
+    if (g.NBUF == 2 && next < groups) {
+      stage(buf ^ 1, next);                            // prefetch the next group while this one is multiplied
+      __pipeline_wait_prior(1);
+    } else {
+      __pipeline_wait_prior(0);
     }
     __syncthreads();
+    const int64_t n0 = grp * g.G;
+    const int ng = (int)((g.N - n0) < g.G ? (g.N - n0) : g.G);
+    const double* gimgs = imgs + (size_t)buf * g.G * img_elems;
     for (int item = warp; item < ng * ipi; item += 8) {
       const int gi = item / ipi, mt0 = (item % ipi) * MT;
-      const double* img = imgs + gi * img_elems;
+      const double* img = gimgs + gi * img_elems;
       int moff[MT];
 #pragma unroll
       for (int t = 0; t < MT; ++t) {
@@ -115,6 +135,7 @@ __global__ void __launch_bounds__(256) conv2d_dmma_kernel(ConvArgs g) {
       }
     }
     __syncthreads();
+    if (g.NBUF == 1 && next < groups) stage(0, next);
   }
 }
 
@@ -131,17 +152,19 @@ template <int NT>
 __global__ void __launch_bounds__(256) conv2d_wgrad_dmma_kernel(WgradArgs g) {
   extern __shared__ double smem[];
   const int a_elems = g.C * g.H * g.W + 1;               // +1: a zero cell that padded rows/positions read
+  const int a_pitch = (a_elems + 1) & ~1;
   const int PG = g.P4 * 4 + 4;                            // pitch of G rows (positions), 4 mod 16 when P4*4 is 0 mod 16
-  double* As = smem;                                      // [C*H*W + 1]
-  double* Gs = As + ((a_elems + 1) & ~1);                 // [NT*8][PG]
-  int* poff = (int*)(Gs + NT * 8 * PG);                   // [P4*4] position -> offset y*W + x (or the zero cell)
+  const int g_elems = NT * 8 * PG;
+  double* As0 = smem;                                     // [2][C*H*W + 1]   (double-buffered)
+  double* Gs0 = As0 + 2 * a_pitch;                        // [2][NT*8][PG]
+  int* poff = (int*)(Gs0 + 2 * g_elems);                  // [P4*4] position -> offset y*W + x (or -1)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int khw = g.kh * g.kw;
   const int zero_cell = a_elems - 1;
 
   for (int p = tid; p < g.P4 * 4; p += 256) poff[p] = p < g.P ? (p / g.Wo) * g.W + (p % g.Wo) : -1;
-  for (int e = tid; e < NT * 8 * PG; e += 256) Gs[e] = 0.0;   // rows f >= F and positions >= P stay zero
-  if (tid == 0) As[zero_cell] = 0.0;
+  for (int e = tid; e < 2 * g_elems; e += 256) Gs0[e] = 0.0;   // rows f >= F and positions >= P stay zero
+  if (tid < 2) As0[tid * a_pitch + zero_cell] = 0.0;
 
   // warp -> (row tiles, k-part): enough row tiles: warps stride over them; few row tiles: split the positions
   int ksplit = 1;
@@ -171,13 +194,29 @@ __global__ void __launch_bounds__(256) conv2d_wgrad_dmma_kernel(WgradArgs g) {
   const int64_t n_lo = (int64_t)blockIdx.x * g.imgs_per_cta;
   const int64_t n_hi = (n_lo + g.imgs_per_cta < g.N) ? n_lo + g.imgs_per_cta : g.N;
   const int chw = g.C * g.H * g.W;
-  for (int64_t n = n_lo; n < n_hi; ++n) {
-    __syncthreads();
+  // stage(buf, n): cp.async of image n (activations and output cotangent) into buffer `buf`
+  auto stage = [&](int buf, int64_t n) {
     const double* a = g.A + n * chw;
     const double* gg = g.G + n * (int64_t)g.F * g.P;
-    for (int e = tid; e < chw; e += 256) As[e] = a[e];
-    for (int e = tid; e < g.F * g.P; e += 256) Gs[(e / g.P) * PG + (e % g.P)] = gg[e];
+    double* as = As0 + buf * a_pitch;
+    double* gs = Gs0 + buf * g_elems;
+    for (int e = tid; e < chw; e += 256) __pipeline_memcpy_async(as + e, a + e, 8);
+    for (int e = tid; e < g.F * g.P; e += 256) __pipeline_memcpy_async(gs + (e / g.P) * PG + (e % g.P), gg + e, 8);
+    __pipeline_commit();
+  };
+  __syncthreads();
+  if (n_lo < n_hi) stage(0, n_lo);
+  for (int64_t n = n_lo; n < n_hi; ++n) {
+    const int buf = (int)((n - n_lo) & 1);
+    if (n + 1 < n_hi) {
+      stage(buf ^ 1, n + 1);                             // prefetch the next image behind this one's MMAs
+      __pipeline_wait_prior(1);
+    } else {
+      __pipeline_wait_prior(0);
+    }
     __syncthreads();
+    const double* As = As0 + buf * a_pitch;
+    const double* Gs = Gs0 + buf * g_elems;
     for (int k4 = k4_lo; k4 < k4_hi; ++k4) {
       const int p = k4 * 4 + (lane & 3);
       const int po = poff[p];
@@ -194,6 +233,7 @@ __global__ void __launch_bounds__(256) conv2d_wgrad_dmma_kernel(WgradArgs g) {
         }
       }
     }
+    __syncthreads();
   }
   // partial result of this CTA's chunk -> global (flipped tap order), FP64 atomics
 #pragma unroll
@@ -288,10 +328,13 @@ static int launch_conv_dmma(ConvArgs& g, size_t smem) {
   size_t img_bytes = (size_t)g.C * g.Hp * g.Wp * sizeof(double);
   size_t fixed = smem;
   int G = (8 + ipi - 1) / ipi;
-  while (G > 1 && fixed + (size_t)G * img_bytes > 200 * 1024) --G;
-  if (fixed + (size_t)G * img_bytes > 200 * 1024) B200AG_FAIL("conv2d: image does not fit in shared memory");
+  int nbuf = 2;
+  if (fixed + (size_t)2 * G * img_bytes > 200 * 1024) nbuf = 1;   // keep all 8 warps busy before double buffering
+  while (G > 1 && fixed + (size_t)nbuf * G * img_bytes > 200 * 1024) --G;
+  if (fixed + (size_t)nbuf * G * img_bytes > 200 * 1024) B200AG_FAIL("conv2d: image does not fit in shared memory");
   g.G = G;
-  size_t total = fixed + (size_t)G * img_bytes;
+  g.NBUF = nbuf;
+  size_t total = fixed + (size_t)nbuf * G * img_bytes;
   int64_t groups = (g.N + G - 1) / G;
   int ctas_per_sm = (int)((220 * 1024) / (total + 1024));
   if (ctas_per_sm < 1) ctas_per_sm = 1;
@@ -392,7 +435,7 @@ int b200ag_conv2d_wgrad(void* dB, const void* A, const void* G, int dtype, int64
     int NT = F <= 8 ? 1 : 2;
     int PG = g.P4 * 4 + 4;
     size_t a_elems = (size_t)(C * H * W + 1);
-    size_t smem = ((a_elems + 1) & ~size_t(1)) * sizeof(double) + (size_t)NT * 8 * PG * sizeof(double) +
+    size_t smem = 2 * (((a_elems + 1) & ~size_t(1)) * sizeof(double) + (size_t)NT * 8 * PG * sizeof(double)) +
                   (size_t)g.P4 * 4 * sizeof(int);
     if (smem <= 200 * 1024) {
       int64_t ctas = (int64_t)sm_count() * 2;
