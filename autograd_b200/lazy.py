@@ -297,9 +297,9 @@ def _maybe_flush_growing(node):
 class Program:
     """Structural description of one fused kernel; ``key`` identifies the generated code."""
 
-    __slots__ = ("instrs", "leaves", "consts", "outputs", "ndim", "idx64", "vec", "key", "cost", "tables", "mode")
+    __slots__ = ("instrs", "leaves", "consts", "outputs", "ndim", "idx64", "vec", "key", "cost", "tables", "mode", "bx")
 
-    def __init__(self, instrs, leaves, consts, outputs, ndim, idx64, vec, cost, tables=(), mode="flat"):
+    def __init__(self, instrs, leaves, consts, outputs, ndim, idx64, vec, cost, tables=(), mode="flat", bx=256):
         self.instrs = instrs      # tuple of (op, in_dtype chars, out dtype char, arg refs)
         self.leaves = leaves      # tuple of (dtype char, layout class 'C'|'S'|'G', has_shift)
         self.consts = consts      # tuple of C scalar kinds: 'd' | 'q' | '?'
@@ -310,7 +310,8 @@ class Program:
         self.cost = cost
         self.tables = tables      # gather sources: tuple of (dtype char, number of indexed dims)
         self.mode = mode          # "flat": one flattened index; "row": rows x inner loop (general-layout operands)
-        self.key = (instrs, leaves, consts, outputs, ndim, idx64, vec, tables, mode)
+        self.bx = bx              # row mode: threads of a CTA along the inner dim (256/bx rows per CTA)
+        self.key = (instrs, leaves, consts, outputs, ndim, idx64, vec, tables, mode, bx)
 
     def launch_config(self, sm_count):
         block = 256
@@ -321,8 +322,11 @@ class Program:
         max_grid = sm_count * 16
         if self.mode == "row":
             inner = dims[-1]
-            gx = (inner + per_block - 1) // per_block
-            gy = max(1, min(n // inner, max_grid // gx))
+            span = self.bx * self.vec
+            gx = (inner + span - 1) // span
+            by = 256 // self.bx
+            nrows = n // inner
+            gy = max(1, min((nrows + by - 1) // by, max_grid // gx))
             return gx * gy
         return max(1, min((n + per_block - 1) // per_block, max_grid))
 
@@ -532,9 +536,11 @@ def materialize(root: Node, store_root: bool = True) -> Mat:
     mode = "row" if g_layouts and dims[-1] >= 128 else "flat"
     if mode == "row" and vec > 1 and dims[-1] % vec:
         vec = 1
+    # short rows: several rows per CTA (64 threads along the row) instead of one mostly idle 256-thread row slice
+    bx = 256 if (mode != "row" or dims[-1] >= 2048 * vec) else 64
 
     program = Program(tuple(instrs), tuple(leaf_descs), tuple(const_kinds), outputs, ndim, idx64, vec, total_cost,
-                      tuple(table_descs), mode)
+                      tuple(table_descs), mode, bx)
 
     out_mats = [Mat.empty(root_shape, o.dtype) for o in outs]
     backend.get().run_program(program, (leaf_ptrs, dims, table_rt), const_values, [m.ptr for m in out_mats], n)
