@@ -43,6 +43,7 @@ _DEFAULT_COST = 12  # transcendental functions
 # An interior node that Python can still see (a VJP closure holds it) is written
 # out as an extra output of the fused kernel once recomputing it would cost more
 # than this; cheaper ones are simply recomputed by whoever needs them later.
+_HEAVY_VEC = int(__import__("os").environ.get("B200AG_HEAVY_VEC", "1"))
 KEEP_COST = 96
 # Re-materialising nodes that keep being recomputed was measured on C4 (fluidsim): +1 % speed for +65 % retained
 # memory (the 200-step tape would no longer fit 180 GB), so it is off; the hook stays for experiments.
@@ -520,8 +521,10 @@ def materialize(root: Node, store_root: bool = True) -> Mat:
         max_item = 16  # gathers are latency-bound scalar loads: no vector path
     vec = max(1, 16 // max_item)
     total_cost = sum(_COST.get(nd_.op, _DEFAULT_COST) for nd_ in order)
-    if total_cost > 400 or n < 4096:
-        vec = 1  # heavy bodies are ALU-bound: keep the code size down
+    if n < 4096:
+        vec = 1
+    elif total_cost > 400:
+        vec = min(vec, _HEAVY_VEC)  # heavy bodies are ALU-bound: keep the code size down
     if vec > 1:
         for (ch, cls, _, _f), lp in zip(leaf_descs, leaf_ptrs):
             if cls == "C" and lp[0] % (np.dtype(ch).itemsize * vec):
