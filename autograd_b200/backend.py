@@ -270,6 +270,16 @@ class CudaBackend:
         self._check(self._lib.b200ag_gemm(
             c, dtype_code(c_dt), *c_str, a, dtype_code(a_dt), *a_str, b, dtype_code(b_dt), *b_str, M, N, K, batch))
 
+    def gemm_f32_tc(self, c, c_rs, a, a_str, b, b_str, M, N, K) -> None:
+        """float32 C = A @ B on the tcgen05 tensor cores (3xTF32); *_str = (row_stride, col_stride) in elements."""
+        self._check(self._lib.b200ag_gemm_f32_tc(c, c_rs, a, a_str[0], a_str[1], b, b_str[0], b_str[1], M, N, K))
+
+    def gemm_f32_mode(self, mode: int) -> int:
+        """0 = float32 products on the FP64 DMMA kernel, 1 = tcgen05 3xTF32 for large ones; returns the old mode."""
+        prev = C.c_int(0)
+        self._check(self._lib.b200ag_gemm_f32_mode(mode, C.byref(prev)))
+        return prev.value
+
     def gather(self, dst, src, dt, idx_ptrs, dims, n_index: int, inner: int) -> None:
         arr = (C.c_void_p * len(idx_ptrs))(*idx_ptrs)
         self._check(self._lib.b200ag_gather(dst, src, dtype_code(dt), arr, len(idx_ptrs), _i64_array(dims),

@@ -221,6 +221,9 @@ extern "C" int b200ag_gemm(void* C, int c_dtype, int64_t c_rs, int64_t c_cs, int
   if (M == 0 || N == 0 || batch == 0) return 0;
   if (c_dtype != B200AG_F64 && c_dtype != B200AG_F32) B200AG_FAIL("gemm: output dtype must be float64 or float32");
   if (batch > 65535) B200AG_FAIL("gemm: batch too large");
+  // large float32 x float32 -> float32 products run on tcgen05 tensor cores (3xTF32, gemm_tc.cu)
+  if (a_dtype == B200AG_F32 && b_dtype == B200AG_F32 && c_dtype == B200AG_F32 && f32_tc_eligible(M, N, K, c_cs, batch))
+    return b200ag_gemm_f32_tc(C, c_rs, A, a_rs, a_cs, B, b_rs, b_cs, M, N, K);
   GemmArgs g{C, A, B, c_rs, c_cs, c_bs, a_rs, a_cs, a_bs, b_rs, b_cs, b_bs, M, N, K, c_dtype == B200AG_F32, 1, K};
   // Split-K: when the output has too few tiles to occupy 148 SMs (weight gradients: small M x N, long K), slices of
   // K go to different CTAs and are combined with FP64 atomics into a zeroed float64 accumulator.

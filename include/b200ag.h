@@ -138,6 +138,17 @@ int b200ag_gemm(void* C, int c_dtype, int64_t c_rs, int64_t c_cs, int64_t c_bs,
                 const void* B, int b_dtype, int64_t b_rs, int64_t b_cs, int64_t b_bs,
                 int64_t M, int64_t N, int64_t K, int64_t batch);
 
+/* float32 x float32 -> float32 products on the tcgen05 tensor cores (accumulator in
+ * TMEM, operands staged by TMA): each operand is split into two TF32 terms and
+ * Ahi*Bhi + Ahi*Blo + Alo*Bhi is accumulated in FP32 ("3xTF32"), which keeps the
+ * result within the float32 tolerance of onp.tensordot's sgemm (numpy_vjps.py:621-637,
+ * 677-719).  C has unit column stride and row stride c_rs; A and B take arbitrary
+ * element strides.  b200ag_gemm routes large all-float32 products here unless
+ * b200ag_gemm_f32_mode(0, ...) selected the FP64 DMMA kernel for them. */
+int b200ag_gemm_f32_tc(void* C, int64_t c_rs, const void* A, int64_t a_rs, int64_t a_cs,
+                       const void* B, int64_t b_rs, int64_t b_cs, int64_t M, int64_t N, int64_t K);
+int b200ag_gemm_f32_mode(int mode, int* previous);
+
 /* ---------------------------------------------------------------- gather / scatter-add
  * out[i] = src[idx0[i], idx1[i], ..., :] (integer-array indexing on the leading
  * nidx axes, ArrayBox.__getitem__, numpy_boxes.py:16-18) and its VJP
