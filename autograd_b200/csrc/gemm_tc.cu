@@ -116,7 +116,8 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 template <int BN>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                   float* __restrict__ C, int M, int N, int Kp, int64_t ldc) {
+                   float* __restrict__ C, int M, int N, int Kp, int64_t ldc, int kb_per_split,
+                   int64_t split_stride, int mma_only) {
   using cfg = Cfg<BN>;
   constexpr int CPT = BN / 2;   // accumulator columns per epilogue thread (two warps share a 32-lane quadrant)
   extern __shared__ uint8_t smem_raw[];
@@ -130,8 +131,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-  const int num_kb = Kp / BK;
+  // split-K: blockIdx.z owns k-blocks [kb0, kb0 + num_kb) and writes its partial product to C + z * split_stride
+  const int kb0 = blockIdx.z * kb_per_split;
+  const int num_kb = min(kb_per_split, Kp / BK - kb0);
   const int num_chunks = (num_kb + KCB - 1) / KCB;
+  C += (int64_t)blockIdx.z * split_stride;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < cfg::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -154,14 +158,16 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     if (lane == 0) {
       // ===== TMA producer =====
       int stage = 0; uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      const int load_kb = mma_only ? min(num_kb, cfg::STAGES) : num_kb;   // diagnostics: tensor-pipe ceiling without loads
+      for (int kb = 0; kb < load_kb; ++kb) {
         mbar_wait(empty_bar(stage), phase ^ 1u);
         const uint32_t s0 = base + stage * cfg::STAGE;
         mbar_expect_tx(full_bar(stage), (uint32_t)cfg::STAGE);
-        tma_load_2d(s0, &map_a, kb * BK, m0, full_bar(stage));                                        // A hi
-        tma_load_2d(s0 + cfg::A_TILE, &map_a, Kp + kb * BK, m0, full_bar(stage));                      // A lo
-        tma_load_2d(s0 + 2 * cfg::A_TILE, &map_b, kb * BK, n0, full_bar(stage));                       // B hi
-        tma_load_2d(s0 + 2 * cfg::A_TILE + cfg::B_TILE, &map_b, Kp + kb * BK, n0, full_bar(stage));    // B lo
+        const int k = (kb0 + kb) * BK;
+        tma_load_2d(s0, &map_a, k, m0, full_bar(stage));                                        // A hi
+        tma_load_2d(s0 + cfg::A_TILE, &map_a, Kp + k, m0, full_bar(stage));                      // A lo
+        tma_load_2d(s0 + 2 * cfg::A_TILE, &map_b, k, n0, full_bar(stage));                       // B hi
+        tma_load_2d(s0 + 2 * cfg::A_TILE + cfg::B_TILE, &map_b, Kp + k, n0, full_bar(stage));    // B lo
         if (++stage == cfg::STAGES) { stage = 0; phase ^= 1u; }
       }
     }
@@ -182,7 +188,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         uint32_t acc = 0;
         const int kb_end = min(kb + KCB, num_kb);
         for (; kb < kb_end; ++kb) {
-          mbar_wait(full_bar(stage), phase);
+          if (!mma_only || kb < cfg::STAGES) mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t s0 = base + stage * cfg::STAGE;
           const uint64_t a_hi = umma_desc(s0), a_lo = umma_desc(s0 + cfg::A_TILE);
@@ -195,7 +201,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             umma_tf32(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
             umma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, 1u);
           }
-          umma_commit(empty_bar(stage));        // frees this smem stage once the MMAs above have read it
+          if (!mma_only) umma_commit(empty_bar(stage));   // frees this smem stage once the MMAs above have read it
           if (++stage == cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
         umma_commit(tfull_bar(buf));            // this chunk's accumulator is complete
@@ -318,15 +324,19 @@ static bool make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t K
   return true;
 }
 
+static int g_mma_only = 0;
+
 template <int BN>
-static int launch(const CUtensorMap& ma, const CUtensorMap& mb, float* C, int M, int N, int Kp, int64_t ldc) {
+static int launch(const CUtensorMap& ma, const CUtensorMap& mb, float* C, int M, int N, int Kp, int64_t ldc, int splits,
+                  int kb_per_split, int64_t split_stride) {
   static bool configured = false;
   if (!configured) {
     B200AG_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM));
     configured = true;
   }
-  dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN);
-  gemm_tf32x3_kernel<BN><<<grid, THREADS, Cfg<BN>::SMEM, stream()>>>(ma, mb, C, M, N, Kp, ldc);
+  dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, splits);
+  gemm_tf32x3_kernel<BN><<<grid, THREADS, Cfg<BN>::SMEM, stream()>>>(ma, mb, C, M, N, Kp, ldc, kb_per_split, split_stride,
+                                                                   g_mma_only);
   B200AG_LAUNCH_CHECK();
   return 0;
 }
@@ -352,6 +362,7 @@ extern "C" {
 int b200ag_gemm_f32_mode(int mode, int* previous) {
   if (previous) *previous = g_f32_mode;
   if (mode == 0 || mode == 1) g_f32_mode = mode;
+  if (mode == 100 || mode == 101) tc::g_mma_only = mode - 100;   // diagnostics: 101 = issue MMAs without reloading operands
   return 0;
 }
 
@@ -381,10 +392,26 @@ int b200ag_gemm_f32_tc(void* C, int64_t c_rs, const void* A, int64_t a_rs, int64
     count_launch();
   }
   const int BN = (N > 128 && ((M + 127) / 128) * ((N + 255) / 256) >= sm_count() / 2) ? 256 : 128;
+  // Split-K when the output has too few tiles for 148 SMs (weight gradients: small M x N, K = batch): every slice
+  // writes its own partial product, summed afterwards in a fixed order (deterministic, round-to-nearest).
+  const int64_t tiles = ((M + 127) / 128) * ((N + BN - 1) / BN);
+  const int64_t num_kb = Kp / tc::BK;
+  int64_t splits = sm_count() / tiles;
+  if (splits > num_kb / 16) splits = num_kb / 16;      // at least 512 values of k per slice
+  if (splits > 16) splits = 16;
+  if (splits < 2 || c_rs != N) splits = 1;
+  int64_t kb_per_split = (num_kb + splits - 1) / splits;
+  splits = (num_kb + kb_per_split - 1) / kb_per_split;
+  void* part = nullptr;
+  if (splits > 1 && b200ag_malloc((size_t)(splits * M * N) * 4, &part)) splits = 1, kb_per_split = num_kb;
+  float* out = splits > 1 ? (float*)part : (float*)C;
+  const int64_t ldc = splits > 1 ? N : c_rs;
   CUtensorMap ma, mb;
   if (!tc::make_map(&ma, (const float*)a2, M, Kp, tc::BM) || !tc::make_map(&mb, (const float*)b2, N, Kp, BN)) rc = 1;
-  if (rc == 0) rc = (BN == 256) ? tc::launch<256>(ma, mb, (float*)C, (int)M, (int)N, (int)Kp, c_rs)
-                                : tc::launch<128>(ma, mb, (float*)C, (int)M, (int)N, (int)Kp, c_rs);
+  if (rc == 0) rc = (BN == 256) ? tc::launch<256>(ma, mb, out, (int)M, (int)N, (int)Kp, ldc, (int)splits, (int)kb_per_split, M * N)
+                                : tc::launch<128>(ma, mb, out, (int)M, (int)N, (int)Kp, ldc, (int)splits, (int)kb_per_split, M * N);
+  if (rc == 0 && splits > 1) rc = b200ag_reduce(C, part, B200AG_F32, B200AG_SUM, 1, splits, M * N);
+  if (part) b200ag_free(part);
   b200ag_free(a2);
   b200ag_free(b2);
   return rc;

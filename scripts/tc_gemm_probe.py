@@ -47,7 +47,9 @@ def bench(M, N, K, reps=10):
     b = b200.asarray(rs.randn(K, N).astype(onp.float32))
     out = b200.array.zeros((M, N), onp.float32)
     ma, mb, mo = a._mat(), b._mat(), out._mat()
-    for mode, name in ((1, "tcgen05 3xTF32"), (0, "DMMA f64-accumulate")):
+    for mode, name in ((1, "tcgen05 3xTF32"), (101, "tcgen05 MMA-only (no loads)"), (0, "DMMA f64-accumulate")):
+        be.gemm_f32_mode(100)
+        be.gemm_f32_mode(1 if mode == 101 else mode)
         be.gemm_f32_mode(mode)
         fn = lambda: be.gemm(mo.ptr, onp.dtype("float32"), (N, 1, 0), ma.ptr, onp.dtype("float32"), (K, 1, 0), mb.ptr,
                              onp.dtype("float32"), (N, 1, 0), M, N, K, 1)
@@ -62,21 +64,23 @@ def bench(M, N, K, reps=10):
         be.synchronize()
         ms = be.event_elapsed_ms(e0, e1) / reps
         print(f"  {name:22s} {M}x{N}x{K}: {ms:.3f} ms  {2.0 * M * N * K / ms / 1e9:.1f} TFLOP/s (fp32-equivalent)", flush=True)
+    be.gemm_f32_mode(100)
     be.gemm_f32_mode(1)
 
 
 if __name__ == "__main__":
     t0 = time.time()
-    check(128, 128, 32)
-    check(128, 256, 64)
-    check(256, 512, 128)
-    check(300, 200, 70)
-    check(1000, 777, 333, ta=True)
-    check(515, 1030, 257, tb=True)
-    check(640, 384, 96, ta=True, tb=True)
-    check(2048, 2048, 2048)
-    check(1024, 1024, 8192)
-    check(4096, 4096, 4096, scale=3.0)
+    if "--quick" not in sys.argv:
+        check(128, 128, 32)
+        check(128, 256, 64)
+        check(256, 512, 128)
+        check(300, 200, 70)
+        check(1000, 777, 333, ta=True)
+        check(515, 1030, 257, tb=True)
+        check(640, 384, 96, ta=True, tb=True)
+        check(2048, 2048, 2048)
+        check(1024, 1024, 8192)
+        check(4096, 4096, 4096, scale=3.0)
     for shape in ((2048, 2048, 2048), (4096, 4096, 4096), (8192, 8192, 4096), (1024, 512, 16384)):
         bench(*shape)
     print("done in %.1f s" % (time.time() - t0))

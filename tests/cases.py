@@ -840,3 +840,31 @@ def grad_case_primitives_imported_before_install():
 
 
 GRAD_CASES["primitives_preimported"] = grad_case_primitives_imported_before_install
+
+
+def grad_case_f32_tensor_core_contractions():
+    """All-float32 contractions large enough for the tcgen05 3xTF32 kernel (csrc/gemm_tc.cu): forward dot and both
+    dot VJPs (G B^T and A^T G, numpy_vjps.py:615-651) of a float32 two-layer net, against float32 NumPy."""
+    import autograd.numpy as np
+
+    r = rs(70)
+    X = (r.randn(640, 512) * 0.5).astype(onp.float32)
+    W1 = (r.randn(512, 384) * 0.05).astype(onp.float32)
+    W2 = (r.randn(384, 256) * 0.05).astype(onp.float32)
+
+    def loss(W1, W2, X):
+        h = np.tanh(np.dot(X, W1))
+        return np.sum(np.dot(h, W2) ** 2) / X.shape[0]
+
+    check(lambda a, b: onp.dot(a, b), X, W1, tol=TOL_F32, what="f32 dot on tensor cores")
+    check(lambda a, b: onp.tensordot(a, b, [[0], [0]]), X, (r.randn(640, 300)).astype(onp.float32), tol=TOL_F32,
+          what="f32 A^T B on tensor cores")
+    for argnum in (0, 1, 2):
+        check_grad(loss, (W1, W2, X), TOL_F32, f"f32 net grad wrt arg {argnum}", argnum=argnum)
+    dev = to_dev([W1, W2, X])
+    from autograd import grad
+
+    assert grad(loss)(*dev).dtype == onp.float32
+
+
+GRAD_CASES["f32_tensor_core_contractions"] = grad_case_f32_tensor_core_contractions

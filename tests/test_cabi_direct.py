@@ -133,6 +133,51 @@ def test_gemm_strides_dtypes_batch(abi):
     assert np.allclose(abi.get(pcb, (4, 9, 5), np.float64), ab @ bb, rtol=1e-10, atol=1e-12)
 
 
+@pytest.mark.parametrize("M,N,K,ta,tb", [(128, 128, 32, False, False), (300, 200, 70, False, False),
+                                          (1000, 777, 333, True, False), (515, 1030, 257, False, True),
+                                          (640, 384, 96, True, True), (256, 384, 6144, True, False),
+                                          (1024, 1024, 4096, False, False)])
+def test_gemm_f32_tensor_core(abi, M, N, K, ta, tb):
+    """tcgen05 3xTF32 product against the float64 product and against NumPy's sgemm (north_star: float32 within 1e-5);
+    transposed views, ragged edges, K not a multiple of the k-block, split-K (small M x N, long K), long K (chunked
+    promotion keeps the error flat)."""
+    r = np.random.RandomState(M + N + K)
+    a = r.randn(*((K, M) if ta else (M, K))).astype(np.float32)
+    b = r.randn(*((N, K) if tb else (K, N))).astype(np.float32)
+    A, B = (a.T if ta else a), (b.T if tb else b)
+    a_str = (1, a.shape[1]) if ta else (a.shape[1], 1)
+    b_str = (1, b.shape[1]) if tb else (b.shape[1], 1)
+    out = abi.empty(M * N * 4)
+    abi.ok(abi.lib.b200ag_gemm_f32_tc(out, N, abi.put(a), a_str[0], a_str[1], abi.put(b), b_str[0], b_str[1], M, N, K))
+    got = abi.get(out, (M, N), np.float32)
+    want = A.astype(np.float64) @ B.astype(np.float64)
+    scale = np.abs(want).max()
+    assert np.abs(got - want).max() / scale < 5e-6
+    assert np.abs(got - A @ B).max() / scale < 1e-5      # NumPy float32 reference, north_star tolerance
+
+
+def test_gemm_f32_mode_switch_and_dispatch(abi):
+    """b200ag_gemm sends a large all-float32 product to the tensor cores unless mode 0 asks for the FP64 DMMA kernel;
+    both agree with the float64 product."""
+    r = np.random.RandomState(5)
+    M, N, K = 512, 640, 768
+    a, b = r.randn(M, K).astype(np.float32), r.randn(K, N).astype(np.float32)
+    want = a.astype(np.float64) @ b.astype(np.float64)
+    pa, pb = abi.put(a), abi.put(b)
+    prev = C.c_int(-1)
+    results = {}
+    for mode in (0, 1):
+        abi.ok(abi.lib.b200ag_gemm_f32_mode(mode, C.byref(prev)))
+        out = abi.empty(M * N * 4)
+        abi.ok(abi.lib.b200ag_gemm(out, F32, N, 1, 0, pa, F32, K, 1, 0, pb, F32, N, 1, 0, M, N, K, 1))
+        results[mode] = abi.get(out, (M, N), np.float32)
+    assert prev.value == 0
+    scale = np.abs(want).max()
+    assert np.abs(results[0] - want).max() / scale < 2e-7    # exact products, FP64 accumulation, one rounding
+    assert np.abs(results[1] - want).max() / scale < 5e-6
+    assert not np.array_equal(results[0], results[1])         # really two different kernels
+
+
 def test_gather_scatter_add(abi):
     rs = np.random.RandomState(4)
     f = rs.randn(50, 40)
