@@ -255,6 +255,204 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2): two CTAs of a cluster, on the two SMs of a TPC, compute a 256 x 256 tile
+// with ONE 256x256x8 UMMA issued by the leader.  Each CTA stages its own 128 rows of A and only HALF of the B tile,
+// so a k-block costs 64 KB of L2->SM traffic per SM instead of 96 KB, and three stages fit in shared memory.  (The
+// single-CTA kernel above is bound by exactly that traffic: ncu shows 10.8 TB/s of L2->SM reads at 65% of the tensor
+// rate, profiles/r01_tc_gemm_ncu.csv.)
+//   full[s]   (leader)   count 2: the leader's producer arrives with expect_tx for BOTH CTAs' bytes, the peer's
+//                        producer arrives remotely; both CTAs' TMA loads complete_tx on the leader's barrier
+//   empty[s]  (each CTA) count 1: tcgen05.commit multicast from the leader's MMA thread
+//   tfull[b]  (each CTA) count 1: tcgen05.commit multicast; tempty[b] (leader) count 2*EPI_WARPS, peer arrives remotely
+namespace pair {
+
+constexpr int BN = 256;
+constexpr int A_TILE = BM * BK * 4;            // 16 KB: this CTA's 128 rows of A
+constexpr int B_TILE = (BN / 2) * BK * 4;      // 16 KB: this CTA's half of the B tile
+constexpr int STAGE = 2 * A_TILE + 2 * B_TILE; // 64 KB
+constexpr int STAGES = 3;
+constexpr int SMEM = STAGES * STAGE + 1024 + 256;
+
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank) {
+  uint32_t out;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(out) : "r"(addr), "r"(rank));
+  return out;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t leader_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(leader_bar)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                        float* __restrict__ C, int M, int N, int Kp, int64_t ldc, int kb_per_split, int64_t split_stride) {
+  constexpr int CPT = BN / 2;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = base + STAGES * STAGE;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int b) { return bars + 8u * (2 * STAGES + b); };
+  auto tempty_bar = [&](int b) { return bars + 8u * (2 * STAGES + 2 + b); };
+  const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_rank();          // 0 = leader (issues the MMAs), 1 = peer
+  const int m0 = blockIdx.x * BM;                // this CTA's 128 rows (blockIdx.x = 2 * pair + rank)
+  const int n0 = blockIdx.y * BN;
+  const int kb0 = blockIdx.z * kb_per_split;
+  const int num_kb = min(kb_per_split, Kp / BK - kb0);
+  const int num_chunks = (num_kb + KCB - 1) / KCB;
+  C += (int64_t)blockIdx.z * split_stride;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 2 * EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+  }
+  if (warp == 1) {   // the same warp of both CTAs allocates the pair's accumulators (2 x 256 columns in each SM)
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)(2 * BN)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();                            // barriers of BOTH CTAs are initialised before anyone signals them
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer (both CTAs): own A rows, own half of B; bytes are counted on the LEADER's full barrier =====
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        const uint32_t s0 = base + stage * STAGE;
+        const uint32_t lead_full = map_to_cta(full_bar(stage), 0);
+        if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * (uint32_t)STAGE);
+        else mbar_arrive_cluster(lead_full);
+        const int k = (kb0 + kb) * BK;
+        const int nb = n0 + (int)rank * (BN / 2);
+        tma_load_2d_pair(s0, &map_a, k, m0, lead_full);
+        tma_load_2d_pair(s0 + A_TILE, &map_a, Kp + k, m0, lead_full);
+        tma_load_2d_pair(s0 + 2 * A_TILE, &map_b, k, nb, lead_full);
+        tma_load_2d_pair(s0 + 2 * A_TILE + B_TILE, &map_b, Kp + k, nb, lead_full);
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      // ===== MMA issuer: one thread of the leader CTA drives the tensor cores of both SMs =====
+      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      int stage = 0; uint32_t phase = 0;
+      int kb = 0;
+      for (int chunk = 0; chunk < num_chunks; ++chunk) {
+        const int buf = chunk & 1;
+        mbar_wait(tempty_bar(buf), (((uint32_t)chunk >> 1) & 1u) ^ 1u);   // both CTAs' epilogues drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+        uint32_t acc = 0;
+        const int kb_end = min(kb + KCB, num_kb);
+        for (; kb < kb_end; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t s0 = base + stage * STAGE;
+          const uint64_t a_hi = umma_desc(s0), a_lo = umma_desc(s0 + A_TILE);
+          const uint64_t b_hi = umma_desc(s0 + 2 * A_TILE), b_lo = umma_desc(s0 + 2 * A_TILE + B_TILE);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);
+            umma_tf32_pair(tmem_d, a_lo + adv, b_hi + adv, idesc, acc);
+            acc = 1;
+            umma_tf32_pair(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
+            umma_tf32_pair(tmem_d, a_hi + adv, b_hi + adv, idesc, 1u);
+          }
+          umma_commit_pair(empty_bar(stage));    // frees this stage in BOTH CTAs
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_pair(tfull_bar(buf));        // wakes the epilogue warps of both CTAs
+      }
+    }
+  } else {
+    // ===== epilogue (both CTAs): this CTA's 128 rows of the pair's accumulator =====
+    const int e = warp - 2;
+    const int q = warp & 3;
+    const int half = e >> 2;
+    float acc[CPT];
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) acc[j] = 0.f;
+    const uint32_t lead_tempty0 = map_to_cta(tempty_bar(0), 0), lead_tempty1 = map_to_cta(tempty_bar(1), 0);
+    for (int chunk = 0; chunk < num_chunks; ++chunk) {
+      const int buf = chunk & 1;
+      mbar_wait(tfull_bar(buf), ((uint32_t)chunk >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + half * CPT);
+#pragma unroll
+      for (int c = 0; c < CPT / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(t0 + (uint32_t)(c * 32), v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[c * 32 + j] += __uint_as_float(v[j]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(buf ? lead_tempty1 : lead_tempty0);
+    }
+    const int row = m0 + q * 32 + lane;
+    float* crow = C + (int64_t)row * ldc;
+    const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+    const int col0 = n0 + half * CPT;
+    if (row < M) {
+      if (vec_ok && col0 + CPT <= N) {
+#pragma unroll
+        for (int j = 0; j < CPT; j += 4)
+          *reinterpret_cast<float4*>(crow + col0 + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < CPT; ++j)
+          if (col0 + j < N) crow[col0 + j] = acc[j];
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();                            // nobody leaves while the peer may still touch its smem / barriers / TMEM
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN)) : "memory");
+  }
+}
+
+}  // namespace pair
+
 // Split pre-pass: dst[r, k] = hi(src[r,k]), dst[r, Kp + k] = lo(src[r,k]); zero for K <= k < Kp.
 // src is any strided float32 view (element strides rs, cs); reads are coalesced along whichever axis is contiguous.
 __global__ void __launch_bounds__(256) split_tf32_kernel(float* __restrict__ dst, const float* __restrict__ src, int R, int K,
@@ -341,6 +539,21 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, float* C, int M,
   return 0;
 }
 
+static int launch_pair(const CUtensorMap& ma, const CUtensorMap& mb, float* C, int M, int N, int Kp, int64_t ldc, int splits,
+                       int kb_per_split, int64_t split_stride) {
+  static bool configured = false;
+  if (!configured) {
+    B200AG_CUDA(cudaFuncSetAttribute(pair::gemm_tf32x3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::SMEM));
+    configured = true;
+  }
+  dim3 grid(2 * ((M + 2 * BM - 1) / (2 * BM)), (N + pair::BN - 1) / pair::BN, splits);
+  pair::gemm_tf32x3_pair_kernel<<<grid, THREADS, pair::SMEM, stream()>>>(ma, mb, C, M, N, Kp, ldc, kb_per_split, split_stride);
+  B200AG_LAUNCH_CHECK();
+  return 0;
+}
+
+static int g_variant = 0;   // 0 = choose automatically, 1 = single-CTA kernels only, 2 = CTA-pair kernel whenever legal
+
 }  // namespace tc
 
 static int g_f32_mode = 1;
@@ -363,6 +576,7 @@ int b200ag_gemm_f32_mode(int mode, int* previous) {
   if (previous) *previous = g_f32_mode;
   if (mode == 0 || mode == 1) g_f32_mode = mode;
   if (mode == 100 || mode == 101) tc::g_mma_only = mode - 100;   // diagnostics: 101 = issue MMAs without reloading operands
+  if (mode >= 200 && mode <= 202) tc::g_variant = mode - 200;    // diagnostics: kernel variant (see tc::g_variant)
   return 0;
 }
 
@@ -392,6 +606,7 @@ int b200ag_gemm_f32_tc(void* C, int64_t c_rs, const void* A, int64_t a_rs, int64
     count_launch();
   }
   const int BN = (N > 128 && ((M + 127) / 128) * ((N + 255) / 256) >= sm_count() / 2) ? 256 : 128;
+  const bool use_pair = tc::g_variant == 2 || (tc::g_variant == 0 && BN == 256 && M >= 256);
   // Split-K when the output has too few tiles for 148 SMs (weight gradients: small M x N, K = batch): every slice
   // writes its own partial product, summed afterwards in a fixed order (deterministic, round-to-nearest).
   const int64_t tiles = ((M + 127) / 128) * ((N + BN - 1) / BN);
@@ -407,8 +622,9 @@ int b200ag_gemm_f32_tc(void* C, int64_t c_rs, const void* A, int64_t a_rs, int64
   float* out = splits > 1 ? (float*)part : (float*)C;
   const int64_t ldc = splits > 1 ? N : c_rs;
   CUtensorMap ma, mb;
-  if (!tc::make_map(&ma, (const float*)a2, M, Kp, tc::BM) || !tc::make_map(&mb, (const float*)b2, N, Kp, BN)) rc = 1;
-  if (rc == 0) rc = (BN == 256) ? tc::launch<256>(ma, mb, out, (int)M, (int)N, (int)Kp, ldc, (int)splits, (int)kb_per_split, M * N)
+  if (!tc::make_map(&ma, (const float*)a2, M, Kp, tc::BM) || !tc::make_map(&mb, (const float*)b2, N, Kp, use_pair ? 128 : BN)) rc = 1;
+  if (rc == 0 && use_pair) rc = tc::launch_pair(ma, mb, out, (int)M, (int)N, (int)Kp, ldc, (int)splits, (int)kb_per_split, M * N);
+  else if (rc == 0) rc = (BN == 256) ? tc::launch<256>(ma, mb, out, (int)M, (int)N, (int)Kp, ldc, (int)splits, (int)kb_per_split, M * N)
                                 : tc::launch<128>(ma, mb, out, (int)M, (int)N, (int)Kp, ldc, (int)splits, (int)kb_per_split, M * N);
   if (rc == 0 && splits > 1) rc = b200ag_reduce(C, part, B200AG_F32, B200AG_SUM, 1, splits, M * N);
   if (part) b200ag_free(part);

@@ -47,10 +47,14 @@ def bench(M, N, K, reps=10):
     b = b200.asarray(rs.randn(K, N).astype(onp.float32))
     out = b200.array.zeros((M, N), onp.float32)
     ma, mb, mo = a._mat(), b._mat(), out._mat()
-    for mode, name in ((1, "tcgen05 3xTF32"), (101, "tcgen05 MMA-only (no loads)"), (0, "DMMA f64-accumulate")):
+    for mode, name in ((201, "tcgen05 3xTF32 1-CTA"), (202, "tcgen05 3xTF32 CTA pair"), (200, "tcgen05 3xTF32 auto"),
+                       (101, "1-CTA MMA-only (no loads)"), (0, "DMMA f64-accumulate")):
         be.gemm_f32_mode(100)
-        be.gemm_f32_mode(1 if mode == 101 else mode)
+        be.gemm_f32_mode(200)
+        be.gemm_f32_mode(0 if mode == 0 else 1)
         be.gemm_f32_mode(mode)
+        if mode == 101:
+            be.gemm_f32_mode(201)
         fn = lambda: be.gemm(mo.ptr, onp.dtype("float32"), (N, 1, 0), ma.ptr, onp.dtype("float32"), (K, 1, 0), mb.ptr,
                              onp.dtype("float32"), (N, 1, 0), M, N, K, 1)
         for _ in range(3):
@@ -63,14 +67,26 @@ def bench(M, N, K, reps=10):
         be.event_record(e1)
         be.synchronize()
         ms = be.event_elapsed_ms(e0, e1) / reps
-        print(f"  {name:22s} {M}x{N}x{K}: {ms:.3f} ms  {2.0 * M * N * K / ms / 1e9:.1f} TFLOP/s (fp32-equivalent)", flush=True)
+        print(f"  {name:28s} {M}x{N}x{K}: {ms:.3f} ms  {2.0 * M * N * K / ms / 1e9:.1f} TFLOP/s (fp32-equivalent)", flush=True)
     be.gemm_f32_mode(100)
+    be.gemm_f32_mode(200)
     be.gemm_f32_mode(1)
 
 
 if __name__ == "__main__":
     t0 = time.time()
     if "--quick" not in sys.argv:
+        be.gemm_f32_mode(202)
+        print("CTA-pair kernel forced:")
+        check(256, 256, 32)
+        check(300, 200, 70)
+        check(1000, 777, 333, ta=True)
+        check(515, 1030, 257, tb=True)
+        check(2048, 2048, 2048)
+        check(256, 384, 6144, ta=True)
+        check(1024, 1024, 8192)
+        be.gemm_f32_mode(200)
+        print("automatic choice:")
         check(128, 128, 32)
         check(128, 256, 64)
         check(256, 512, 128)
