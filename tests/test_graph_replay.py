@@ -86,3 +86,33 @@ def test_value_dependent_control_flow_is_rejected(cuda_dev):
         fast(b200.asarray(onp.ones(8)))
     # the backend must be usable again afterwards
     assert float((b200.asarray(onp.ones(4)) * 2).get().sum()) == 8.0
+
+
+def test_replayed_float32_net_uses_tensor_core_gemm(cuda_dev):
+    """A float32 net whose dot VJPs run on the tcgen05 kernels (TMA descriptors, cluster launch, split-K workspace)
+    must be capturable and replayable like everything else."""
+    import autograd.numpy as np
+    import autograd_b200 as b200
+    from autograd import grad
+
+    r = onp.random.RandomState(3)
+    X = (r.randn(640, 512) * 0.5).astype(onp.float32)
+    W1 = (r.randn(512, 384) * 0.05).astype(onp.float32)
+    W2 = (r.randn(384, 256) * 0.05).astype(onp.float32)
+
+    def loss(W1, W2, X):
+        return np.sum(np.dot(np.tanh(np.dot(X, W1)), W2) ** 2) / X.shape[0]
+
+    g = grad(loss, (0, 1))
+    with b200.host_arrays():
+        want = g(W1, W2, X)
+    fast = b200.capture(g)
+    for scale in (1.0, 1.0, 0.5):
+        got = fast(b200.asarray(W1 * onp.float32(scale)), b200.asarray(W2), b200.asarray(X))
+        if scale != 1.0:
+            with b200.host_arrays():
+                want = g(W1 * onp.float32(scale), W2, X)
+        for a, w_ in zip(got, want):
+            assert a.dtype == onp.float32
+            cases.assert_close(a.get(), w_, cases.TOL_F32, "replayed float32 net gradient")
+    assert len(fast.num_nodes()) == 1
