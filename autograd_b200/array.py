@@ -375,7 +375,7 @@ class DeviceArray:
     def __setitem__(self, idx, value):
         kind, info = _parse_index(self.shape, idx)
         if kind != "basic":
-            raise NotImplementedError("autograd_b200: item assignment supports basic (slice/int) indices only")
+            return self._assign_at(info, value)
         self._own_buffer()
         view = _basic_view(self._mat(), info)
         value = asarray(value, dtype=self.dtype) if not isinstance(value, DeviceArray) else value
@@ -385,6 +385,22 @@ class DeviceArray:
         if src.shifts is not None:
             src = DeviceArray(lazy.leaf(src))._cmat()
         backend.get().copy_strided(view.ptr, view.dtype, view.strides, src.ptr, src.dtype, src.strides, view.shape)
+
+    def _assign_at(self, info, value):
+        """x[index arrays] = value (e.g. ``unsort[permutation] = range(n)`` in unpermuter, numpy_vjps.py:803-806)."""
+        self._own_buffer()
+        m = self._mat()
+        if not m.is_contiguous:
+            raise NotImplementedError("autograd_b200: item assignment with array indices needs a contiguous target")
+        idx_arrays, idx_shape, n_lead = info
+        inner_shape = self.shape[n_lead:]
+        v = value if isinstance(value, DeviceArray) else asarray(np.asarray(value))
+        if v.dtype != self.dtype:
+            v = v.astype(self.dtype)
+        vm = broadcast_to(v, tuple(idx_shape) + tuple(inner_shape))._cmat()
+        ptrs = [a._cmat() for a in idx_arrays]
+        backend.get().scatter_assign(m.ptr, vm.ptr, self.dtype, [p.ptr for p in ptrs], list(self.shape[:n_lead]),
+                                     prod(idx_shape), prod(inner_shape))
 
     def _own_buffer(self):
         """Make sure this handle is backed by real memory that may be written in place."""
@@ -1090,6 +1106,207 @@ def diff(a, n=1, axis=-1, prepend=None, append=None):
     return a
 
 
+def _cumulate(a, op, axis, dtype):
+    a = asarray(a)
+    if axis is None:
+        a, axis = ravel(a), 0
+    axis = _normalize_axis(axis, a.ndim) if a.ndim else 0
+    if a.ndim == 0:
+        a = reshape(a, (1,))
+    dt = np.dtype(dtype) if dtype is not None else (np.dtype(np.int64) if a.dtype.kind in "bi" and a.dtype.itemsize < 8
+                                                      or a.dtype.kind == "b" else a.dtype)
+    if a.dtype != dt:
+        a = a.astype(dt)
+    if a.size == 0:
+        return a
+    src = a._cmat()
+    out = Mat.empty(a.shape, dt)
+    backend.get().cumulate(out.ptr, src.ptr, dt, op, prod(a.shape[:axis]), a.shape[axis], prod(a.shape[axis + 1:]))
+    return DeviceArray(lazy.leaf(out))
+
+
+def cumsum(a, axis=None, dtype=None, out=None):
+    """np.cumsum (VJP: grad_np_cumsum, numpy_vjps.py:539-549) on the device scan kernel."""
+    return _cumulate(a, "sum", axis, dtype)
+
+
+def cumprod(a, axis=None, dtype=None, out=None):
+    return _cumulate(a, "prod", axis, dtype)
+
+
+def _sorted(a, axis, want_keys, want_idx):
+    a = asarray(a)
+    if a.dtype == np.bool_:
+        raise NotImplementedError("autograd_b200: sorting boolean arrays is not supported")
+    if axis is None:
+        a, axis = ravel(a), 0
+    if a.ndim == 0:
+        raise np.exceptions.AxisError("axis 0 is out of bounds for array of dimension 0")
+    axis = _normalize_axis(axis, a.ndim)
+    moved = moveaxis(a, axis, -1) if axis != a.ndim - 1 else a
+    shape = moved.shape
+    n = shape[-1]
+    rows = prod(shape[:-1])
+    keys = Mat.empty(shape, a.dtype) if want_keys else None
+    idx = Mat.empty(shape, np.dtype(np.int64)) if want_idx else None
+    if rows and n:
+        src = moved._cmat()
+        be = backend.get()
+        for r0 in range(0, rows, 65535):      # grid.y limit of the sort kernels
+            r1 = min(rows, r0 + 65535)
+            be.sort(None if keys is None else keys.ptr + r0 * n * a.dtype.itemsize,
+                    None if idx is None else idx.ptr + r0 * n * 8, src.ptr + r0 * n * a.dtype.itemsize, a.dtype, r1 - r0, n)
+
+    def back(m):
+        r = DeviceArray(lazy.leaf(m))
+        return moveaxis(r, -1, axis) if axis != a.ndim - 1 else r
+
+    return (back(keys) if want_keys else None), (back(idx) if want_idx else None)
+
+
+def sort(a, axis=-1, kind=None, order=None, **kw):
+    """np.sort: stable ascending row sort, NaN last (grad_sort, numpy_vjps.py:774-789)."""
+    if order is not None:
+        raise NotImplementedError("autograd_b200: structured-array sort order is not supported")
+    return _sorted(a, axis, True, False)[0]
+
+
+def argsort(a, axis=-1, kind=None, order=None, **kw):
+    """np.argsort: int64 permutation of the stable sort (bit-exact against kind='stable', and against any kind when
+    the keys are distinct)."""
+    if order is not None:
+        raise NotImplementedError("autograd_b200: structured-array sort order is not supported")
+    return _sorted(a, axis, False, True)[1]
+
+
+def kron(a, b):
+    a, b = asarray(a), asarray(b)
+    nd = max(a.ndim, b.ndim)
+    a = reshape(a, (1,) * (nd - a.ndim) + a.shape)
+    b = reshape(b, (1,) * (nd - b.ndim) + b.shape)
+    ash = tuple(x for d in a.shape for x in (d, 1))
+    bsh = tuple(x for d in b.shape for x in (1, d))
+    return reshape(reshape(a, ash) * reshape(b, bsh), tuple(x * y for x, y in zip(a.shape, b.shape)))
+
+
+def rot90(m, k=1, axes=(0, 1)):
+    m = asarray(m)
+    a0, a1 = (_normalize_axis(x, m.ndim) for x in axes)
+    if a0 == a1:
+        raise ValueError("Axes must be different.")
+    k %= 4
+    if k == 0:
+        return m
+    if k == 2:
+        return flip(flip(m, a0), a1)
+    if k == 1:
+        return swapaxes(flip(m, a1), a0, a1)
+    return flip(swapaxes(m, a0, a1), a1)
+
+
+def rollaxis(a, axis, start=0):
+    a = asarray(a)
+    axis = _normalize_axis(axis, a.ndim)
+    if start < 0:
+        start += a.ndim
+    if not 0 <= start <= a.ndim:
+        raise np.exceptions.AxisError(f"start {start} is out of bounds")
+    if axis < start:
+        start -= 1
+    return a if axis == start else moveaxis(a, axis, start)
+
+
+def average(a, axis=None, weights=None, returned=False, keepdims=False):
+    a = asarray(a)
+    if weights is None:
+        avg = mean(a, axis=axis, keepdims=keepdims)
+        if returned:
+            return avg, full_like(avg, a.size / max(avg.size, 1))
+        return avg
+    w = asarray(weights)
+    if w.shape != a.shape:
+        if axis is None or w.ndim != 1 or w.shape[0] != a.shape[axis]:
+            raise TypeError("Axis must be specified when shapes of a and weights differ.")
+        w = reshape(w, tuple(w.shape[0] if i == _normalize_axis(axis, a.ndim) else 1 for i in range(a.ndim)))
+        w = broadcast_to(w, a.shape)
+    scl = sum_(w, axis=axis, keepdims=keepdims)
+    avg = sum_(a * w, axis=axis, keepdims=keepdims) / scl
+    return (avg, scl) if returned else avg
+
+
+def select(condlist, choicelist, default=0):
+    if len(condlist) != len(choicelist):
+        raise ValueError("list of cases must be same length as list of conditions")
+    out = default
+    for c, v in zip(reversed(list(condlist)), reversed(list(choicelist))):
+        out = where(c, v, out)
+    return out
+
+
+def sinc(x):
+    x = asarray(x)
+    if x.dtype.kind != "f":
+        x = x.astype(np.float64)
+    y = np.pi * where(x == 0, 1.0e-20, x)
+    return elementwise("sin", np.sin, y) / y
+
+
+def cross(a, b, axisa=-1, axisb=-1, axisc=-1, axis=None):
+    if axis is not None:
+        axisa = axisb = axisc = axis
+    a, b = moveaxis(asarray(a), axisa, -1), moveaxis(asarray(b), axisb, -1)
+    if a.shape[-1] != 3 or b.shape[-1] != 3:
+        raise ValueError("autograd_b200: np.cross supports 3-vectors only")
+    a0, a1, a2 = a[..., 0], a[..., 1], a[..., 2]
+    b0, b1, b2 = b[..., 0], b[..., 1], b[..., 2]
+    out = stack([a1 * b2 - a2 * b1, a2 * b0 - a0 * b2, a0 * b1 - a1 * b0], axis=-1)
+    return moveaxis(out, -1, axisc)
+
+
+def gradient(f, *varargs, axis=None, edge_order=1):
+    """np.gradient with uniform spacing: central differences inside, one-sided first-order differences at the edges."""
+    f = asarray(f)
+    if edge_order != 1:
+        raise NotImplementedError("autograd_b200: np.gradient supports edge_order=1 only")
+    axes = tuple(range(f.ndim)) if axis is None else tuple(_normalize_axis(x, f.ndim) for x in np.atleast_1d(axis))
+    if len(varargs) == 0:
+        dx = [1.0] * len(axes)
+    elif len(varargs) == 1 and np.ndim(varargs[0]) == 0:
+        dx = [varargs[0]] * len(axes)
+    elif len(varargs) == len(axes) and all(np.ndim(v) == 0 for v in varargs):
+        dx = list(varargs)
+    else:
+        raise NotImplementedError("autograd_b200: np.gradient supports scalar spacings only")
+    if f.dtype.kind != "f":
+        f = f.astype(np.float64)
+    outs = []
+    for ax, h in zip(axes, dx):
+        if f.shape[ax] < 2:
+            raise ValueError("Shape of array too small to calculate a numerical gradient, at least 2 elements are required.")
+
+        def sl(s):
+            idx = [slice(None)] * f.ndim
+            idx[ax] = s
+            return tuple(idx)
+
+        inner = (f[sl(slice(2, None))] - f[sl(slice(None, -2))]) / (2.0 * h)
+        first = (f[sl(slice(1, 2))] - f[sl(slice(0, 1))]) / h
+        last = (f[sl(slice(-1, None))] - f[sl(slice(-2, -1))]) / h
+        outs.append(concatenate([first, inner, last], axis=ax))
+    return outs[0] if axis is not None and np.ndim(axis) == 0 or f.ndim == 1 and len(outs) == 1 else tuple(outs)
+
+
+def angle(z, deg=False):
+    z = asarray(z)
+    zero = zeros_like(z, dtype=z.dtype if z.dtype.kind == "f" else np.float64)
+    a = elementwise("arctan2", np.arctan2, zero, z)
+    return a * (180.0 / np.pi) if deg else a
+
+
+def real_if_close(a, tol=100):
+    return asarray(a)
+
+
 # =================================================================== indexing
 def _parse_index(shape, idx):
     """Classify ``idx``: ("basic", [(kind, ...)]) or ("adv", (index arrays, index shape, n leading dims))."""
@@ -1690,6 +1907,8 @@ UFUNC_OPS = {
     np.logical_and: "logical_and", np.logical_or: "logical_or", np.logical_xor: "logical_xor",
     np.logical_not: "logical_not", np.isfinite: "isfinite", np.isnan: "isnan", np.isinf: "isinf",
     np.conjugate: "conjugate", np.copysign: "copysign",
+    np.deg2rad: "deg2rad", np.radians: "deg2rad", np.rad2deg: "rad2deg", np.degrees: "rad2deg",
+    np.logaddexp2: "logaddexp2",
 }
 UFUNC_REDUCE = {np.add: "sum", np.multiply: "prod", np.maximum: "max", np.minimum: "min",
                 np.logical_and: "all", np.logical_or: "any"}
@@ -1722,7 +1941,10 @@ FUNCTIONS = {
     np.astype: lambda a, dtype, copy=True, **kw: asarray(a).astype(dtype),
     np.meshgrid: meshgrid, np.linspace: linspace,
     np.tril: tril, np.triu: triu, np.diag: diag, np.diagonal: diagonal, np.trace: trace, np.diff: diff,
+    np.cumsum: cumsum, np.cumprod: cumprod, np.sort: sort, np.argsort: argsort, np.kron: kron, np.rot90: rot90,
+    np.rollaxis: rollaxis, np.average: average, np.select: select, np.sinc: sinc, np.cross: cross,
+    np.gradient: gradient, np.angle: angle, np.real_if_close: real_if_close,
 }
 # NumPy's own pure-Python implementations of these only call other dispatched functions.
-DECOMPOSE = {np.hstack, np.vstack, np.dstack, np.column_stack, np.atleast_3d, np.rot90, np.kron,
+DECOMPOSE = {np.hstack, np.vstack, np.dstack, np.column_stack, np.atleast_3d,
              np.split, np.array_split, np.hsplit, np.vsplit, np.dsplit}

@@ -290,6 +290,18 @@ class CudaBackend:
         self._check(self._lib.b200ag_scatter_add(dst, src, dtype_code(dt), arr, len(idx_ptrs), _i64_array(dims),
                                                  n_index, inner))
 
+    def scatter_assign(self, dst, src, dt, idx_ptrs, dims, n_index: int, inner: int) -> None:
+        arr = (C.c_void_p * len(idx_ptrs))(*idx_ptrs)
+        self._check(self._lib.b200ag_scatter_assign(dst, src, dtype_code(dt), arr, len(idx_ptrs), _i64_array(dims),
+                                                    n_index, inner))
+
+    def cumulate(self, dst, src, dt, op: str, outer: int, n: int, inner: int) -> None:
+        self._check(self._lib.b200ag_cumulate(dst, src, dtype_code(dt), REDUCE_CODE[op], outer, n, inner))
+
+    def sort(self, keys_out, idx_out, src, dt, rows: int, n: int) -> None:
+        """Row-wise stable ascending sort; keys_out / idx_out (int64 argsort) may be None."""
+        self._check(self._lib.b200ag_sort(keys_out, idx_out, src, dtype_code(dt), rows, n))
+
     def conv2d(self, out, a, b, dt, N, Cc, H, W, F, kh, kw, mode: int, flip: int) -> None:
         self._check(self._lib.b200ag_conv2d(out, a, b, dtype_code(dt), N, Cc, H, W, F, kh, kw, mode, flip))
 

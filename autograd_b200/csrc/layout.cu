@@ -206,6 +206,19 @@ __global__ void __launch_bounds__(256) scatter_add_kernel(T* __restrict__ dst, c
   }
 }
 
+// x[idx] = values (integer-array item assignment, e.g. unpermuter in numpy_vjps.py:803-806).  With duplicate indices
+// NumPy keeps the last value; here the winner among duplicates is unspecified.
+template <typename T>
+__global__ void __launch_bounds__(256) scatter_assign_kernel(T* __restrict__ dst, const T* __restrict__ src,
+                                                              IndexDesc d, int64_t n_index, int64_t inner) {
+  int64_t n = n_index * inner;
+  int64_t step = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+    int64_t r = i / inner, c = i - r * inner;
+    dst[linear_row(d, r) * inner + c] = src[i];
+  }
+}
+
 }  // namespace b200ag
 
 using namespace b200ag;
@@ -301,6 +314,24 @@ int b200ag_scatter_add(void* dst, const void* src, int dtype, const int64_t* con
     case B200AG_I64: scatter_add_kernel<int64_t><<<grid, 256, 0, stream()>>>((int64_t*)dst, (const int64_t*)src, d, n_index, inner); break;
     case B200AG_I32: scatter_add_kernel<int32_t><<<grid, 256, 0, stream()>>>((int32_t*)dst, (const int32_t*)src, d, n_index, inner); break;
     default: B200AG_FAIL("scatter_add: unsupported dtype");
+  }
+  B200AG_LAUNCH_CHECK();
+  return 0;
+}
+
+int b200ag_scatter_assign(void* dst, const void* src, int dtype, const int64_t* const* idx, int nidx,
+                          const int64_t* dst_dims, int64_t n_index, int64_t inner) {
+  B200AG_CHECK_INIT();
+  IndexDesc d;
+  if (fill_index_desc(d, idx, nidx, dst_dims)) return 1;
+  int64_t n = n_index * inner;
+  if (n == 0) return 0;
+  unsigned grid = grid_for(n, 256, 16);
+  switch (dtype_size(dtype)) {
+    case 8: scatter_assign_kernel<int64_t><<<grid, 256, 0, stream()>>>((int64_t*)dst, (const int64_t*)src, d, n_index, inner); break;
+    case 4: scatter_assign_kernel<int32_t><<<grid, 256, 0, stream()>>>((int32_t*)dst, (const int32_t*)src, d, n_index, inner); break;
+    case 1: scatter_assign_kernel<uint8_t><<<grid, 256, 0, stream()>>>((uint8_t*)dst, (const uint8_t*)src, d, n_index, inner); break;
+    default: B200AG_FAIL("scatter_assign: unsupported dtype");
   }
   B200AG_LAUNCH_CHECK();
   return 0;

@@ -313,6 +313,32 @@ def install(creation: bool = True):
     nw.parse_einsum_input = parse_einsum_input
     anp.parse_einsum_input = parse_einsum_input
 
+    # ------------------------------------------------------------ np.select on device values
+    # numpy_wrapper.py:110-112 builds the result element by element from an object array of boxes; on device operands
+    # the same "first true condition wins" is composed from the traced ``where`` primitive instead.
+    from autograd.tracer import isbox
+
+    def getval(v):
+        while isbox(v):
+            v = v._value
+        return v
+
+    ref_select = nw.select
+
+    def select(condlist, choicelist, default=0):
+        condlist, choicelist = list(condlist), list(choicelist)
+        if not any(isinstance(getval(v), DeviceArray) for v in condlist + choicelist + [default]):
+            return ref_select(condlist, choicelist, default)
+        if len(condlist) != len(choicelist):
+            raise ValueError("list of cases must be same length as list of conditions")
+        out = default
+        for c, v in zip(reversed(condlist), reversed(choicelist)):
+            out = anp.where(c, v, out)
+        return out
+
+    nw.select = select
+    anp.select = select
+
     # ------------------------------------------------------------ creation functions
     if creation:
         def switchable(dev_fn, host_fn):

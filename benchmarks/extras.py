@@ -252,6 +252,18 @@ def kernels(be):
         B = b200.asarray(onp.random.RandomState(5).rand(K, N))
         r = time_device(be, lambda: np.dot(A, B), warmup=2, reps=10)
         out[f"dgemm {M}x{N}x{K}"] = {"ms": r["ms"], "TFLOP/s": 2.0 * M * N * K / (r["ms"] * 1e-3) / 1e12}
+    # float32 products on tcgen05 (3xTF32): forward shape, and the two VJP shapes G B^T / A^T G (transposed views)
+    for (M, N, K) in ((8192, 8192, 4096), (4096, 4096, 4096), (1024, 512, 16384)):
+        A = b200.asarray(onp.random.RandomState(4).rand(M, K).astype(onp.float32))
+        B = b200.asarray(onp.random.RandomState(5).rand(K, N).astype(onp.float32))
+        G = b200.asarray(onp.random.RandomState(6).rand(M, N).astype(onp.float32))
+        for name, fn, flops in ((f"sgemm(3xTF32, tcgen05) {M}x{N}x{K}", lambda: np.dot(A, B), 2.0 * M * N * K),
+                                (f"  its VJP wrt A (G B^T) {M}x{K}x{N}", lambda: np.dot(G, B.T), 2.0 * M * N * K),
+                                (f"  its VJP wrt B (A^T G) {K}x{N}x{M}", lambda: np.dot(A.T, G), 2.0 * M * N * K)):
+            r = time_device(be, fn, warmup=2, reps=5)
+            tf = flops / (r["ms"] * 1e-3) / 1e12
+            out[name] = {"ms": r["ms"], "TFLOP/s fp32-equivalent": tf, "TF32 TFLOP/s": 3 * tf,
+                         "frac_of_nominal_tf32_peak": 3 * tf / 1100.0, "launches": r["launches"]}
     return out
 
 

@@ -161,6 +161,27 @@ int b200ag_gather(void* dst, const void* src, int dtype,
 int b200ag_scatter_add(void* dst, const void* src, int dtype,
                        const int64_t* const* idx, int nidx, const int64_t* dst_dims,
                        int64_t n_index, int64_t inner);
+/* x[idx] = values for integer index arrays (item assignment on a raw array, e.g.
+ * `unsort[permutation] = range(n)` in unpermuter, numpy_vjps.py:803-806).  Same
+ * index convention as b200ag_scatter_add; the winner among duplicate indices is
+ * unspecified (NumPy: the last one). */
+int b200ag_scatter_assign(void* dst, const void* src, int dtype,
+                          const int64_t* const* idx, int nidx, const int64_t* dst_dims,
+                          int64_t n_index, int64_t inner);
+
+/* ---------------------------------------------------------------- scans and sorts
+ * b200ag_cumulate: np.cumsum (op = B200AG_SUM) / np.cumprod (B200AG_PROD) along the
+ * middle axis of a contiguous [outer, n, inner] view (numpy_vjps.py:539-549).
+ * b200ag_sort: every row of a contiguous [rows, n] array sorted ascending in NumPy's
+ * order (NaN last); keys_out receives the sorted values, idx_out the int64 argsort
+ * (either may be NULL).  The sort is stable, so indices are bit-exact against
+ * np.argsort(kind="stable") and, without ties, against any kind
+ * (np.sort / np.argsort behind grad_sort, numpy_vjps.py:774-812). */
+int b200ag_cumulate(void* dst, const void* src, int dtype, int op,
+                    int64_t outer, int64_t n, int64_t inner);
+int b200ag_sort(void* keys_out, int64_t* idx_out, const void* src, int dtype,
+                int64_t rows, int64_t n);
+
 
 /* ---------------------------------------------------------------- logsumexp
  * scipy.special.logsumexp(a, axis, keepdims=True) over the middle axis of

@@ -868,3 +868,89 @@ def grad_case_f32_tensor_core_contractions():
 
 
 GRAD_CASES["f32_tensor_core_contractions"] = grad_case_f32_tensor_core_contractions
+
+
+def case_scan_sort_surface():
+    """cumsum/cumprod, sort/argsort (indices bit-exact), item assignment with index arrays, and the
+    composed functions kron / rot90 / rollaxis / average / select / sinc / cross / gradient / deg2rad / logaddexp2."""
+    r = rs(80)
+    a = r.randn(7, 300)
+    check(lambda a: onp.cumsum(a, axis=1), a, tol=TOL_REDUCE, what="cumsum last axis")
+    check(lambda a: onp.cumsum(a, axis=0), a, tol=TOL_ELEMENTWISE, what="cumsum axis 0 (sequential, same order)")
+    check(lambda a: onp.cumsum(a), a, tol=TOL_REDUCE, what="cumsum flattened")
+    check(lambda a: onp.cumprod(1.0 + 0.01 * a, axis=1), a, tol=TOL_REDUCE, what="cumprod")
+    big = r.randn(3, 40000)
+    check(lambda a: onp.cumsum(a, axis=1), big, tol=TOL_REDUCE, what="cumsum long rows (segmented scan)")
+    check(lambda a: onp.cumsum(a.astype(onp.float32), axis=1), big[:, :5000], tol=TOL_F32, what="cumsum f32")
+    ints = r.randint(-50, 50, (5, 1000))
+    check(lambda a: onp.cumsum(a, axis=1), ints, what="cumsum int64 exact")
+    # sort / argsort: distinct keys -> indices bit-exact for any kind; ties + NaN -> compare against kind='stable'
+    for shape in ((1000,), (6, 257), (3, 5000), (2, 3, 64)):
+        x = r.randn(*shape)
+        check(lambda x: onp.sort(x, axis=-1), x, what=f"sort {shape}")
+        check(lambda x: onp.argsort(x, axis=-1), x, what=f"argsort {shape}")
+    x = r.randn(50, 40)
+    check(lambda x: (onp.sort(x, axis=0), onp.argsort(x, axis=0)), x, what="sort axis 0")
+    check(lambda x: onp.sort(x, axis=None), x, what="sort flattened")
+    t = onp.round(r.randn(4, 600) * 3.0)
+    t[1, 5] = onp.nan
+    t[1, 77] = onp.nan
+    t[2, 0] = onp.inf
+    t[2, 9] = -onp.inf
+    check(lambda x: onp.argsort(x, axis=1, kind="stable"), t, what="argsort ties/NaN/inf (stable)")
+    check(lambda x: onp.sort(x, axis=1), t, what="sort ties/NaN/inf")
+    check(lambda x: onp.argsort(x, kind="stable"), r.randint(0, 20, 5000), what="argsort int64 stable")
+    check(lambda x: onp.sort(x.astype(onp.float32)), r.randn(3000), what="sort f32")
+    # item assignment with an index array (unpermuter)
+    perm = r.permutation(500)
+    dev = b200.array.zeros(500, dtype=onp.int64)
+    dev[b200.asarray(perm)] = list(range(500))
+    want = onp.zeros(500, dtype=onp.int64)
+    want[perm] = list(range(500))
+    assert onp.array_equal(dev.get(), want)
+    m, v3, w3 = r.randn(4, 6), r.randn(5, 3), r.randn(5, 3)
+    check(lambda a, b: onp.kron(a, b), m, r.randn(3, 2), what="kron")
+    check(lambda a: onp.kron(a, a[0]), m, what="kron 2-D x 1-D")
+    for k in range(4):
+        check(lambda a: onp.rot90(a, k), m, what=f"rot90 k={k}")
+    check(lambda a: onp.rollaxis(a.reshape(2, 2, 6), 2, 0), m, what="rollaxis")
+    check(lambda a: (onp.average(a), onp.average(a, axis=1), onp.average(a, axis=0, weights=onp.arange(1.0, 5.0))), m,
+          tol=TOL_REDUCE, what="average")
+    check(lambda a: onp.select([a > 1, a < -1], [a * 2, a * a], 0.5), m, what="select")
+    check(lambda a: onp.sinc(a), onp.concatenate([m.ravel(), [0.0]]), what="sinc")
+    check(lambda a, b: onp.cross(a, b), v3, w3, what="cross")
+    check(lambda a: onp.gradient(a, axis=1), m, what="gradient axis")
+    check(lambda a: onp.gradient(a, 0.5), m[0], what="gradient 1-D spacing")
+    check(lambda a: onp.gradient(a), m, what="gradient all axes")
+    check(lambda a: (onp.deg2rad(a), onp.rad2deg(a), onp.radians(a), onp.degrees(a)), m, what="deg/rad")
+    check(lambda a: onp.deg2rad(a.astype(onp.float32)), m, tol=TOL_F32, what="deg2rad f32")
+    check(lambda a, b: onp.logaddexp2(a, b), m, m[::-1] * 2.0, what="logaddexp2")
+
+
+OP_CASES["scan_sort_surface"] = case_scan_sort_surface
+
+
+def grad_case_scan_sort_surface():
+    """Reference VJP rules of the widened surface on the device type: cumsum (numpy_vjps.py:539-549), sort
+    (:774-789, through argsort + unpermuter's index-array assignment), kron, cross, gradient, sinc, ..."""
+    import autograd.numpy as np
+
+    r = rs(81)
+    a = r.randn(6, 40)
+    v = r.randn(200)
+    check_grad(lambda x: np.sum(np.cumsum(x, axis=1) ** 2), (a,), TOL_REDUCE, "cumsum axis 1")
+    check_grad(lambda x: np.sum(np.cumsum(x, axis=0) * x), (a,), TOL_REDUCE, "cumsum axis 0")
+    check_grad(lambda x: np.sum(np.cumsum(x) ** 2), (v,), TOL_REDUCE, "cumsum flat")
+    check_grad(lambda x: np.sum(np.sort(x) * np.arange(200.0)), (v,), TOL_REDUCE, "sort 1-D")
+    check_grad(lambda x: np.sum(np.kron(x, x[:2, :3]) ** 2), (a,), TOL_REDUCE, "kron")
+    check_grad(lambda x: np.sum(np.cross(x[:, :3], x[:, 3:6]) ** 2), (a,), TOL_REDUCE, "cross")
+    check_grad(lambda x: np.sum(np.gradient(x, axis=1) ** 2), (a,), TOL_REDUCE, "gradient")
+    check_grad(lambda x: np.sum(np.sinc(x) * x), (a,), TOL_REDUCE, "sinc")
+    check_grad(lambda x: np.sum(np.deg2rad(x) ** 2 + np.rad2deg(x)), (a,), TOL_REDUCE, "deg2rad/rad2deg")
+    check_grad(lambda x: np.sum(np.logaddexp2(x, 2.0 * x)), (a,), TOL_REDUCE, "logaddexp2")
+    check_grad(lambda x: np.sum(np.rot90(x)[:5, :5] * x[:5, :5]), (a,), TOL_REDUCE, "rot90")
+    check_grad(lambda x: np.sum(np.rollaxis(x, 1)[3] ** 2), (a,), TOL_REDUCE, "rollaxis")
+    check_grad(lambda x: np.sum(np.select([x > 0.5], [x ** 2], x)), (a,), TOL_REDUCE, "select")
+
+
+GRAD_CASES["scan_sort_surface"] = grad_case_scan_sort_surface

@@ -27,6 +27,7 @@ _OPS1 = {
     "cosh": np.cosh, "tanh": np.tanh, "arcsinh": np.arcsinh, "arccosh": np.arccosh, "arctanh": np.arctanh,
     "floor": np.floor, "ceil": np.ceil, "trunc": np.trunc, "rint": np.rint, "logical_not": np.logical_not,
     "isfinite": np.isfinite, "isnan": np.isnan, "isinf": np.isinf, "conjugate": np.conjugate,
+    "deg2rad": np.deg2rad, "rad2deg": np.rad2deg,
 }
 _OPS2 = {
     "add": np.add, "subtract": np.subtract, "multiply": np.multiply, "divide": np.true_divide, "power": np.power,
@@ -35,6 +36,7 @@ _OPS2 = {
     "less_equal": np.less_equal, "greater": np.greater, "greater_equal": np.greater_equal,
     "logical_and": np.logical_and, "logical_or": np.logical_or, "logical_xor": np.logical_xor,
     "arctan2": np.arctan2, "hypot": np.hypot, "logaddexp": np.logaddexp, "copysign": np.copysign,
+    "logaddexp2": np.logaddexp2,
 }
 
 
@@ -374,6 +376,33 @@ class FakeBackend:
         d = del_[d0: d0 + total].reshape(-1, inner)
         sel, s0 = self._elems(src, dt)
         np.add.at(d, row, sel[s0: s0 + n_index * inner].reshape(n_index, inner))
+
+    def scatter_assign(self, dst, src, dt, idx_ptrs, dims, n_index, inner):
+        self._launches += 1
+        row = self._rows(idx_ptrs, dims, n_index)
+        del_, d0 = self._elems(dst, dt)
+        total = int(np.prod(dims)) * inner
+        d = del_[d0: d0 + total].reshape(-1, inner)
+        sel, s0 = self._elems(src, dt)
+        d[row] = sel[s0: s0 + n_index * inner].reshape(n_index, inner)
+
+    def cumulate(self, dst, src, dt, op, outer, n, inner):
+        self._launches += 1
+        s = self._view3(src, dt, outer, n, inner)
+        d = self._view3(dst, dt, outer, n, inner)
+        d[...] = (np.cumsum if op == "sum" else np.cumprod)(s, axis=1, dtype=np.dtype(dt))
+
+    def sort(self, keys_out, idx_out, src, dt, rows, n):
+        self._launches += 1
+        sel, s0 = self._elems(src, dt)
+        s = sel[s0: s0 + rows * n].reshape(rows, n)
+        order = np.argsort(s, axis=1, kind="stable")
+        if keys_out is not None:
+            kel, k0 = self._elems(keys_out, dt)
+            kel[k0: k0 + rows * n] = np.take_along_axis(s, order, axis=1).reshape(-1)
+        if idx_out is not None:
+            iel, i0 = self._elems(idx_out, np.int64)
+            iel[i0: i0 + rows * n] = order.reshape(-1)
 
     def conv2d(self, out, a, b, dt, N, C, H, W, F, kh, kw, mode, flip):
         self._launches += 1

@@ -178,6 +178,41 @@ def test_gemm_f32_mode_switch_and_dispatch(abi):
     assert not np.array_equal(results[0], results[1])         # really two different kernels
 
 
+def test_cumulate_and_sort(abi):
+    """b200ag_cumulate against np.cumsum/np.cumprod; b200ag_sort against np.sort / np.argsort(kind='stable') with ties,
+    NaN and infinities (indices bit-exact), rows longer than one shared-memory tile, non-power-of-two lengths."""
+    r = np.random.RandomState(9)
+    x = r.randn(5, 70000)
+    out = abi.empty(x.nbytes)
+    abi.ok(abi.lib.b200ag_cumulate(out, abi.put(x), F64, 0, 5, 70000, 1))
+    want = np.cumsum(x, axis=1)
+    assert np.abs(abi.get(out, x.shape, np.float64) - want).max() <= 1e-10 * np.abs(want).max()
+    y = r.randn(4, 33, 6)
+    out = abi.empty(y.nbytes)
+    abi.ok(abi.lib.b200ag_cumulate(out, abi.put(y), F64, 0, 4, 33, 6))
+    assert np.array_equal(abi.get(out, y.shape, np.float64), np.cumsum(y, axis=1))     # same order as NumPy
+    p = 1.0 + 0.001 * r.randn(3, 5000)
+    out = abi.empty(p.nbytes)
+    abi.ok(abi.lib.b200ag_cumulate(out, abi.put(p), F64, 3, 3, 5000, 1))
+    assert np.allclose(abi.get(out, p.shape, np.float64), np.cumprod(p, axis=1), rtol=1e-11, atol=0)
+    for rows, n in ((1, 1), (3, 7), (4, 2048), (2, 2049), (3, 10000), (1, 300001)):
+        k = np.round(r.randn(rows, n) * 50.0) if n > 100 else r.randn(rows, n)
+        if n > 100:
+            k[0, 3] = np.nan
+            k[0, n // 2] = np.nan
+            k[-1, 1] = np.inf
+            k[-1, 2] = -np.inf
+        keys, idx = abi.empty(k.nbytes), abi.empty(k.size * 8)
+        abi.ok(abi.lib.b200ag_sort(keys, idx, abi.put(k), F64, rows, n))
+        order = np.argsort(k, axis=1, kind="stable")
+        assert np.array_equal(abi.get(idx, k.shape, np.int64), order), (rows, n)
+        assert np.array_equal(abi.get(keys, k.shape, np.float64), np.take_along_axis(k, order, axis=1), equal_nan=True)
+    ki = r.randint(-1000, 1000, (2, 5000)).astype(np.int32)
+    idx = abi.empty(ki.size * 8)
+    abi.ok(abi.lib.b200ag_sort(None, idx, abi.put(ki), I32, 2, 5000))
+    assert np.array_equal(abi.get(idx, ki.shape, np.int64), np.argsort(ki, axis=1, kind="stable"))
+
+
 def test_gather_scatter_add(abi):
     rs = np.random.RandomState(4)
     f = rs.randn(50, 40)
