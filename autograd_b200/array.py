@@ -1910,6 +1910,19 @@ UFUNC_OPS = {
     np.deg2rad: "deg2rad", np.radians: "deg2rad", np.rad2deg: "rad2deg", np.degrees: "rad2deg",
     np.logaddexp2: "logaddexp2",
 }
+try:   # scipy.special's ufuncs arrive through __array_ufunc__ like NumPy's (autograd/scipy/special.py wraps them)
+    import scipy.special as _sps
+
+    for _name, _op in (("erf", "sp_erf"), ("erfc", "sp_erfc"), ("erfinv", "sp_erfinv"), ("erfcinv", "sp_erfcinv"),
+                       ("erfcx", "sp_erfcx"), ("gammaln", "sp_gammaln"), ("gamma", "sp_gamma"), ("psi", "sp_digamma"),
+                       ("digamma", "sp_digamma"), ("ndtr", "sp_ndtr"), ("ndtri", "sp_ndtri"), ("log_ndtr", "sp_log_ndtr"),
+                       ("expit", "sp_expit"), ("logit", "sp_logit"), ("j0", "sp_j0"), ("j1", "sp_j1"), ("y0", "sp_y0"),
+                       ("y1", "sp_y1"), ("i0", "sp_i0"), ("i1", "sp_i1")):
+        _uf = getattr(_sps, _name, None)
+        if isinstance(_uf, np.ufunc):
+            UFUNC_OPS[_uf] = _op
+except ImportError:   # SciPy is an optional dependency of the reference (pyproject.toml:55-56)
+    pass
 UFUNC_REDUCE = {np.add: "sum", np.multiply: "prod", np.maximum: "max", np.minimum: "min",
                 np.logical_and: "all", np.logical_or: "any"}
 

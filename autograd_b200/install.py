@@ -313,6 +313,44 @@ def install(creation: bool = True):
     nw.parse_einsum_input = parse_einsum_input
     anp.parse_einsum_input = parse_einsum_input
 
+    # ------------------------------------------------------------ scipy.stats.norm (autograd/scipy/stats/norm.py:9-14)
+    # pdf/cdf/sf/logpdf/logcdf/logsf are primitives around scipy.stats.norm methods, which coerce to ndarray; on device
+    # operands the same formulas (scipy/stats/_continuous_distns.py norm_gen: _norm_pdf, ndtr, log_ndtr) are composed from
+    # device ufuncs.  The reference's VJPs (norm.py:16-82) are kept.
+    try:
+        import scipy.special as sps
+        import autograd.scipy.stats.norm as anorm
+    except ImportError:
+        anorm = None
+    if anorm is not None:
+        log_sqrt_2pi = 0.9189385332046727417803297364056176398     # _norm_pdf_logC
+        sqrt_2pi = 2.506628274631000502415765284811045253          # _norm_pdf_C
+
+        def _standardise(x, loc, scale):
+            return (A.asarray(x) - loc) / scale
+
+        def _norm_raw(name, ref):
+            def raw(x, loc=0.0, scale=1.0):
+                if not any(isinstance(v, DeviceArray) for v in (x, loc, scale)):
+                    return ref(x, loc, scale)
+                y = _standardise(x, loc, scale)
+                if name == "pdf":
+                    return onp.exp(-(y ** 2) / 2.0) / sqrt_2pi / scale
+                if name == "logpdf":
+                    return -(y ** 2) / 2.0 - log_sqrt_2pi - onp.log(scale)
+                if name == "cdf":
+                    return sps.ndtr(y)
+                if name == "sf":
+                    return sps.ndtr(-y)
+                if name == "logcdf":
+                    return sps.log_ndtr(y)
+                return sps.log_ndtr(-y)
+            return raw
+
+        for _name in ("pdf", "logpdf", "cdf", "sf", "logcdf", "logsf"):
+            _prim = getattr(anorm, _name)
+            _swap_raw(_prim, _norm_raw(_name, _prim.fun))
+
     # ------------------------------------------------------------ np.select on device values
     # numpy_wrapper.py:110-112 builds the result element by element from an object array of boxes; on device operands
     # the same "first true condition wins" is composed from the traced ``where`` primitive instead.

@@ -954,3 +954,64 @@ def grad_case_scan_sort_surface():
 
 
 GRAD_CASES["scan_sort_surface"] = grad_case_scan_sort_surface
+
+
+def case_scipy_special_ufuncs():
+    """scipy.special ufuncs reached through autograd.scipy.special (special.py:42-117) on the device: CUDA libm twins
+    (erf family, lgamma/tgamma, normcdf, Bessel j0/j1/y0/y1/i0/i1) plus generated expit/logit/digamma/log_ndtr."""
+    import scipy.special as sps
+
+    r = rs(90)
+    x = r.randn(3000) * 2.0
+    pos = onp.abs(x) + 0.05
+    unit = r.rand(3000) * 0.98 + 0.01
+    tol = 1e-12
+    for name, arg in (("erf", x), ("erfc", x), ("erfcx", x), ("ndtr", x * 2), ("log_ndtr", x * 4), ("expit", x * 5),
+                      ("j0", x * 5), ("j1", x * 5), ("i0", x), ("i1", x), ("y0", pos * 5), ("y1", pos * 5),
+                      ("gammaln", pos * 6), ("gamma", pos * 4), ("psi", pos * 6), ("psi", -pos * 3 - 0.013),
+                      ("erfinv", unit * 2 - 1), ("erfcinv", unit * 2 * 0.99 + 0.005), ("ndtri", unit), ("logit", unit)):
+        fn = getattr(sps, name)
+        check(lambda a, fn=fn: fn(a), arg, tol=tol, what=f"scipy.special.{name}")
+    check(lambda a: sps.erf(a.astype(onp.float32)), x, tol=TOL_F32, what="erf f32")
+    edge = onp.array([0.0, -0.0, onp.inf, -onp.inf, onp.nan, 1.0, 2.0, -1.0, 1e-300, 170.0])
+    check(lambda a: (sps.erf(a), sps.expit(a), sps.ndtr(a)), edge, tol=tol, what="special edge values")
+    check(lambda a: sps.gammaln(a), onp.array([1.0, 2.0, 0.5, 1e-8, 100.0, 1e6, onp.inf]), tol=tol, what="gammaln edges")
+    check(lambda a: sps.psi(a), onp.array([1.0, 0.5, 1e-6, 100.0, 1e8, -0.5, -2.5, onp.inf]), tol=tol, what="psi edges")
+
+
+OP_CASES["scipy_special_ufuncs"] = case_scipy_special_ufuncs
+
+
+def grad_case_scipy_stats_norm():
+    """autograd.scipy.stats.norm on device operands (norm.py:9-82) — every function, every argument — and a
+    black-box-SVI style objective (examples/black_box_svi.py:16-38: Gaussian entropy + Monte-Carlo log-density with
+    host-side random draws mixed into device computations)."""
+    import autograd.numpy as np
+    import autograd.scipy.stats.norm as norm
+    from autograd.scipy.special import erf, expit, gammaln
+
+    r = rs(91)
+    x, loc, scale = r.randn(5, 40), r.randn(40) * 0.3, onp.abs(r.randn(40)) + 0.5
+    for name in ("pdf", "logpdf", "cdf", "sf", "logcdf", "logsf"):
+        fn = getattr(norm, name)
+        for argnum in (0, 1, 2):
+            check_grad(lambda x, l, s, fn=fn: np.sum(fn(x, l, s) * np.cos(x)), (x, loc, scale), TOL_REDUCE,
+                       f"norm.{name} wrt arg {argnum}", argnum=argnum)
+    check_grad(lambda x: np.sum(erf(x) * expit(x) + gammaln(x ** 2 + 1.0)), (x,), TOL_REDUCE, "special-function chain")
+    D, S = 40, 64
+    eps = r.randn(S, D)          # the example draws its samples on the host (npr.RandomState); only params are traced
+
+    def logprob(z):
+        return norm.logpdf(z[:, 0], 0.0, 1.35) + np.sum(norm.logpdf(z[:, 1:], 0.0, np.exp(z[:, :1])), axis=1)
+
+    def neg_elbo(params, eps):
+        mean, log_std = params[:D], params[D:]
+        samples = eps * np.exp(log_std) + mean
+        entropy = 0.5 * D * (1.0 + np.log(2 * np.pi)) + np.sum(log_std)
+        return -(entropy + np.mean(logprob(samples)))
+
+    check_grad(neg_elbo, (onp.concatenate([r.randn(D) * 0.1, -1.0 + 0.1 * r.randn(D)]), eps), TOL_REDUCE,
+               "black-box SVI objective")
+
+
+GRAD_CASES["scipy_stats_norm"] = grad_case_scipy_stats_norm

@@ -40,6 +40,16 @@ _OPS2 = {
 }
 
 
+import scipy.special as _sps
+
+_OPS1.update({
+    "sp_erf": _sps.erf, "sp_erfc": _sps.erfc, "sp_erfinv": _sps.erfinv, "sp_erfcinv": _sps.erfcinv, "sp_erfcx": _sps.erfcx,
+    "sp_gammaln": _sps.gammaln, "sp_gamma": _sps.gamma, "sp_digamma": _sps.psi, "sp_ndtr": _sps.ndtr,
+    "sp_ndtri": _sps.ndtri, "sp_log_ndtr": _sps.log_ndtr, "sp_expit": _sps.expit, "sp_logit": _sps.logit,
+    "sp_j0": _sps.j0, "sp_j1": _sps.j1, "sp_y0": _sps.y0, "sp_y1": _sps.y1, "sp_i0": _sps.i0, "sp_i1": _sps.i1,
+})
+
+
 class FakeBackend:
     name = "fake-host"
     sm_count = 148
