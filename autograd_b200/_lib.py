@@ -76,6 +76,7 @@ PROTOTYPES = {
                       C.c_int, C.c_int],
     "b200ag_conv2d_wgrad": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64,
                             c_i64],
+    "b200ag_conv_mode": [C.c_int, C.POINTER(C.c_int)],
     "b200ag_comm_create": [C.c_int, C.c_int, C.c_size_t, C.c_void_p],
     "b200ag_comm_connect": [C.c_void_p],
     "b200ag_comm_allreduce_sum_f64": [C.c_void_p, C.c_void_p, c_i64],

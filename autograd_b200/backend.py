@@ -305,6 +305,12 @@ class CudaBackend:
     def conv2d(self, out, a, b, dt, N, Cc, H, W, F, kh, kw, mode: int, flip: int) -> None:
         self._check(self._lib.b200ag_conv2d(out, a, b, dtype_code(dt), N, Cc, H, W, F, kh, kw, mode, flip))
 
+    def conv_mode(self, direct: int) -> int:
+        """1 = direct CUDA-core kernels for few-channel float64 layers (default), 0 = DMMA implicit GEMM only."""
+        prev = C.c_int(0)
+        self._check(self._lib.b200ag_conv_mode(direct, C.byref(prev)))
+        return prev.value
+
     def conv2d_wgrad(self, db, a, g, dt, N, Cc, H, W, F, kh, kw) -> None:
         self._check(self._lib.b200ag_conv2d_wgrad(db, a, g, dtype_code(dt), N, Cc, H, W, F, kh, kw))
 

@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libb200ag.so")
 STAMP_PATH = os.path.join(HERE, "csrc", ".build_stamp")
 
-SOURCES = ["core.cu", "layout.cu", "reduce.cu", "gemm.cu", "gemm_tc.cu", "scan_sort.cu", "conv.cu", "comm.cu"]
+SOURCES = ["core.cu", "layout.cu", "reduce.cu", "gemm.cu", "gemm_tc.cu", "scan_sort.cu", "conv.cu", "conv_direct.cu", "comm.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -16,6 +16,13 @@
 
 namespace b200ag {
 
+// conv_direct.cu: register-tiled CUDA-core kernels for layers with few output channels (0 done, 1 error, 2 not covered)
+int conv2d_direct_try(double* out, const double* A, const double* B, int64_t N, int C, int H, int W, int F, int kh, int kw,
+                      int Ho, int Wo, int py, int px, int flip);
+int conv2d_wgrad_direct_try(double* dB, const double* A, const double* G, int64_t N, int C, int H, int W, int F, int kh,
+                            int kw, int Ho, int Wo);
+int g_conv_direct = 1;   // b200ag_conv_mode: 0 = implicit-GEMM DMMA kernels only
+
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(c0), "+d"(c1)
@@ -383,6 +390,11 @@ int b200ag_conv2d(void* out, const void* A, const void* B, int dtype, int64_t N,
   }
   int64_t total = N * F * Ho * Wo;
   if (total == 0) return 0;
+  if (dtype == B200AG_F64 && g_conv_direct && F <= 8 && C <= 4) {
+    int rc = conv2d_direct_try((double*)out, (const double*)A, (const double*)B, N, (int)C, (int)H, (int)W, (int)F, (int)kh,
+                               (int)kw, (int)Ho, (int)Wo, (int)py, (int)px, flip);
+    if (rc != 2) return rc;
+  }
   if (dtype == B200AG_F64 && F <= 16) {
     ConvArgs g;
     g.out = (double*)out; g.A = (const double*)A; g.B = (const double*)B;
@@ -425,6 +437,11 @@ int b200ag_conv2d_wgrad(void* dB, const void* A, const void* G, int dtype, int64
   if (es == 0) B200AG_FAIL("conv2d_wgrad: unsupported dtype");
   if (b200ag_memset(dB, 0, (size_t)nout * es)) return 1;
   if (N == 0 || nout == 0) return 0;
+  if (dtype == B200AG_F64 && g_conv_direct && F <= 8 && C <= 4) {
+    int rc = conv2d_wgrad_direct_try((double*)dB, (const double*)A, (const double*)G, N, (int)C, (int)H, (int)W, (int)F,
+                                     (int)kh, (int)kw, (int)Ho, (int)Wo);
+    if (rc != 2) return rc;
+  }
   if (dtype == B200AG_F64 && F <= 16 && (C * kh * kw + 7) / 8 <= 24) {
     WgradArgs g;
     g.dB = (double*)dB; g.A = (const double*)A; g.G = (const double*)G;
@@ -463,6 +480,14 @@ int b200ag_conv2d_wgrad(void* dB, const void* A, const void* G, int dtype, int64
   else
     B200AG_FAIL("conv2d_wgrad: unsupported dtype");
   B200AG_LAUNCH_CHECK();
+  return 0;
+}
+
+// 1 (default): layers with few output channels use the direct CUDA-core kernels of conv_direct.cu; 0: always the
+// implicit-GEMM DMMA kernels.  Returns the previous setting through *previous (may be null).
+int b200ag_conv_mode(int direct, int* previous) {
+  if (previous) *previous = g_conv_direct;
+  if (direct == 0 || direct == 1) g_conv_direct = direct;
   return 0;
 }
 

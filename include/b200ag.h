@@ -203,6 +203,11 @@ int b200ag_conv2d(void* out, const void* A, const void* B, int dtype,
 int b200ag_conv2d_wgrad(void* dB, const void* A, const void* G, int dtype,
                         int64_t N, int64_t C, int64_t H, int64_t W,
                         int64_t F, int64_t kh, int64_t kw);
+/* Kernel family for float64 convolutions: 1 (default) = layers with few output channels
+ * (F <= 8, C <= 4, 3- or 5-wide filters) run on register-tiled CUDA-core kernels, everything
+ * else on the implicit-GEMM DMMA kernels; 0 = DMMA kernels only. */
+int b200ag_conv_mode(int direct, int* previous);
+
 
 /* ---------------------------------------------------------------- gradient allreduce over NVLink peer memory
  * Not in the reference (single process).  Sum of batch-sharded gradient vectors, one process per GPU: every rank
