@@ -1675,6 +1675,12 @@ def tensordot(a, b, axes=2):
     b2 = reshape(transpose(b, axes_b + free_b), (K, N))
     if K == 0:
         return zeros(out_shape, _float_result(a, b))
+    if K == 1:
+        # outer product (e.g. the 1-D . 1-D dot adjoint tensordot(g, B, 0), numpy_vjps.py:621): a lazy broadcast multiply
+        # that fuses into its consumer instead of a K=1 GEMM over M x N tiles
+        dt = _float_result(a, b)
+        prodv = reshape(a2, (M, 1)) * reshape(b2, (1, N))
+        return reshape(prodv if prodv.dtype == dt else prodv.astype(dt), out_shape)
     return reshape(_gemm2d(a2, b2), out_shape)
 
 

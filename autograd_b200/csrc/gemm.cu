@@ -231,7 +231,8 @@ extern "C" int b200ag_gemm(void* C, int c_dtype, int64_t c_rs, int64_t c_cs, int
   // aim for ONE full wave: 3 CTAs of the 64x64 kernel are resident per SM (register-limited)
   int64_t slots = 3 * (int64_t)sm_count();
   int64_t want = slots / tiles;
-  int64_t max_by_k = K / 128;
+  // tiny outputs (a handful of tiles) are pure load-latency chains of K/16 dependent slabs: cut K finer there
+  int64_t max_by_k = (tiles <= (int64_t)sm_count() / 4) ? K / 48 : K / 128;
   int64_t splits = want < max_by_k ? want : max_by_k;
   if (splits > 64) splits = 64;
   void* scratch = nullptr;

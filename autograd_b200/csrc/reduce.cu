@@ -180,6 +180,7 @@ static int reduce_impl(T* dst, const T* src, int64_t outer, int64_t reduce, int6
       if (split > max_split) split = max_split;
       if (split < 1) split = 1;
     }
+    if (outer * reduce <= 65536) split = 1;   // tiny inputs: a second launch costs more than the parallelism gains
     int64_t chunk = (reduce + split - 1) / split;
     split = (reduce + chunk - 1) / chunk;
     if (split == 1) {
@@ -210,6 +211,7 @@ static int reduce_impl(T* dst, const T* src, int64_t outer, int64_t reduce, int6
     if (split > max_split) split = max_split;
     if (split < 1) split = 1;
   }
+  if (outer * reduce * inner <= 131072) split = 1;   // tiny inputs (bias gradients): one launch instead of two
   int64_t chunk = (reduce + split - 1) / split;
   split = (reduce + chunk - 1) / chunk;
   int64_t nwork = base * split;
