@@ -11,6 +11,7 @@ host; payloads live in HBM and are only produced by libb200ag.so kernels.
 from __future__ import annotations
 
 import numbers
+import weakref
 import operator
 
 import numpy as np
@@ -408,7 +409,9 @@ class DeviceArray:
         if node.mat is None:
             lazy.materialize(node)
         m = node.mat
-        if m.shifts is not None or any(st == 0 and s > 1 for s, st in zip(m.shape, m.strides)):
+        m.buf.version += 1            # an in-place write follows: memoised copies of the old contents are stale
+        shared = node.nhandles > 1 and node in _MEMO_NODES   # NumPy would have made independent copies: copy on write
+        if shared or m.shifts is not None or any(st == 0 and s > 1 for s, st in zip(m.shape, m.strides)):
             c = self._cmat() if m.shifts is not None else None
             if c is None:
                 c = Mat.empty(m.shape, m.dtype)
@@ -973,6 +976,21 @@ def concatenate(arrays, axis=0, out=None, dtype=None, casting="same_kind"):
         if a.ndim != nd or any(a.shape[i] != shape[i] for i in range(nd) if i != axis):
             raise ValueError("all the input array dimensions except for the concatenation axis must match exactly")
     shape[axis] = sum(a.shape[axis] for a in arrays)
+    # The same pieces concatenated again (the four gates of an LSTM cell hstack identical (input, hiddens, ones),
+    # examples/lstm.py:38-49) return the first copy: the result is immutable unless written in place, which bumps the
+    # buffer version and so changes the key.
+    for a in arrays:
+        if a._node.mat is None and a._node.op != "full" and a.size:
+            a._mat()
+    key = _concat_key(arrays, axis, out_dtype)
+    if key is not None:
+        hit = _CONCAT_MEMO.get(key)
+        if hit is not None:
+            node = hit[0]()
+            if node is not None and node.mat is not None and node.mat.buf.version == hit[1] and \
+                    all(r() is a._node for r, a in zip(hit[2], arrays) if r is not None):
+                return DeviceArray(node)
+            del _CONCAT_MEMO[key]
     out_m = Mat.empty(shape, out_dtype)
     be = backend.get()
     pos = 0
@@ -986,7 +1004,32 @@ def concatenate(arrays, axis=0, out=None, dtype=None, casting="same_kind"):
         be.copy_strided(out_m.ptr + dst_off * out_dtype.itemsize, out_dtype, out_m.strides, m.ptr, m.dtype, m.strides,
                         m.shape)
         pos += a.shape[axis]
-    return DeviceArray(lazy.leaf(out_m))
+    out_node = lazy.leaf(out_m)
+    if key is not None:
+        if len(_CONCAT_MEMO) > 64:
+            _CONCAT_MEMO.clear()
+        refs = [None if part[0] == "full" else weakref.ref(a._node) for part, a in zip(key[0], arrays)]
+        _CONCAT_MEMO[key] = (weakref.ref(out_node), out_m.buf.version, refs)
+        _MEMO_NODES.add(out_node)
+    return DeviceArray(out_node)
+
+
+_CONCAT_MEMO = {}
+_MEMO_NODES = weakref.WeakSet()   # nodes that several independent results may share: copied before an in-place write
+
+
+def _concat_key(arrays, axis, out_dtype):
+    """Identity of a concatenation: materialised pieces by (node id, buffer version), symbolic constants by value."""
+    parts = []
+    for a in arrays:
+        node = a._node
+        if node.mat is not None:
+            parts.append((id(node), node.mat.buf.version))
+        elif node.op == "full" and isinstance(node.args[0], lazy.Const):
+            parts.append(("full", repr(node.args[0].value), node.shape, str(node.dtype)))
+        else:
+            return None
+    return (tuple(parts), axis, str(out_dtype))
 
 
 def stack(arrays, axis=0, out=None):

@@ -9,6 +9,8 @@
 // Tiling: CTA tile BM×BN×16, double-buffered in shared memory as [row][k] with a
 // 4-double pad (conflict-free 64-bit fragment loads), register-staged global
 // prefetch of the next k-slab while the current one is multiplied.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b200ag {
@@ -188,11 +190,25 @@ static int launch_gemm(const GemmArgs& g, int64_t batch) {
   return 0;
 }
 
+// development knobs (read once): B200AG_GEMM_TILE = 1 (64x64) / 2 (128x128) / 3 (128x64), B200AG_GEMM_SPLITS = n
+static int tune_tile() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("B200AG_GEMM_TILE"); v = e ? atoi(e) : 0; }
+  return v;
+}
+static int tune_splits() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("B200AG_GEMM_SPLITS"); v = e ? atoi(e) : 0; }
+  return v;
+}
+
 template <typename TA, typename TB, bool AK, bool BKM>
 static int pick_tile(const GemmArgs& g, int64_t batch) {
   // Large tiles only when they still give every SM a CTA; otherwise 64x64 tiles for more parallelism.
   int64_t big = ((g.M + 127) / 128) * ((g.N + 127) / 128) * batch;
-  if (big >= 2 * (int64_t)sm_count()) return launch_gemm<TA, TB, 128, 128, 64, 32, AK, BKM>(g, batch);
+  const int forced = tune_tile();
+  if (forced == 2 || (forced == 0 && big >= 2 * (int64_t)sm_count())) return launch_gemm<TA, TB, 128, 128, 64, 32, AK, BKM>(g, batch);
+  if (forced == 3) return launch_gemm<TA, TB, 128, 64, 32, 32, AK, BKM>(g, batch);
   return launch_gemm<TA, TB, 64, 64, 32, 32, AK, BKM>(g, batch);
 }
 
@@ -235,6 +251,7 @@ extern "C" int b200ag_gemm(void* C, int c_dtype, int64_t c_rs, int64_t c_cs, int
   int64_t max_by_k = (tiles <= (int64_t)sm_count() / 4) ? K / 48 : K / 128;
   int64_t splits = want < max_by_k ? want : max_by_k;
   if (splits > 64) splits = 64;
+  if (tune_splits() > 0) splits = tune_splits() <= K / 16 ? tune_splits() : K / 16;
   void* scratch = nullptr;
   void* real_c = C;
   bool dense_c = (c_cs == 1 && c_rs == N && (batch == 1 || c_bs == M * N));

@@ -56,10 +56,11 @@ MAX_LEAVES = 48
 class Buffer:
     """Owner of one device allocation; freed back to the pool when unreferenced."""
 
-    __slots__ = ("ptr", "nbytes", "__weakref__")
+    __slots__ = ("ptr", "nbytes", "version", "__weakref__")
 
     def __init__(self, nbytes: int, upload: bool = False):
         self.nbytes = int(nbytes)
+        self.version = 0          # bumped before every in-place write (DeviceArray._own_buffer): invalidates memoised copies
         be = backend.get()
         self.ptr = be.malloc_upload(self.nbytes) if upload else be.malloc(self.nbytes)
 

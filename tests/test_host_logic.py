@@ -2,6 +2,7 @@
 protocol dispatch, autograd registration) exercised on tests/fakedev.FakeBackend.  Generated CUDA
 sources are still compiled with NVRTC (offline) so code-generation errors fail here."""
 
+import numpy as onp
 import pytest
 
 import cases
@@ -32,3 +33,25 @@ def test_ops(name, fake_dev):
 @pytest.mark.parametrize("name", sorted(cases.GRAD_CASES))
 def test_grads(name, fake_dev):
     cases.GRAD_CASES[name]()
+
+
+def test_concatenate_memo_is_invisible(fake_dev):
+    """Repeated concatenation of the same pieces (the four gate hstacks of an LSTM cell) reuses the first copy, yet
+    behaves like independent NumPy copies: writes to one result or to an input never leak into another result."""
+    import autograd.numpy as np
+    import autograd_b200 as b200
+
+    x = b200.asarray(onp.arange(6.0).reshape(2, 3))
+    h = b200.asarray(onp.ones((2, 2))) * 3.0
+    a = np.hstack((x, h, np.ones((2, 1))))
+    n0 = fake_dev.launch_count()
+    b = np.hstack((x, h, np.ones((2, 1))))
+    assert fake_dev.launch_count() == n0            # memo hit: nothing launched
+    assert onp.array_equal(a.get(), b.get())
+    b[0, 0] = 99.0                                  # copy-on-write: `a` keeps its value
+    assert a.get()[0, 0] == 0.0 and b.get()[0, 0] == 99.0
+    x[0, 0] = -5.0                                  # input written in place: the memo entry is stale
+    c = np.hstack((x, h, np.ones((2, 1))))
+    assert c.get()[0, 0] == -5.0 and a.get()[0, 0] == 0.0
+    d = np.hstack((x, h, np.ones((2, 1)) * 2.0))    # different constant piece: different result
+    assert d.get()[0, -1] == 2.0 and c.get()[0, -1] == 1.0
