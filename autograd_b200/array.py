@@ -725,8 +725,12 @@ def reshape(a, shape=None, order="C", *, newshape=None, copy=None):
     if shape == a.shape:
         return a
     node = a._node
-    if node.mat is None and _reshape_transparent(node):
-        return DeviceArray(_reshape_lazy(node, shape, node.shape, {}))
+    if node.mat is None:
+        if _reshape_transparent(node):
+            return DeviceArray(_reshape_lazy(node, shape, node.shape, {}))
+        unit = _reshape_unit_axes_lazy(node, shape)
+        if unit is not None:
+            return DeviceArray(unit)
     m = a._mat()
     new_strides = _reshape_strides(m, shape)
     if new_strides is None:
@@ -777,6 +781,171 @@ def _reshape_lazy(node, shape, root_shape, memo):
         res = Node(node.op, args, node.in_dtypes, new_shape, node.dtype)
     memo[node.nid] = res
     return res
+
+
+_SELECTABLE_SPECIAL = ("where", "cast", "full")
+
+
+def _select_lazy(node, ndim, axis, index, memo):
+    """``node[..., index, ...]`` along ``axis`` of the ``ndim``-dimensional root, pushed down to the leaves of a pending
+    elementwise expression (elementwise ops commute with slicing).  The axis disappears from every operand; operands
+    that broadcast along it (missing leading axis or size 1) keep their data.  Returns None when some operand cannot
+    be sliced symbolically (gather tables, rolled views of that axis)."""
+    hit = memo.get(node.nid, memo)
+    if hit is not memo:
+        return hit
+    shape = node.shape
+    ax = axis - (ndim - len(shape))          # right-aligned broadcasting
+    if ax < 0:
+        res = node                            # broadcasts along the missing leading axes: unchanged
+    elif node.mat is not None:
+        m = node.mat
+        if m.shifts is not None and m.shifts[ax] != 0:
+            res = None
+        else:
+            i = 0 if shape[ax] == 1 else index
+            shifts = None if m.shifts is None else m.shifts[:ax] + m.shifts[ax + 1:]
+            if shifts is not None and not any(shifts):
+                shifts = None
+            res = lazy.leaf(Mat(m.buf, shape[:ax] + shape[ax + 1:], m.strides[:ax] + m.strides[ax + 1:],
+                                m.offset + i * m.strides[ax], m.dtype, shifts))
+    elif node.op == "full":
+        res = Node("full", node.args, node.in_dtypes, shape[:ax] + shape[ax + 1:], node.dtype)
+    elif node.op == "scatter":
+        res = None
+    else:
+        args = []
+        for k, a in enumerate(node.args):
+            if type(a) is Node and not (node.op == "gather" and k == 0):   # a gather's table is not indexed by position
+                a = _select_lazy(a, len(shape), ax, index, memo)
+                if a is None:
+                    break
+            args.append(a)
+        res = Node(node.op, tuple(args), node.in_dtypes, shape[:ax] + shape[ax + 1:], node.dtype) \
+            if len(args) == len(node.args) else None
+    memo[node.nid] = res
+    return res
+
+
+def _insert_axis_lazy(node, ndim, pos, memo):
+    """A new size-1 axis at position ``pos`` of the ``ndim``-dimensional root, pushed down to the leaves of a pending
+    elementwise expression (the keepdims / expand_dims reshapes of reduction VJPs).  Returns None when impossible."""
+    hit = memo.get(node.nid, memo)
+    if hit is not memo:
+        return hit
+    shape = node.shape
+    p = pos - (ndim - len(shape))
+    if p <= 0:
+        res = node                            # the new axis lies left of this operand's axes: still broadcasts as is
+    elif node.mat is not None:
+        m = node.mat
+        shifts = None if m.shifts is None else m.shifts[:p] + (0,) + m.shifts[p:]
+        res = lazy.leaf(Mat(m.buf, shape[:p] + (1,) + shape[p:], m.strides[:p] + (0,) + m.strides[p:], m.offset,
+                            m.dtype, shifts))
+    elif node.op == "full":
+        res = Node("full", node.args, node.in_dtypes, shape[:p] + (1,) + shape[p:], node.dtype)
+    elif node.op == "scatter":
+        res = None
+    else:
+        args = []
+        for k, a in enumerate(node.args):
+            if type(a) is Node and not (node.op == "gather" and k == 0):
+                a = _insert_axis_lazy(a, len(shape), p, memo)
+                if a is None:
+                    break
+            args.append(a)
+        res = Node(node.op, tuple(args), node.in_dtypes, shape[:p] + (1,) + shape[p:], node.dtype) \
+            if len(args) == len(node.args) else None
+    memo[node.nid] = res
+    return res
+
+
+def _reshape_unit_axes_lazy(node, new_shape):
+    """Reshape of a pending expression that only removes and/or inserts size-1 axes, done symbolically."""
+    old_shape = node.shape
+    if [d for d in old_shape if d != 1] != [d for d in new_shape if d != 1]:
+        return None
+    if _pending_size(node, 48) > 48:
+        return None
+    cur = node
+    for ax in range(len(old_shape) - 1, -1, -1):          # drop every size-1 axis, last first
+        if old_shape[ax] == 1:
+            cur = _select_lazy(cur, len(cur.shape), ax, 0, {})
+            if cur is None:
+                return None
+    for pos, d in enumerate(new_shape):                    # insert the size-1 axes of the target, first to last
+        if d == 1:
+            if pos == 0 and len(cur.shape) >= 0:
+                # a leading axis: every operand keeps broadcasting, only the root's shape changes
+                nxt = _insert_leading_axis(cur)
+            else:
+                nxt = _insert_axis_lazy(cur, len(cur.shape), pos, {})
+            if nxt is None:
+                return None
+            cur = nxt
+    return cur if cur.shape == tuple(new_shape) else None
+
+
+def _insert_leading_axis(node):
+    if node.mat is not None:
+        m = node.mat
+        shifts = None if m.shifts is None else (0,) + m.shifts
+        return lazy.leaf(Mat(m.buf, (1,) + node.shape, (0,) + m.strides, m.offset, m.dtype, shifts))
+    return Node(node.op, node.args, node.in_dtypes, (1,) + node.shape, node.dtype)
+
+
+def _pending_size(node, limit):
+    """Number of pending (unmaterialised) nodes under ``node``, or ``limit`` + 1 when there are more."""
+    stack, seen = [node], set()
+    while stack:
+        nd_ = stack.pop()
+        if nd_.nid in seen or nd_.mat is not None:
+            continue
+        seen.add(nd_.nid)
+        if len(seen) > limit:
+            return limit + 1
+        stack.extend(a for a in nd_.args if type(a) is Node)
+    return len(seen)
+
+
+_SHORT_REDUCE_ON = __import__("os").environ.get("B200AG_SHORT_REDUCE", "1") != "0"
+_SHORT_REDUCE = {"sum": ("add", np.add), "prod": ("multiply", np.multiply), "max": ("maximum", np.maximum),
+                 "min": ("minimum", np.minimum)}
+
+
+def _reduce_short_axes(a, op, axes, work_dtype):
+    """Reductions over SHORT axes (pooling windows, `sum(x == ans)` over a window: at most 8 slices in total) as a
+    pending elementwise combination of the slices — no reduction kernel, no materialised input; the result fuses into
+    its consumers (the max-pool VJP `g * (x == ans) / sum(x == ans)`, numpy_vjps.py:515-530, becomes one kernel).
+    Returns None when the fast path does not apply."""
+    if op not in _SHORT_REDUCE or not axes or not _SHORT_REDUCE_ON:
+        return None
+    slices = prod(a.shape[ax] for ax in axes)
+    if slices > 8 or slices < 2 or a.size // slices < 4096:
+        return None
+    node = a._node
+    if node.mat is None and _pending_size(node, 24) > 24:
+        node = lazy.leaf(a._cmat())            # deep expressions: compute once, then slice the buffer
+    opname, ufunc = _SHORT_REDUCE[op]
+    cur = [node]
+    ndim = a.ndim
+    for ax in sorted(axes, reverse=True):       # last axis first keeps the earlier axis numbers valid
+        nxt = []
+        for piece in cur:
+            for i in range(a.shape[ax]):
+                sel = _select_lazy(piece, ndim, ax, i, {})
+                if sel is None:
+                    return None
+                nxt.append(sel)
+        cur = nxt
+        ndim -= 1
+    pieces = [DeviceArray(p) for p in cur]
+    if pieces[0].dtype != work_dtype:
+        pieces = [p.astype(work_dtype) for p in pieces]
+    acc = pieces[0]
+    for piece in pieces[1:]:
+        acc = elementwise(opname, ufunc, acc, piece)
+    return acc
 
 
 def _reshape_strides(m: Mat, new_shape):
@@ -1523,6 +1692,8 @@ def reduce_(a, op, axis=None, keepdims=False, dtype=None):
             raise ValueError("zero-size array to reduction operation which has no identity")
         ident = {"sum": 0, "prod": 1, "all": 1, "any": 0}[op]
         res = full(kept_shape, ident, work_dtype)
+    elif op in _SHORT_REDUCE and (fast := _reduce_short_axes(a, op, axes, work_dtype)) is not None:
+        res = fast                              # shape without the reduced axes; reshape below re-inserts them lazily
     else:
         be = backend.get()
         cur = a._cmat()

@@ -44,6 +44,8 @@ _DEFAULT_COST = 12  # transcendental functions
 # out as an extra output of the fused kernel once recomputing it would cost more
 # than this; cheaper ones are simply recomputed by whoever needs them later.
 _HEAVY_VEC = int(__import__("os").environ.get("B200AG_HEAVY_VEC", "1"))
+EXPAND_MIN_COST = 12     # cheaper sub-expressions (a max, a compare) are recomputed in place: reading them back costs as much
+EXPAND_WORK = 3.0e7     # repeated op-units (elements x cost) that justify one extra launch, see materialize()
 KEEP_COST = 96
 # Re-materialising nodes that keep being recomputed was measured on C4 (fluidsim): +1 % speed for +65 % retained
 # memory (the 200-step tape would no longer fit 180 GB), so it is off; the hook stays for experiments.
@@ -299,9 +301,11 @@ def _maybe_flush_growing(node):
 class Program:
     """Structural description of one fused kernel; ``key`` identifies the generated code."""
 
-    __slots__ = ("instrs", "leaves", "consts", "outputs", "ndim", "idx64", "vec", "key", "cost", "tables", "mode", "bx")
+    __slots__ = ("instrs", "leaves", "consts", "outputs", "ndim", "idx64", "vec", "key", "cost", "tables", "mode", "bx",
+                 "bdims")
 
-    def __init__(self, instrs, leaves, consts, outputs, ndim, idx64, vec, cost, tables=(), mode="flat", bx=256):
+    def __init__(self, instrs, leaves, consts, outputs, ndim, idx64, vec, cost, tables=(), mode="flat", bx=256,
+                 bdims=None):
         self.instrs = instrs      # tuple of (op, in_dtype chars, out dtype char, arg refs)
         self.leaves = leaves      # tuple of (dtype char, layout class 'C'|'S'|'G', has_shift)
         self.consts = consts      # tuple of C scalar kinds: 'd' | 'q' | '?'
@@ -313,7 +317,10 @@ class Program:
         self.tables = tables      # gather sources: tuple of (dtype char, number of indexed dims)
         self.mode = mode          # "flat": one flattened index; "row": rows x inner loop (general-layout operands)
         self.bx = bx              # row mode: threads of a CTA along the inner dim (256/bx rows per CTA)
-        self.key = (instrs, leaves, consts, outputs, ndim, idx64, vec, tables, mode, bx)
+        # flat kernels over large general-layout spaces bake the divisor dims (all but the first) as literals, so the
+        # per-element coordinate split compiles to multiply-shift instead of integer division
+        self.bdims = bdims
+        self.key = (instrs, leaves, consts, outputs, ndim, idx64, vec, tables, mode, bx, bdims)
 
     def launch_config(self, sm_count):
         block = 256
@@ -400,6 +407,25 @@ def materialize(root: Node, store_root: bool = True) -> Mat:
     order, leaf_nodes = _collect([root])
     root_shape = root.shape
     n = prod(root_shape)
+
+    # A pending sub-expression that lives on a SMALLER iteration space and is broadcast into a larger one would be
+    # recomputed once per element of the larger space (the tanh VJP at pooled resolution feeding the 4x larger
+    # max-pool VJP of examples/convnet.py).  When the repeated work outweighs a launch, compute it once at its own size.
+    if n >= 65536:
+        small = []
+        for nd_ in order:
+            if nd_.mat is not None:
+                continue
+            pn = prod(nd_.shape)
+            for a in nd_.args:
+                if type(a) is Node and a.mat is None and a.op not in ("full", "scatter"):
+                    an = prod(a.shape)
+                    if an and an * 2 <= pn and a.cost >= EXPAND_MIN_COST and float(pn - an) * a.cost >= EXPAND_WORK:
+                        small.append(a)
+        if small:
+            for a in small:
+                materialize(a)
+            order, leaf_nodes = _collect([root])
 
     # interior nodes that Python still holds and that are costly to recompute become extra outputs
     # (b) or that have already been recomputed REUSE_LIMIT times (a loop keeps coming back to them: the
@@ -543,8 +569,9 @@ def materialize(root: Node, store_root: bool = True) -> Mat:
     # short rows: several rows per CTA (64 threads along the row) instead of one mostly idle 256-thread row slice
     bx = 256 if (mode != "row" or dims[-1] >= 2048 * vec) else 64
 
+    bdims = tuple(int(d) for d in dims[1:]) if (mode == "flat" and g_layouts and n >= (1 << 20)) else None
     program = Program(tuple(instrs), tuple(leaf_descs), tuple(const_kinds), outputs, ndim, idx64, vec, total_cost,
-                      tuple(table_descs), mode, bx)
+                      tuple(table_descs), mode, bx, bdims)
 
     out_mats = [Mat.empty(root_shape, o.dtype) for o in outs]
     backend.get().run_program(program, (leaf_ptrs, dims, table_rt), const_values, [m.ptr for m in out_mats], n)

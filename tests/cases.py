@@ -1015,3 +1015,64 @@ def grad_case_scipy_stats_norm():
 
 
 GRAD_CASES["scipy_stats_norm"] = grad_case_scipy_stats_norm
+
+
+def case_short_axis_reductions():
+    """Reductions over short axes (pooling windows) are recorded as pending elementwise combinations of slices
+    (array._reduce_short_axes / _select_lazy / _insert_axis_lazy): values must match NumPy for every op, for keepdims,
+    for broadcasting operands inside the pending expression, for rolled and strided views, ints and bools."""
+    r = rs(95)
+    x = r.randn(40, 6, 12, 2, 12, 2)
+    b = r.randn(1, 6, 1, 1, 1, 1)
+    for op in (onp.max, onp.min, onp.sum, onp.prod):
+        check(lambda a: op(a, axis=3), x, tol=TOL_REDUCE, what=f"{op.__name__} axis 3")
+        check(lambda a: op(op(a, axis=3), axis=4), x, tol=TOL_REDUCE, what=f"{op.__name__} chained (pooling)")
+        check(lambda a: op(a, axis=(3, 5)), x, tol=TOL_REDUCE, what=f"{op.__name__} two axes at once")
+        check(lambda a: op(a, axis=5, keepdims=True), x, tol=TOL_REDUCE, what=f"{op.__name__} keepdims")
+        check(lambda a, b: op(onp.tanh(a + b) * 2.0, axis=3), x, b, tol=TOL_REDUCE, what=f"{op.__name__} of a pending expression")
+    check(lambda a, b: onp.sum((a + b) == onp.max(a + b, axis=3, keepdims=True), axis=3, keepdims=True), x, b,
+          what="count of argmax locations (int64, bit-exact)")
+    check(lambda a: onp.max(onp.roll(a, 1, axis=2), axis=3), x, tol=TOL_REDUCE, what="max of a rolled view")
+    check(lambda a: onp.sum(onp.roll(a, 1, axis=3), axis=3), x, tol=TOL_REDUCE, what="sum over the rolled axis")
+    check(lambda a: onp.max(a[:, :, ::2, :, 1:, :], axis=5), x, tol=TOL_REDUCE, what="max of a strided view")
+    check(lambda a: onp.sum(a > 0, axis=5), x, what="bool sum -> int64")
+    check(lambda a: onp.max((a * 10).astype(onp.int64), axis=3), x, what="int64 max")
+    check(lambda a, b: onp.expand_dims(onp.exp(a + b), 2), x, b, tol=TOL_ELEMENTWISE, what="expand_dims of pending expression")
+    check(lambda a, b: onp.squeeze((a + b)[:, :, :1] * 3.0, axis=2), x, b, tol=TOL_ELEMENTWISE, what="squeeze of pending expression")
+    big = r.randn(200, 6, 12, 2, 12, 2)          # > 2^20 elements: flat general-layout kernels with baked divisor dims
+    bb = r.randn(1, 6, 1, 1, 1, 1)
+    check(lambda a, b: onp.max(onp.max(a + b, axis=3), axis=4), big, bb, tol=TOL_REDUCE, what="large chained max")
+    check(lambda a, b: (a + b) * ((a + b) == onp.max(a + b, axis=5, keepdims=True)), big, bb, tol=TOL_ELEMENTWISE,
+          what="large broadcast-back of a short-axis max")
+    check(lambda a: onp.transpose(a, (0, 2, 4, 1, 3, 5)) * 2.0 + a.reshape(200, 12, 12, 6, 2, 2), big, tol=TOL_ELEMENTWISE,
+          what="large transposed operand (flat general layout)")
+    nanx = x.copy()
+    nanx[0, 0, 0, 1, 0, 0] = onp.nan
+    check(lambda a: onp.max(a, axis=3), nanx, tol=TOL_REDUCE, what="max propagates NaN like NumPy")
+
+
+OP_CASES["short_axis_reductions"] = case_short_axis_reductions
+
+
+def grad_case_max_pool():
+    """Max-pool block of examples/convnet.py:109-118 with the grad_chooser VJP (numpy_vjps.py:515-530), ties included
+    (equal maxima share the cotangent)."""
+    import autograd.numpy as np
+
+    r = rs(96)
+    X = r.randn(40, 6, 24, 24)
+    X[0, 0, 0, 0] = X[0, 0, 0, 1] = X[0, 0, 1, 0] = 7.0       # a tie inside one pooling window
+    bias = r.randn(1, 6, 1, 1)
+
+    def pooled(x, b):
+        y6 = np.reshape(x + b, (40, 6, 12, 2, 12, 2))
+        p = np.max(np.max(y6, axis=3), axis=4)
+        return np.sum(np.tanh(p) ** 2 * np.arange(1.0, 13.0))
+
+    for argnum in (0, 1):
+        check_grad(pooled, (X, bias), TOL_REDUCE, f"max-pool grad wrt arg {argnum}", argnum=argnum)
+    check_grad(lambda x: np.sum(np.mean(np.reshape(x, (40, 6, 12, 2, 12, 2)), axis=(3, 5)) ** 2), (X,), TOL_REDUCE,
+               "average-pool grad")
+
+
+GRAD_CASES["max_pool"] = grad_case_max_pool

@@ -55,3 +55,29 @@ def test_concatenate_memo_is_invisible(fake_dev):
     assert c.get()[0, 0] == -5.0 and a.get()[0, 0] == 0.0
     d = np.hstack((x, h, np.ones((2, 1)) * 2.0))    # different constant piece: different result
     assert d.get()[0, -1] == 2.0 and c.get()[0, -1] == 1.0
+
+
+def test_costly_small_subexpressions_are_computed_once(fake_dev, monkeypatch):
+    """lazy.materialize computes a costly pending sub-expression of a smaller shape once, at its own size, instead of
+    once per element of the larger space it is broadcast into (same values either way)."""
+    import autograd_b200 as b200
+    from autograd_b200 import lazy
+
+    r = onp.random.RandomState(4)
+    small, big = r.randn(64, 1), r.randn(64, 2048)
+    want = onp.tanh(onp.exp(small) / onp.cosh(small)) * big
+    sizes = []
+    orig = fake_dev.run_program
+
+    def spy(program, leaf_info, const_values, out_ptrs, n):
+        sizes.append(n)
+        return orig(program, leaf_info, const_values, out_ptrs, n)
+
+    monkeypatch.setattr(fake_dev, "run_program", spy)
+    for threshold, expect in ((1.0e18, [64 * 2048]), (1.0e3, [64, 64 * 2048])):
+        monkeypatch.setattr(lazy, "EXPAND_WORK", threshold)
+        del sizes[:]
+        s, b = b200.asarray(small), b200.asarray(big)
+        got = (onp.tanh(onp.exp(s) / onp.cosh(s)) * b).get()
+        assert sizes == expect
+        cases.assert_close(got, want, cases.TOL_ELEMENTWISE, "broadcast sub-expression")
