@@ -58,6 +58,7 @@ PROTOTYPES = {
     "b200ag_kernel_max_active_blocks": [C.c_void_p, C.c_int, C.c_size_t, C.POINTER(C.c_int)],
     "b200ag_copy_strided": [C.c_void_p, C.c_int, c_i64_p, C.c_void_p, C.c_int, c_i64_p, c_i64_p, C.c_int],
     "b200ag_add_strided": [C.c_void_p, C.c_int, c_i64_p, C.c_void_p, c_i64_p, c_i64_p, C.c_int],
+    "b200ag_concat": [C.c_void_p, C.c_int, c_void_pp, c_i64_p, C.c_int, c_i64],
     "b200ag_reduce": [C.c_void_p, C.c_void_p, C.c_int, C.c_int, c_i64, c_i64, c_i64],
     "b200ag_argreduce": [C.c_void_p, C.c_void_p, C.c_int, C.c_int, c_i64, c_i64, c_i64],
     "b200ag_gemm": [C.c_void_p, C.c_int, c_i64, c_i64, c_i64,
@@ -80,6 +81,7 @@ PROTOTYPES = {
     "b200ag_comm_create": [C.c_int, C.c_int, C.c_size_t, C.c_void_p],
     "b200ag_comm_connect": [C.c_void_p],
     "b200ag_comm_allreduce_sum_f64": [C.c_void_p, C.c_void_p, c_i64],
+    "b200ag_comm_mode": [C.c_int, C.POINTER(C.c_int)],
     "b200ag_comm_status": [C.POINTER(C.c_int)],
     "b200ag_comm_destroy": [],
     "b200ag_graph_begin": [],

@@ -1162,8 +1162,16 @@ def concatenate(arrays, axis=0, out=None, dtype=None, casting="same_kind"):
             del _CONCAT_MEMO[key]
     out_m = Mat.empty(shape, out_dtype)
     be = backend.get()
+    live = [a for a in arrays if a.size]
+    if 3 <= len(live) <= 16 and all(a.dtype == out_dtype and a._node.mat is not None and a._node.mat.is_contiguous
+                                    and a._node.mat.shifts is None for a in live):
+        # contiguous pieces of one dtype: a single launch instead of one strided copy per piece
+        outer = prod(shape[:axis])
+        rest = prod(shape[axis + 1:])
+        be.concat(out_m.ptr, out_dtype, [a._node.mat.ptr for a in live], [a.shape[axis] * rest for a in live], outer)
+        live = []
     pos = 0
-    for a in arrays:
+    for a in (arrays if live else ()):
         if a.size == 0:
             continue
         m = a._mat()

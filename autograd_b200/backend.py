@@ -256,6 +256,11 @@ class CudaBackend:
         self._check(self._lib.b200ag_add_strided(
             dst, dtype_code(dt), _i64_array(dst_strides), src, _i64_array(src_strides), _i64_array(shape), nd))
 
+    def concat(self, dst, dt, src_ptrs, inner, outer: int) -> None:
+        """dst[outer, sum(inner)] = hstack of contiguous pieces [outer, inner[k]] of dtype ``dt`` (<= 16 pieces)."""
+        arr = (C.c_void_p * len(src_ptrs))(*src_ptrs)
+        self._check(self._lib.b200ag_concat(dst, dtype_code(dt), arr, _i64_array(inner), len(src_ptrs), outer))
+
     def reduce(self, dst, src, dt, op: str, outer: int, red: int, inner: int) -> None:
         self._check(self._lib.b200ag_reduce(dst, src, dtype_code(dt), REDUCE_CODE[op], outer, red, inner))
 
@@ -304,6 +309,12 @@ class CudaBackend:
 
     def conv2d(self, out, a, b, dt, N, Cc, H, W, F, kh, kw, mode: int, flip: int) -> None:
         self._check(self._lib.b200ag_conv2d(out, a, b, dtype_code(dt), N, Cc, H, W, F, kh, kw, mode, flip))
+
+    def comm_mode(self, mode: int) -> int:
+        """Peer allreduce algorithm: 0 automatic, 1 one-shot, 2 two-shot; returns the previous setting."""
+        prev = C.c_int(0)
+        self._check(self._lib.b200ag_comm_mode(mode, C.byref(prev)))
+        return prev.value
 
     def conv_mode(self, direct: int) -> int:
         """1 = direct CUDA-core kernels for few-channel float64 layers (default), 0 = DMMA implicit GEMM only."""

@@ -14,12 +14,14 @@ namespace b200ag {
 struct PeerComm {
   int rank = 0, world = 1;
   size_t slot_bytes = 0;
-  unsigned char* local = nullptr;      // [2 slots][slot_bytes] data, then flags [2][world] u32, then epoch u32, status u32
+  unsigned char* local = nullptr;      // [2 slots][slot_bytes] data, [slot_bytes] reduced chunks (two-shot), then flags:
+                                       // A [2][world] u32 at +0, B [2][world] u32 at +1024, epoch/status/arrival at +2048
   unsigned char* peers[16] = {nullptr};
   uint32_t* flags_of[16] = {nullptr};  // flags array inside each peer's block
   size_t flags_off = 0;
 };
 static PeerComm g_comm;
+static int g_comm_mode = 0;   // 0 = choose by rank count and size, 1 = one-shot, 2 = two-shot (b200ag_comm_mode)
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -48,6 +50,7 @@ __global__ void __launch_bounds__(256) peer_publish_kernel(double* slots, const 
   double* dst = slots + (int64_t)(*epoch & 1) * slot_elems;
   const int64_t step = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) dst[i] = src[i];
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) dst[n] = 0.0;   // pad to a whole double2 (two-shot path)
 }
 
 __global__ void __launch_bounds__(256) peer_allreduce_kernel(AllreduceArgs a) {
@@ -109,6 +112,103 @@ __global__ void __launch_bounds__(256) peer_allreduce_kernel(AllreduceArgs a) {
   }
 }
 
+
+// Two-shot variant for larger rank counts: rank r first reduces chunk r of every peer's vector (reduce-scatter by
+// pulling over NVLink), publishes the reduced chunk, then gathers the other ranks' reduced chunks.  Per rank this
+// moves 2 x (world-1)/world of the vector instead of (world-1) x the vector, and every rank receives the same bits.
+//   flags A: "my input is published"  flags B: "my reduced chunk is ready"  (both carry the epoch, double-slotted)
+__global__ void __launch_bounds__(256) peer_allreduce2_kernel(AllreduceArgs a, double* my_result) {
+  __shared__ int ok;
+  __shared__ unsigned last;
+  const uint32_t epoch = *a.epoch;
+  const int slot = epoch & 1;
+  uint32_t* flagsB_mine = a.my_flags + 256;          // B flags live 1024 bytes after the A flags
+  if (threadIdx.x == 0) {
+    if (blockIdx.x == 0) {
+      __threadfence_system();
+      for (int p = 0; p < a.world; ++p) st_release_sys(a.peer_flags[p] + slot * a.world + a.rank, epoch);
+    }
+    int good = 1;
+    for (int p = 0; p < a.world && good; ++p) {
+      const uint32_t* f = a.my_flags + slot * a.world + p;
+      long long spins = 0;
+      while (ld_acquire_sys(f) != epoch) {
+        if (++spins > 20000000LL) { good = 0; *a.status = 1; break; }
+        __nanosleep(64);
+      }
+    }
+    ok = good;
+  }
+  __syncthreads();
+  const int64_t off = (int64_t)slot * a.slot_elems;
+  const int64_t npairs = (a.n + 1) >> 1;                         // vectors are padded to an even length in the slots
+  const int64_t chunk = (npairs + a.world - 1) / a.world;        // double2 pairs per rank
+  const int64_t c_lo = (int64_t)a.rank * chunk, c_hi = min(c_lo + chunk, npairs);
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ok) {
+    for (int64_t i = c_lo + tid; i < c_hi; i += step) {
+      double2 v[16];
+#pragma unroll
+      for (int p = 0; p < 16; ++p)
+        if (p < a.world) v[p] = __ldcv(reinterpret_cast<const double2*>(a.peer_data[p] + off) + i);
+      double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+      for (int p = 0; p < 16; ++p)
+        if (p < a.world) { acc.x += v[p].x; acc.y += v[p].y; }
+      reinterpret_cast<double2*>(my_result)[i] = acc;            // result area is indexed like the full vector
+    }
+  }
+  // every CTA of this rank has written its part of the chunk: the last one to arrive announces it
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned done = atomicAdd(a.epoch + 2, 1u);
+    last = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    a.epoch[2] = 0;
+    __threadfence_system();
+    for (int p = 0; p < a.world; ++p) st_release_sys(a.peer_flags[p] + 256 + slot * a.world + a.rank, epoch);
+  }
+  // gather: wait for every rank's reduced chunk, copy it out
+  if (threadIdx.x == 0) {
+    int good = ok;
+    for (int p = 0; p < a.world && good; ++p) {
+      const uint32_t* f = flagsB_mine + slot * a.world + p;
+      long long spins = 0;
+      while (ld_acquire_sys(f) != epoch) {
+        if (++spins > 20000000LL) { good = 0; *a.status = 1; break; }
+        __nanosleep(64);
+      }
+    }
+    ok = good;
+  }
+  __syncthreads();
+  if (ok) {
+    for (int64_t i = tid; i < npairs; i += step) {
+      const int p = (int)(i / chunk);
+      // peer p's result area sits 2 slots after its data base
+      const double2 v = __ldcv(reinterpret_cast<const double2*>(a.peer_data[p] + 2 * a.slot_elems) + i);
+      if (2 * i + 1 < a.n) reinterpret_cast<double2*>(a.out)[i] = v;
+      else a.out[2 * i] = v.x;
+    }
+  }
+  // second arrival round: the last CTA advances the epoch (arrival counter epoch[3])
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned done = atomicAdd(a.epoch + 3, 1u);
+    last = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    a.epoch[3] = 0;
+    a.epoch[0] = epoch + 1;
+  }
+}
+
 }  // namespace b200ag
 
 using namespace b200ag;
@@ -121,7 +221,7 @@ int b200ag_comm_create(int rank, int world, size_t slot_bytes, void* ipc_handle_
   if (world < 1 || world > 16 || rank < 0 || rank >= world) B200AG_FAIL("comm_create: bad rank/world (max 16 ranks)");
   if (g_comm.local) B200AG_FAIL("comm_create: already created");
   slot_bytes = (slot_bytes + 255) & ~size_t(255);
-  size_t flags_off = 2 * slot_bytes;
+  size_t flags_off = 3 * slot_bytes;
   size_t total = flags_off + 4096;
   void* p = nullptr;
   B200AG_CUDA(cudaMalloc(&p, total));
@@ -160,7 +260,7 @@ int b200ag_comm_connect(const void* handles) {
 int b200ag_comm_allreduce_sum_f64(void* out, const void* src, int64_t n) {
   B200AG_CHECK_INIT();
   if (!g_comm.local || !g_comm.peers[g_comm.world - 1]) B200AG_FAIL("comm_allreduce: communicator is not connected");
-  if ((size_t)n * 8 > g_comm.slot_bytes) B200AG_FAIL("comm_allreduce: message larger than the comm slot");
+  if ((size_t)(n + 1) * 8 > g_comm.slot_bytes) B200AG_FAIL("comm_allreduce: message larger than the comm slot");
   if (n == 0) return 0;
   AllreduceArgs a;
   a.out = (double*)out;
@@ -180,6 +280,21 @@ int b200ag_comm_allreduce_sum_f64(void* out, const void* src, int64_t n) {
   peer_publish_kernel<<<pgrid, 256, 0, stream()>>>((double*)g_comm.local, (const double*)src, n, a.slot_elems, a.epoch);
   B200AG_LAUNCH_CHECK();
   if (((uintptr_t)out & 15) != 0) B200AG_FAIL("comm_allreduce: output must be 16-byte aligned");
+  // measured at 1.42 MB: one-shot 21 / 43 us at 2 / 8 ranks, two-shot 31 / 66 us (two flag rounds + a grid-wide arrival):
+  // the two-shot form only pays once the (world-1)x larger one-shot traffic dominates, i.e. for multi-megabyte vectors
+  const bool two_shot = g_comm_mode == 2 || (g_comm_mode == 0 && g_comm.world >= 4 && n >= (1 << 19));
+  if (two_shot) {
+    // every CTA takes part in a grid-wide arrival round, so all of them must be resident at once
+    int64_t pairs_per_rank = ((n + 1) / 2 + g_comm.world - 1) / g_comm.world;
+    unsigned grid = (unsigned)((pairs_per_rank + 255) / 256);
+    unsigned cap = (unsigned)sm_count();
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    double* my_result = (double*)(g_comm.local + 2 * g_comm.slot_bytes);
+    peer_allreduce2_kernel<<<grid, 256, 0, stream()>>>(a, my_result);
+    B200AG_LAUNCH_CHECK();
+    return 0;
+  }
   unsigned grid = (unsigned)((n / 2 + 255) / 256);
   unsigned cap = (unsigned)sm_count() * 4;   // all CTAs are resident: they only wait on remote flags, never on each other
   if (grid > cap) grid = cap;
@@ -206,6 +321,14 @@ int b200ag_comm_destroy(void) {
     if (p != g_comm.rank && g_comm.peers[p]) cudaIpcCloseMemHandle(g_comm.peers[p]);
   cudaFree(g_comm.local);
   g_comm = PeerComm();
+  return 0;
+}
+
+// Algorithm of b200ag_comm_allreduce_sum_f64: 0 = automatic (two-shot from 4 ranks and 4 MB up), 1 = one-shot,
+// 2 = two-shot (reduce-scatter + all-gather over peer memory).
+int b200ag_comm_mode(int mode, int* previous) {
+  if (previous) *previous = g_comm_mode;
+  if (mode >= 0 && mode <= 2) g_comm_mode = mode;
   return 0;
 }
 

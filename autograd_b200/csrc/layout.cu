@@ -206,6 +206,29 @@ __global__ void __launch_bounds__(256) scatter_add_kernel(T* __restrict__ dst, c
   }
 }
 
+// np.concatenate of contiguous pieces of one dtype in ONE launch (flatten of a gradient tree: misc/flatten.py:11-27,
+// the pieces handed to the allreduce).  Piece k is viewed as [outer, inner[k]], the result as [outer, sum inner].
+struct ConcatDesc {
+  const void* src[16];
+  int64_t inner[16];
+  int64_t start[17];
+  int npieces;
+  int64_t outer, total_inner;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) concat_kernel(T* __restrict__ dst, ConcatDesc d) {
+  const int64_t n = d.outer * d.total_inner;
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += step) {
+    const int64_t row = idx / d.total_inner, col = idx - row * d.total_inner;
+    int k = 0;
+#pragma unroll 1
+    while (k + 1 < d.npieces && col >= d.start[k + 1]) ++k;
+    dst[idx] = reinterpret_cast<const T*>(d.src[k])[row * d.inner[k] + (col - d.start[k])];
+  }
+}
+
 // x[idx] = values (integer-array item assignment, e.g. unpermuter in numpy_vjps.py:803-806).  With duplicate indices
 // NumPy keeps the last value; here the winner among duplicates is unspecified.
 template <typename T>
@@ -332,6 +355,34 @@ int b200ag_scatter_assign(void* dst, const void* src, int dtype, const int64_t* 
     case 4: scatter_assign_kernel<int32_t><<<grid, 256, 0, stream()>>>((int32_t*)dst, (const int32_t*)src, d, n_index, inner); break;
     case 1: scatter_assign_kernel<uint8_t><<<grid, 256, 0, stream()>>>((uint8_t*)dst, (const uint8_t*)src, d, n_index, inner); break;
     default: B200AG_FAIL("scatter_assign: unsupported dtype");
+  }
+  B200AG_LAUNCH_CHECK();
+  return 0;
+}
+
+int b200ag_concat(void* dst, int dtype, const void* const* srcs, const int64_t* inner, int npieces, int64_t outer) {
+  B200AG_CHECK_INIT();
+  if (npieces < 1 || npieces > 16) B200AG_FAIL("concat: between 1 and 16 pieces per call");
+  ConcatDesc d;
+  d.npieces = npieces;
+  d.outer = outer;
+  int64_t pos = 0;
+  for (int k = 0; k < npieces; ++k) {
+    d.src[k] = srcs[k];
+    d.inner[k] = inner[k];
+    d.start[k] = pos;
+    pos += inner[k];
+  }
+  d.start[npieces] = pos;
+  d.total_inner = pos;
+  int64_t n = outer * pos;
+  if (n == 0) return 0;
+  unsigned grid = grid_for(n, 256, 8);
+  switch (dtype_size(dtype)) {
+    case 8: concat_kernel<int64_t><<<grid, 256, 0, stream()>>>((int64_t*)dst, d); break;
+    case 4: concat_kernel<int32_t><<<grid, 256, 0, stream()>>>((int32_t*)dst, d); break;
+    case 1: concat_kernel<uint8_t><<<grid, 256, 0, stream()>>>((uint8_t*)dst, d); break;
+    default: B200AG_FAIL("concat: unsupported dtype");
   }
   B200AG_LAUNCH_CHECK();
   return 0;

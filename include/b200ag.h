@@ -113,6 +113,11 @@ int b200ag_copy_strided(void* dst, int dst_dtype, const int64_t* dst_strides,
 int b200ag_add_strided(void* dst, int dtype, const int64_t* dst_strides,
                        const void* src, const int64_t* src_strides,
                        const int64_t* shape, int ndim);
+/* np.concatenate of up to 16 contiguous pieces of one dtype in a single launch: piece k is
+ * [outer, inner[k]], dst is [outer, sum(inner)] (np.concatenate behind concatenate_args and
+ * misc.flatten, numpy_wrapper.py:57-59, misc/flatten.py:11-27). */
+int b200ag_concat(void* dst, int dtype, const void* const* srcs, const int64_t* inner,
+                  int npieces, int64_t outer);
 
 /* ---------------------------------------------------------------- reductions
  * np.sum / np.max / np.min / np.prod over one contiguous group of axes of a
@@ -217,6 +222,9 @@ int b200ag_comm_create(int rank, int world, size_t slot_bytes, void* ipc_handle_
 int b200ag_comm_connect(const void* handles);
 int b200ag_comm_allreduce_sum_f64(void* out, const void* src, int64_t n);
 int b200ag_comm_status(int* timed_out);
+/* 0 = choose automatically (one-shot; two-shot reduce-scatter + all-gather from 4 ranks and
+ * 4 MB up), 1 = one-shot, 2 = two-shot. */
+int b200ag_comm_mode(int mode, int* previous);
 int b200ag_comm_destroy(void);
 
 /* ---------------------------------------------------------------- CUDA graphs

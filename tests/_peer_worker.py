@@ -24,8 +24,20 @@ want = onp.zeros(178110)
 for v in all_vecs:                                            # rank order, like the kernel
     want = want + v
 
-# 1. eager calls, many epochs (exercises both slots and the epoch counter)
+# 1. eager calls, many epochs (exercises both slots and the epoch counter), one-shot and two-shot interleaved,
+#    plus an odd length and a short vector through both algorithms
+for mode in (1, 2):
+    be.comm_mode(mode)
+    for n_el in (178109, 7, 2):
+        xs = b200.asarray(all_vecs[rank][:n_el].copy())
+        dist.allreduce_sum_(xs)
+        exp = onp.zeros(n_el)
+        for v in all_vecs:
+            exp = exp + v[:n_el]
+        assert onp.array_equal(xs.get(), exp), f"rank {rank} mode {mode} n {n_el}"
+be.comm_mode(0)
 for it in range(20):
+    be.comm_mode(1 + (it % 2))
     x = b200.asarray(all_vecs[rank] * (it + 1))
     dist.allreduce_sum_(x)
     got = x.get()
@@ -38,6 +50,7 @@ for it in range(20):
         coef = onp.linalg.lstsq(A[:2000], got[:2000], rcond=None)[0]
         raise AssertionError(f"rank {rank} iter {it}: summed coefficients {coef} (expected {it + 1} each), status {be.comm_status()}")
 assert be.comm_status() == 0
+be.comm_mode(0)
 
 # 2. bit-identical across ranks
 import torch
@@ -78,11 +91,17 @@ def timeit(fn, reps=200):
     return be.event_elapsed_ms(e0, e1) / reps * 1e3
 
 y = b200.asarray(all_vecs[rank]).materialize()
+be.comm_mode(1)
+t_one = timeit(lambda: dist.allreduce_sum_(y))
+be.comm_mode(2)
+t_two = timeit(lambda: dist.allreduce_sum_(y))
+be.comm_mode(0)
 t_peer = timeit(lambda: dist.allreduce_sum_(y))
 dist._peer["ready"] = False
 t_nccl = timeit(lambda: dist.allreduce_sum_(y))
 dist._peer["ready"] = True
 if rank == 0:
-    print(f"peer-memory allreduce 1.42 MB x{world}: {t_peer:.1f} us/call; NCCL via torch: {t_nccl:.1f} us/call", flush=True)
+    print(f"peer-memory allreduce 1.42 MB x{world}: one-shot {t_one:.1f} us, two-shot {t_two:.1f} us, automatic {t_peer:.1f} us/call; "
+          f"NCCL via torch: {t_nccl:.1f} us/call", flush=True)
 print(f"rank {rank}/{world} peer allreduce ok", flush=True)
 dist._pg.barrier()

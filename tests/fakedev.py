@@ -324,6 +324,17 @@ class FakeBackend:
         del_, didx = self._strided(dst, dt, shape, dst_strides)
         np.add.at(del_, didx, sel[sidx])
 
+    def concat(self, dst, dt, src_ptrs, inner, outer):
+        self._launches += 1
+        total = int(sum(inner))
+        del_, d0 = self._elems(dst, dt)
+        d = del_[d0: d0 + outer * total].reshape(outer, total)
+        pos = 0
+        for ptr, k in zip(src_ptrs, inner):
+            sel, s0 = self._elems(ptr, dt)
+            d[:, pos: pos + k] = sel[s0: s0 + outer * k].reshape(outer, k)
+            pos += k
+
     def _view3(self, ptr, dt, outer, red, inner):
         el, e0 = self._elems(ptr, dt)
         return el[e0: e0 + outer * red * inner].reshape(outer, red, inner)
