@@ -223,7 +223,8 @@ int b200ag_comm_connect(const void* handles);
 int b200ag_comm_allreduce_sum_f64(void* out, const void* src, int64_t n);
 int b200ag_comm_status(int* timed_out);
 /* 0 = choose automatically (one-shot; two-shot reduce-scatter + all-gather from 4 ranks and
- * 4 MB up), 1 = one-shot, 2 = two-shot. */
+ * 4 MB up), 1 = one-shot (pull), 2 = two-shot, 3 = one-shot push (every rank writes its vector into
+ * the peers' inboxes, the sum reads local memory only). */
 int b200ag_comm_mode(int mode, int* previous);
 int b200ag_comm_destroy(void);
 

@@ -26,7 +26,7 @@ for v in all_vecs:                                            # rank order, like
 
 # 1. eager calls, many epochs (exercises both slots and the epoch counter), one-shot and two-shot interleaved,
 #    plus an odd length and a short vector through both algorithms
-for mode in (1, 2):
+for mode in (1, 2, 3):
     be.comm_mode(mode)
     for n_el in (178109, 7, 2):
         xs = b200.asarray(all_vecs[rank][:n_el].copy())
@@ -37,7 +37,7 @@ for mode in (1, 2):
         assert onp.array_equal(xs.get(), exp), f"rank {rank} mode {mode} n {n_el}"
 be.comm_mode(0)
 for it in range(20):
-    be.comm_mode(1 + (it % 2))
+    be.comm_mode(1 + (it % 3))
     x = b200.asarray(all_vecs[rank] * (it + 1))
     dist.allreduce_sum_(x)
     got = x.get()
@@ -95,13 +95,15 @@ be.comm_mode(1)
 t_one = timeit(lambda: dist.allreduce_sum_(y))
 be.comm_mode(2)
 t_two = timeit(lambda: dist.allreduce_sum_(y))
+be.comm_mode(3)
+t_push = timeit(lambda: dist.allreduce_sum_(y))
 be.comm_mode(0)
 t_peer = timeit(lambda: dist.allreduce_sum_(y))
 dist._peer["ready"] = False
 t_nccl = timeit(lambda: dist.allreduce_sum_(y))
 dist._peer["ready"] = True
 if rank == 0:
-    print(f"peer-memory allreduce 1.42 MB x{world}: one-shot {t_one:.1f} us, two-shot {t_two:.1f} us, automatic {t_peer:.1f} us/call; "
+    print(f"peer-memory allreduce 1.42 MB x{world}: one-shot pull {t_one:.1f} us, two-shot {t_two:.1f} us, push {t_push:.1f} us, automatic {t_peer:.1f} us/call; "
           f"NCCL via torch: {t_nccl:.1f} us/call", flush=True)
 print(f"rank {rank}/{world} peer allreduce ok", flush=True)
 dist._pg.barrier()
