@@ -15,6 +15,8 @@ part of the key.
 
 from __future__ import annotations
 
+import weakref
+
 import numpy as np
 
 from . import backend, lazy
@@ -60,10 +62,11 @@ def _out_leaves(tree, acc):
 
 
 class _Recording:
-    __slots__ = ("graph", "static_inputs", "outputs", "nodes", "__weakref__")
+    __slots__ = ("graph", "static_inputs", "outputs", "nodes", "seen", "__weakref__")
 
     def __init__(self, graph, static_inputs, outputs, nodes):
         self.graph, self.static_inputs, self.outputs, self.nodes = graph, static_inputs, outputs, nodes
+        self.seen = [None] * len(static_inputs)   # per input: what was copied in last (buffer identity + version)
 
     def __del__(self):
         try:
@@ -91,18 +94,24 @@ class CapturedFunction:
             rec = self._record(be, args, leaves)
             self._recordings[key] = rec
         else:
-            for dst, src in zip(rec.static_inputs, leaves):
-                self._refresh(be, dst, src)
+            for i, (dst, src) in enumerate(zip(rec.static_inputs, leaves)):
+                self._refresh(be, dst, src, rec.seen, i)
         be.graph_launch(rec.graph)
         return rec.outputs
 
     @staticmethod
-    def _refresh(be, dst: DeviceArray, src):
+    def _refresh(be, dst: DeviceArray, src, seen, i):
         dm = dst._node.mat
         if isinstance(src, DeviceArray):
             sm = src._cmat()
             if sm.ptr != dm.ptr:
+                # the same, unmodified source buffer as last time (same Buffer OBJECT, not merely the same address, and
+                # no in-place write since): the static copy is still current
+                tag = seen[i]
+                if tag is not None and tag[0]() is sm.buf and tag[1] == sm.buf.version and tag[2] == sm.offset:
+                    return
                 be.d2d(dm.ptr, sm.ptr, src.nbytes)
+                seen[i] = (weakref.ref(sm.buf), sm.buf.version, sm.offset)
         else:
             be.h2d(dm.ptr, np.asarray(src, dtype=dm.dtype, order="C"))
 

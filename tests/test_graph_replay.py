@@ -116,3 +116,30 @@ def test_replayed_float32_net_uses_tensor_core_gemm(cuda_dev):
             assert a.dtype == onp.float32
             cases.assert_close(a.get(), w_, cases.TOL_F32, "replayed float32 net gradient")
     assert len(fast.num_nodes()) == 1
+
+
+def test_replay_skips_unchanged_inputs_but_sees_every_change(cuda_dev):
+    """Inputs are re-copied into the recording only when they changed: the same unmodified array costs nothing, an
+    in-place write (buffer version) or a new array (even one recycled at the same address) is picked up."""
+    import autograd.numpy as np
+    import autograd_b200 as b200
+    from autograd import grad
+
+    f = b200.capture(grad(lambda x: np.sum(np.sin(x) * x)))
+    ref = lambda v: onp.cos(v) * v + onp.sin(v)
+    h = onp.linspace(0.0, 3.0, 4096)
+    x = b200.asarray(h)
+    cases.assert_close(f(x).get(), ref(h), cases.TOL_REDUCE, "first replay")
+    n0 = cuda_dev.launch_count()
+    f(x)
+    same = cuda_dev.launch_count() - n0
+    x[5] = 7.5                                       # in-place write
+    h2 = h.copy(); h2[5] = 7.5
+    n0 = cuda_dev.launch_count()
+    cases.assert_close(f(x).get(), ref(h2), cases.TOL_REDUCE, "after an in-place write")
+    assert cuda_dev.launch_count() - n0 >= same      # the refresh copy is back
+    for k in range(4):                               # fresh arrays, freed in between: addresses get recycled
+        hk = h + k
+        xk = b200.asarray(hk)
+        cases.assert_close(f(xk).get(), ref(hk), cases.TOL_REDUCE, f"new array {k}")
+        del xk
