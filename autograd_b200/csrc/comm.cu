@@ -160,9 +160,9 @@ __global__ void __launch_bounds__(256) peer_allreduce2_kernel(AllreduceArgs a, d
     }
   }
   // every CTA of this rank has written its part of the chunk: the last one to arrive announces it
-  __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence();
     unsigned done = atomicAdd(a.epoch + 2, 1u);
     last = (done == gridDim.x - 1);
   }
@@ -244,9 +244,11 @@ __global__ void __launch_bounds__(256) peer_push_kernel(PushArgs a) {
     const double v = a.src[a.n - 1];
     for (int p = 0; p < a.world; ++p) reinterpret_cast<double*>(a.peer_base[p] + dst_off)[a.n - 1] = v;
   }
-  __threadfence_system();                       // this CTA's stores are visible system-wide before it reports in
+  // CTA barrier, then ONE thread orders the CTA's stores before its arrival (a system fence by every thread costs tens
+  // of microseconds); the last arriver's system fence + release store publishes everything by cumulativity
   __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence();
     unsigned done = atomicAdd(a.epoch + 4, 1u);
     last = (done == gridDim.x - 1);
   }
