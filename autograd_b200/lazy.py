@@ -44,6 +44,9 @@ _DEFAULT_COST = 12  # transcendental functions
 # out as an extra output of the fused kernel once recomputing it would cost more
 # than this; cheaper ones are simply recomputed by whoever needs them later.
 _HEAVY_VEC = int(__import__("os").environ.get("B200AG_HEAVY_VEC", "1"))
+_ROW_TUNE = tuple(int(v) for v in __import__("os").environ.get("B200AG_ROW_TUNE", "").split(",")) \
+    if __import__("os").environ.get("B200AG_ROW_TUNE") else None
+_GRID_MULT = int(__import__("os").environ.get("B200AG_GRID_MULT", "16"))
 EXPAND_MIN_COST = 12     # cheaper sub-expressions (a max, a compare) are recomputed in place: reading them back costs as much
 EXPAND_WORK = 3.0e7     # repeated op-units (elements x cost) that justify one extra launch, see materialize()
 KEEP_COST = 96
@@ -328,7 +331,7 @@ class Program:
 
     def grid(self, n, dims, sm_count):
         per_block = 256 * self.vec
-        max_grid = sm_count * 16
+        max_grid = sm_count * _GRID_MULT
         if self.mode == "row":
             inner = dims[-1]
             span = self.bx * self.vec
@@ -568,6 +571,12 @@ def materialize(root: Node, store_root: bool = True) -> Mat:
         vec = 1
     # short rows: several rows per CTA (64 threads along the row) instead of one mostly idle 256-thread row slice
     bx = 256 if (mode != "row" or dims[-1] >= 2048 * vec) else 64
+    if mode == "row" and _ROW_TUNE:            # development knobs: "bx,vec" (0 keeps the default)
+        tb, tv = _ROW_TUNE
+        if tb:
+            bx = tb
+        if tv and dims[-1] % tv == 0 and tv <= vec:
+            vec = tv
 
     bdims = tuple(int(d) for d in dims[1:]) if (mode == "flat" and g_layouts and n >= (1 << 20)) else None
     program = Program(tuple(instrs), tuple(leaf_descs), tuple(const_kinds), outputs, ndim, idx64, vec, total_cost,
