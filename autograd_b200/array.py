@@ -1151,6 +1151,7 @@ def concatenate(arrays, axis=0, out=None, dtype=None, casting="same_kind"):
     for a in arrays:
         if a._node.mat is None and a._node.op != "full" and a.size:
             a._mat()
+    # (graph.capture clears the memo when a capture begins and ends, so entries never cross that boundary)
     key = _concat_key(arrays, axis, out_dtype)
     if key is not None:
         hit = _CONCAT_MEMO.get(key)

@@ -53,6 +53,7 @@ class CudaBackend:
         self.device = device
         self._check(self._lib.b200ag_init(device))
         self._kernels = {}  # Program.key -> compiled kernel record
+        self.capturing = False  # True between graph_begin and graph_end (results computed now are baked into a graph)
         self.profile = None  # set to a list to collect (program, n, start_event, stop_event) per fused launch
         sms, major, minor, mem = C.c_int(), C.c_int(), C.c_int(), C.c_size_t()
         self._check(self._lib.b200ag_device_info(C.byref(sms), C.byref(major), C.byref(minor), C.byref(mem)))
@@ -186,9 +187,11 @@ class CudaBackend:
     # ------------------------------------------------------------ CUDA graphs
     def graph_begin(self) -> None:
         self._check(self._lib.b200ag_graph_begin())
+        self.capturing = True
 
     def graph_end(self) -> int:
         p = C.c_void_p()
+        self.capturing = False
         self._check(self._lib.b200ag_graph_end(C.byref(p)))
         return p.value
 

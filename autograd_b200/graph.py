@@ -132,7 +132,11 @@ class CapturedFunction:
             static.append(d.copy() if isinstance(leaf, DeviceArray) and self.copy_inputs else d)
         be.synchronize()
         static_args = _rebuild(args, iter(static))
-        # 3. capture the same call
+        # 3. capture the same call.  Memoised results (array._CONCAT_MEMO) must not cross the capture boundary in either
+        #    direction: a buffer computed outside would be baked in stale, one recorded inside only exists after a replay.
+        from . import array as _array
+
+        _array._CONCAT_MEMO.clear()
         be.graph_begin()
         try:
             out = self.fn(*static_args)
@@ -141,6 +145,7 @@ class CapturedFunction:
             for a in acc:
                 a.materialize()
         except BaseException:
+            _array._CONCAT_MEMO.clear()
             try:
                 g = be.graph_end()
                 be.graph_destroy(g)
@@ -148,6 +153,7 @@ class CapturedFunction:
                 pass
             raise
         graph = be.graph_end()
+        _array._CONCAT_MEMO.clear()
         return _Recording(graph, static, out, be.graph_num_nodes(graph))
 
     def num_nodes(self):
