@@ -1517,6 +1517,38 @@ def gradient(f, *varargs, axis=None, edge_order=1):
     return outs[0] if axis is not None and np.ndim(axis) == 0 or f.ndim == 1 and len(outs) == 1 else tuple(outs)
 
 
+def norm(x, ord=None, axis=None, keepdims=False):
+    """np.linalg.norm for vector norms and the Frobenius matrix norm (VJP: autograd/numpy/linalg.py:91-144), composed
+    from device reductions.  Spectral / nuclear matrix norms need an SVD and are not offered."""
+    x = asarray(x)
+    if x.dtype.kind != "f":
+        x = x.astype(np.float64)
+    matrix = isinstance(axis, tuple) and len(axis) == 2 or (axis is None and x.ndim == 2 and ord is not None)
+    if matrix:
+        if ord not in (None, "fro"):
+            raise NotImplementedError(f"autograd_b200: matrix norm ord={ord!r} is not implemented on the device")
+        return elementwise("sqrt", np.sqrt, reduce_(x * x, "sum", axis, keepdims))
+    if axis is None and ord is not None and x.ndim > 2:
+        raise ValueError("Improper number of dimensions to norm.")
+    if ord is None or ord == 2 or ord == "fro":
+        if ord == "fro" and not (axis is None and x.ndim == 2):
+            raise ValueError("Invalid norm order 'fro' for vectors")
+        return elementwise("sqrt", np.sqrt, reduce_(x * x, "sum", axis, keepdims))
+    ax = None if axis is None else axis
+    mag = elementwise("abs", np.absolute, x)
+    if ord == np.inf:
+        return reduce_(mag, "max", ax, keepdims)
+    if ord == -np.inf:
+        return reduce_(mag, "min", ax, keepdims)
+    if ord == 0:
+        return reduce_((x != 0).astype(x.dtype), "sum", ax, keepdims)
+    if ord == 1:
+        return reduce_(mag, "sum", ax, keepdims)
+    if isinstance(ord, str):
+        raise ValueError(f"Invalid norm order '{ord}' for vectors")
+    return reduce_(mag ** ord, "sum", ax, keepdims) ** (1.0 / ord)
+
+
 def angle(z, deg=False):
     z = asarray(z)
     zero = zeros_like(z, dtype=z.dtype if z.dtype.kind == "f" else np.float64)
@@ -2185,7 +2217,7 @@ FUNCTIONS = {
     np.tril: tril, np.triu: triu, np.diag: diag, np.diagonal: diagonal, np.trace: trace, np.diff: diff,
     np.cumsum: cumsum, np.cumprod: cumprod, np.sort: sort, np.argsort: argsort, np.kron: kron, np.rot90: rot90,
     np.rollaxis: rollaxis, np.average: average, np.select: select, np.sinc: sinc, np.cross: cross,
-    np.gradient: gradient, np.angle: angle, np.real_if_close: real_if_close,
+    np.gradient: gradient, np.angle: angle, np.real_if_close: real_if_close, np.linalg.norm: norm,
 }
 # NumPy's own pure-Python implementations of these only call other dispatched functions.
 DECOMPOSE = {np.hstack, np.vstack, np.dstack, np.column_stack, np.atleast_3d,

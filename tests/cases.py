@@ -1076,3 +1076,24 @@ def grad_case_max_pool():
 
 
 GRAD_CASES["max_pool"] = grad_case_max_pool
+
+
+def grad_case_linalg_norm():
+    """np.linalg.norm (vector norms, Frobenius) and its reference VJP (autograd/numpy/linalg.py:91-144) on the device."""
+    import autograd.numpy as np
+    import autograd.numpy.linalg as la
+
+    r = rs(97)
+    x = r.randn(6, 40)
+    for o in (None, 1, 2, 3, onp.inf, -onp.inf, 0):
+        check(lambda a: onp.linalg.norm(a[0], o), x, tol=TOL_REDUCE, what=f"vector norm ord={o}")
+        check(lambda a: onp.linalg.norm(a, o, axis=1), x, tol=TOL_REDUCE, what=f"norm ord={o} axis=1")
+    check(lambda a: (onp.linalg.norm(a), onp.linalg.norm(a, "fro"), onp.linalg.norm(a, axis=0, keepdims=True)), x,
+          tol=TOL_REDUCE, what="Frobenius / keepdims")
+    check_grad(lambda a: la.norm(a), (x,), TOL_REDUCE, "grad of the 2-norm")
+    check_grad(lambda a: np.sum(la.norm(a, axis=1) ** 2), (x,), TOL_REDUCE, "grad of row norms")
+    check_grad(lambda a: np.sum(la.norm(a, 3, axis=0)), (x,), TOL_REDUCE, "grad of the 3-norm")
+    check_grad(lambda a: la.norm(a, "fro") * np.sum(a), (x,), TOL_REDUCE, "grad of the Frobenius norm")
+
+
+GRAD_CASES["linalg_norm"] = grad_case_linalg_norm
