@@ -305,10 +305,10 @@ class Program:
     """Structural description of one fused kernel; ``key`` identifies the generated code."""
 
     __slots__ = ("instrs", "leaves", "consts", "outputs", "ndim", "idx64", "vec", "key", "cost", "tables", "mode", "bx",
-                 "bdims")
+                 "bdims", "share")
 
     def __init__(self, instrs, leaves, consts, outputs, ndim, idx64, vec, cost, tables=(), mode="flat", bx=256,
-                 bdims=None):
+                 bdims=None, share=None):
         self.instrs = instrs      # tuple of (op, in_dtype chars, out dtype char, arg refs)
         self.leaves = leaves      # tuple of (dtype char, layout class 'C'|'S'|'G', has_shift)
         self.consts = consts      # tuple of C scalar kinds: 'd' | 'q' | '?'
@@ -323,7 +323,10 @@ class Program:
         # flat kernels over large general-layout spaces bake the divisor dims (all but the first) as literals, so the
         # per-element coordinate split compiles to multiply-shift instead of integer division
         self.bdims = bdims
-        self.key = (instrs, leaves, consts, outputs, ndim, idx64, vec, tables, mode, bx, bdims)
+        # flat kernels: general-layout leaves with identical strides (the window slices of a pooled tensor) share one
+        # element-offset computation; share[i] = index of the leaf whose offset leaf i reuses
+        self.share = share
+        self.key = (instrs, leaves, consts, outputs, ndim, idx64, vec, tables, mode, bx, bdims, share)
 
     def launch_config(self, sm_count):
         block = 256
@@ -579,8 +582,18 @@ def materialize(root: Node, store_root: bool = True) -> Mat:
             vec = tv
 
     bdims = tuple(int(d) for d in dims[1:]) if (mode == "flat" and g_layouts and n >= (1 << 20)) else None
+    share = None
+    if mode == "flat" and len(g_slots) > 1:
+        rep, first = list(range(len(leaf_descs))), {}
+        for slot in g_slots:
+            st_, sh_ = leaf_ptrs[slot][1], leaf_ptrs[slot][2]
+            if any(sh_):
+                continue
+            rep[slot] = first.setdefault(tuple(st_), slot)
+        if any(r != i for i, r in enumerate(rep)):
+            share = tuple(rep)
     program = Program(tuple(instrs), tuple(leaf_descs), tuple(const_kinds), outputs, ndim, idx64, vec, total_cost,
-                      tuple(table_descs), mode, bx, bdims)
+                      tuple(table_descs), mode, bx, bdims, share)
 
     out_mats = [Mat.empty(root_shape, o.dtype) for o in outs]
     backend.get().run_program(program, (leaf_ptrs, dims, table_rt), const_values, [m.ptr for m in out_mats], n)
