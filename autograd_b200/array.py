@@ -27,11 +27,16 @@ def _is_box(x) -> bool:
 
 
 class DeviceArray:
-    __slots__ = ("_node", "__weakref__")
+    __slots__ = ("_node", "_weak", "__weakref__")
     __array_priority__ = 1000.0
 
     def __init__(self, node: Node):
         self._node = node
+        # True only for the symbolic result of a REBOUND creation function (``autograd.numpy.zeros/ones/full``,
+        # install.py) that no operation has touched yet: such a value carries no evidence of where the caller
+        # computes, so combined with host-only operands it behaves as the host array NumPy would have made
+        # (``_host_only_operands``) — host-only code keeps host results while the backend is installed.
+        self._weak = False
         node.nhandles += 1
 
     def __del__(self):
@@ -201,8 +206,14 @@ class DeviceArray:
                 res = res.astype(dtype)
             if out is not None:
                 (target,) = out if isinstance(out, tuple) else (out,)
+                if isinstance(target, np.ndarray):
+                    # `x += y` on a host accumulator (core.py:262-264: the cotangent of a HOST argument, created by
+                    # ArrayVSpace.zeros) receiving a device contribution: the value of a host argument's gradient
+                    # lives on the host, so this is an explicit device→host read of the contribution.
+                    target[...] = res.get()
+                    return target
                 if not isinstance(target, DeviceArray):
-                    raise TypeError("autograd_b200: out= must be a DeviceArray")
+                    raise TypeError("autograd_b200: out= must be a DeviceArray or a host ndarray")
                 target._assign(res)
                 return target
             return res
@@ -221,8 +232,15 @@ class DeviceArray:
             if ufunc is not np.add:
                 raise TypeError(f"autograd_b200: numpy.{ufunc.__name__}.at has no device implementation")
             target, idx, values = inputs
+            if isinstance(target, np.ndarray):
+                # untake into the cotangent of a HOST argument (numpy_vjps.py:941-950 with vs = ArrayVSpace): the
+                # device contribution is read back explicitly, like the `out=` host accumulator above
+                idx = tuple(i.get() if isinstance(i, DeviceArray) else i for i in idx) if isinstance(idx, tuple) else \
+                    (idx.get() if isinstance(idx, DeviceArray) else idx)
+                np.add.at(target, idx, values.get() if isinstance(values, DeviceArray) else values)
+                return None
             if not isinstance(target, DeviceArray):
-                raise TypeError("autograd_b200: np.add.at target must be a DeviceArray")
+                raise TypeError("autograd_b200: np.add.at target must be a DeviceArray or a host ndarray")
             target._add_at(idx, values)
             return None
         return NotImplemented
@@ -424,6 +442,23 @@ class DeviceArray:
     def _add_at(self, idx, values):
         """np.add.at(self, idx, values): unbuffered in-place accumulation (numpy_vjps.py:946-948)."""
         self._own_buffer()
+        mixed = _mixed_index(self.shape, idx)
+        if mixed is not None:
+            # scatter into a contiguous stand-in of the (sliced, transposed) view, then one strided in-place add
+            v2, n_other = _mixed_view(self, mixed)
+            arrays = tuple(mixed[2])
+            idx_shape = lazy.broadcast_shapes([tuple(np.shape(i)) for i in arrays])
+            probe_shape = tuple(idx_shape) + tuple(v2.shape[len(arrays):])
+            nidx, pos = len(probe_shape) - n_other, mixed[3]
+            out_shape = probe_shape if not (pos and nidx) else \
+                probe_shape[nidx:nidx + pos] + probe_shape[:nidx] + probe_shape[nidx + pos:]
+            vals = broadcast_to(asarray(values), out_shape)
+            if pos and nidx:
+                vals = moveaxis(vals, tuple(range(pos, pos + nidx)), tuple(range(nidx)))
+            tmp = zeros(v2.shape, self.dtype).copy()
+            tmp._add_at(arrays, vals)
+            v2._add_at(Ellipsis, tmp)
+            return
         m = self._mat()
         kind, info = _parse_index(self.shape, idx)
         be = backend.get()
@@ -565,8 +600,25 @@ def arange(*args, **kwargs):
     return _upload(np.arange(*args, **kwargs))
 
 
-def linspace(*args, **kwargs):
-    return _upload(np.linspace(*args, **kwargs))
+def linspace(start, stop, num=50, endpoint=True, retstep=False, dtype=None, axis=0):
+    if not isinstance(start, DeviceArray) and not isinstance(stop, DeviceArray):
+        return _upload(np.linspace(start, stop, num, endpoint, retstep, dtype, axis))
+    # device end points (the JVP ``linspace(g, 0, num)``, numpy_jvps.py:169-173): NumPy's own formula
+    # ``arange(num) * (delta / div) + start`` with the last sample pinned to ``stop`` (numpy/_core/function_base.py)
+    if retstep or axis != 0 or np.ndim(start) or np.ndim(stop):
+        raise NotImplementedError("autograd_b200: linspace with device end points supports scalar ends on axis 0 only")
+    num = int(num)
+    div = num - 1 if endpoint else num
+    start, stop = asarray(start) * 1.0, asarray(stop) * 1.0
+    y = _upload(np.arange(0, num, dtype=np.float64))
+    if div > 0:
+        y = y * ((stop - start) / div) + start
+    else:
+        y = y * (stop - start) + start
+    if endpoint and num > 1:
+        y = y.copy()
+        y[-1] = stop
+    return y if dtype is None else y.astype(dtype)
 
 
 def eye(*args, **kwargs):
@@ -617,7 +669,37 @@ def _operand(x):
     raise TypeError(f"autograd_b200: cannot use operand of type {type(x).__name__} in a device computation")
 
 
+def _host_only_operands(inputs):
+    """Dispatch on operand type (overrides must keep working for plain ndarray code).  If the only device
+    operands are untouched symbolic constants from the rebound creation functions (``anp.zeros(anp.shape(g))`` inside a
+    reference rule, numpy_vjps.py:228, numpy_jvps.py:150) and the caller's data is host NumPy, return the operands with
+    those constants restated as zero-stride host broadcasts — the computation never concerned the device.  Otherwise
+    None.  Nothing is read back from the device: a weak value is (fill value, shape, dtype), all host metadata."""
+    weak = host = False
+    for x in inputs:
+        if isinstance(x, DeviceArray):
+            if not x._weak:
+                return None
+            weak = True
+        elif isinstance(x, (np.ndarray, np.generic)):
+            host = True
+    if not weak:
+        return None
+    if not host and any(isinstance(x, DeviceArray) and x.ndim for x in inputs):
+        return None   # Python scalars only: `anp.zeros(n) + 1.0` is device work; 0-d constants are plain scalars
+    out = []
+    for x in inputs:
+        if isinstance(x, DeviceArray):
+            nd_ = x._node
+            x = np.broadcast_to(np.asarray(nd_.args[0].value, dtype=nd_.dtype), nd_.shape)
+        out.append(x)
+    return out
+
+
 def elementwise(opname, ufunc, *inputs) -> DeviceArray:
+    host = _host_only_operands(inputs)
+    if host is not None:
+        return ufunc(*host)
     args = [_operand(x) for x in inputs]
     return DeviceArray(lazy.make_op(opname, ufunc, args))
 
@@ -625,6 +707,9 @@ def elementwise(opname, ufunc, *inputs) -> DeviceArray:
 def where(cond, x=None, y=None):
     if x is None and y is None:
         raise NotImplementedError("autograd_b200: np.where(cond) (nonzero) is not implemented on device")
+    host = _host_only_operands((cond, x, y))
+    if host is not None:
+        return np.where(*host)
     c, a, b = _operand(cond), _operand(x), _operand(y)
     if type(c) is Const:
         return asarray(x if c.value else y)
@@ -1068,6 +1153,21 @@ def atleast_2d(*arys):
             a = reshape(a, (1, 1))
         elif a.ndim == 1:
             a = reshape(a, (1, a.shape[0]))
+        res.append(a)
+    return res[0] if len(res) == 1 else tuple(res)
+
+
+def atleast_3d(*arys):
+    """np.atleast_3d: () -> (1,1,1), (N,) -> (1,N,1), (M,N) -> (M,N,1) (numpy/_core/shape_base.py)."""
+    res = []
+    for a in arys:
+        a = asarray(a)
+        if a.ndim == 0:
+            a = reshape(a, (1, 1, 1))
+        elif a.ndim == 1:
+            a = reshape(a, (1, a.shape[0], 1))
+        elif a.ndim == 2:
+            a = reshape(a, a.shape + (1,))
         res.append(a)
     return res[0] if len(res) == 1 else tuple(res)
 
@@ -1630,6 +1730,61 @@ def _parse_index(shape, idx):
     return "adv", (dev, idx_shape, len(dev))
 
 
+def _mixed_index(shape, idx):
+    """Index arrays mixed with slices / newaxis, or not on the leading axes (``x[3, 2:, [1, 3]]``, ``x[:, cols]``).
+    NumPy's rule (advanced indexing, "combining advanced and basic indexing"): the basic part is a view; the
+    broadcast index dimensions replace the indexed axes in place when the advanced entries (arrays AND integers)
+    are adjacent, and come first otherwise.  Returns None for the plain leading form ``_parse_index`` handles, else
+    (basic index making the view, view axes carrying an advanced index, those indices, destination of the index
+    dims or None for "first")."""
+    if not isinstance(idx, tuple):
+        idx = (idx,)
+
+    def is_arr(i):
+        return isinstance(i, (DeviceArray, np.ndarray, list))
+
+    if not any(is_arr(i) for i in idx):
+        return None
+    k = 0
+    while k < len(idx) and (is_arr(idx[k]) or isinstance(idx[k], (numbers.Integral, np.integer))):
+        k += 1
+    if all((isinstance(j, slice) and j == slice(None)) or j is Ellipsis for j in idx[k:]):
+        return None
+    if sum(1 for i in idx if i is Ellipsis) > 1:
+        raise IndexError("an index can only have a single ellipsis ('...')")
+    n_real = sum(1 for i in idx if i is not None and i is not Ellipsis)
+    if n_real > len(shape):
+        raise IndexError(f"too many indices for array: array is {len(shape)}-dimensional, but {n_real} were indexed")
+    entries = []
+    for i in idx:
+        if i is Ellipsis:
+            entries += [slice(None)] * (len(shape) - n_real)
+        else:
+            entries.append(i)
+    entries += [slice(None)] * (len(shape) - sum(1 for e in entries if e is not None))
+    basic, adv_dims, arrays, adv_entries = [], [], [], []
+    for e_i, e in enumerate(entries):
+        if e is None or isinstance(e, slice):
+            basic.append(e)
+        elif is_arr(e) or isinstance(e, (numbers.Integral, np.integer)):
+            adv_dims.append(len(basic))
+            basic.append(slice(None))
+            arrays.append(e if is_arr(e) else int(e))
+            adv_entries.append(e_i)
+        else:
+            raise IndexError(f"unsupported index {e!r}")
+    adjacent = adv_entries[-1] - adv_entries[0] + 1 == len(adv_entries)
+    return tuple(basic), adv_dims, arrays, (adv_dims[0] if adjacent else None)
+
+
+def _mixed_view(a, mixed):
+    """The basic view of ``a`` with the advanced axes moved to the front, ready for the leading-axes gather/scatter."""
+    basic, adv_dims, arrays, pos = mixed
+    v = getitem(a, basic)
+    others = [d for d in range(v.ndim) if d not in adv_dims]
+    return transpose(v, adv_dims + others), len(others)
+
+
 def _basic_view(m: Mat, ops) -> Mat:
     if m.shifts is not None:
         raise AssertionError("rolled views must be made contiguous before slicing")
@@ -1654,6 +1809,14 @@ def _basic_view(m: Mat, ops) -> Mat:
 def getitem(a: DeviceArray, idx):
     if _is_box(idx):
         return NotImplemented
+    mixed = _mixed_index(a.shape, idx)
+    if mixed is not None:
+        v2, n_other = _mixed_view(a, mixed)
+        r = getitem(v2, tuple(mixed[2]))
+        nidx, pos = r.ndim - n_other, mixed[3]
+        if pos and nidx:
+            r = moveaxis(r, tuple(range(nidx)), tuple(range(pos, pos + nidx)))
+        return r
     kind, info = _parse_index(a.shape, idx)
     if kind == "basic":
         m = a._mat()
@@ -2034,6 +2197,26 @@ def _einsum_parse(subscripts, shapes):
     return ex, out
 
 
+def _einsum_diagonal(sub, o):
+    """A repeated index inside one operand ('lli') reads that operand's diagonal over the repeated axes: a strided
+    view (stride = sum of the axes' strides) kept at the first occurrence's position — no copy."""
+    mt = o._mat()
+    if mt.shifts is not None:
+        mt = o._cmat()
+    new_sub, shape, strides = [], [], []
+    for i, ch in enumerate(sub):
+        if ch in new_sub:
+            j = new_sub.index(ch)
+            if mt.shape[i] != shape[j]:
+                raise ValueError(f"einsum: dimensions in operand for collapsing index {ch!r} don't match")
+            strides[j] += mt.strides[i]
+        else:
+            new_sub.append(ch)
+            shape.append(mt.shape[i])
+            strides.append(mt.strides[i])
+    return "".join(new_sub), DeviceArray(lazy.leaf(Mat(mt.buf, tuple(shape), tuple(strides), mt.offset, mt.dtype)))
+
+
 def einsum(*operands, **kwargs):
     """np.einsum for device operands: every pairwise step is transposes + one (batched) DMMA GEMM."""
     if kwargs.get("out") is not None:
@@ -2053,9 +2236,9 @@ def einsum(*operands, **kwargs):
         return einsum(spec, *ops)
     spec, ops = operands[0], [asarray(o) for o in operands[1:]]
     ins, out = _einsum_parse(spec, [o.shape for o in ops])
-    for sub in ins:
+    for k, sub in enumerate(ins):
         if len(set(sub)) != len(sub):
-            raise NotImplementedError("autograd_b200: einsum with a repeated index inside one operand (diagonal) is not implemented")
+            ins[k], ops[k] = _einsum_diagonal(sub, ops[k])
     sizes = {}
     for sub, o in zip(ins, ops):
         for ch, n in zip(sub, o.shape):
@@ -2201,7 +2384,7 @@ FUNCTIONS = {
     np.shape: _np_shape, np.ndim: _np_ndim, np.size: _np_size, np.result_type: _result_type,
     np.iscomplexobj: iscomplexobj, np.isrealobj: isrealobj,
     np.reshape: reshape, np.ravel: ravel, np.transpose: transpose, np.swapaxes: swapaxes, np.moveaxis: moveaxis,
-    np.expand_dims: expand_dims, np.squeeze: squeeze, np.atleast_1d: atleast_1d, np.atleast_2d: atleast_2d,
+    np.expand_dims: expand_dims, np.squeeze: squeeze, np.atleast_1d: atleast_1d, np.atleast_2d: atleast_2d, np.atleast_3d: atleast_3d,
     np.broadcast_to: broadcast_to, np.flip: flip, np.flipud: flipud, np.fliplr: fliplr, np.roll: roll,
     np.concatenate: concatenate, np.stack: stack, np.repeat: repeat, np.tile: tile, np.pad: pad, np.take: take,
     np.sum: sum_, np.prod: prod_, np.max: amax, np.amax: amax, np.min: amin, np.amin: amin, np.mean: mean,

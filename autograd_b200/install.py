@@ -377,21 +377,132 @@ def install(creation: bool = True):
     nw.select = select
     anp.select = select
 
+    # ------------------------------------------------------------ cotangents of HOST arguments stay host values
+    # backward_pass (core.py:24-33) gives a parent whatever type its first cotangent has.  When a host scalar/ndarray
+    # is differentiated through device data (``grad(lambda s: np.sum(np.tanh(s * X_dev)))(0.5)``) the reference
+    # contract is vspace(gradient) == vspace(argument) (test_util.py:38): the contribution is read back when — and only
+    # when — the differentiated argument of that primitive call is a host value.  Calls whose differentiated arguments
+    # are all device values (every node of C1-C5) get the registered rule back unchanged: no cost at backward time.
+    from autograd import core as _core
+    from autograd.tracer import getval as _getval
+
+    land = primitive(lambda x: x.get() if type(x) is DeviceArray else x)   # traced, so it also works under outer traces
+    defvjp(land, lambda ans, x: lambda g: g)
+    defjvp(land, lambda g, ans, x: land(g))
+
+    def _host_landing(vjpmaker):
+        def maker(argnums, ans, args, kwargs):
+            vjp = vjpmaker(argnums, ans, args, kwargs)
+            host = [isinstance(_getval(args[i]), (float, int, onp.ndarray, onp.generic)) for i in argnums]
+            if not any(host):
+                return vjp
+
+            def vjp_host(g):
+                return tuple(land(o) if h and type(_getval(o)) is DeviceArray else o for o, h in zip(vjp(g), host))
+            return vjp_host
+        maker._b200ag_host_landing = True
+        return maker
+
+    for _fun, _maker in list(_core.primitive_vjps.items()):
+        if not getattr(_maker, "_b200ag_host_landing", False):
+            _core.primitive_vjps[_fun] = _host_landing(_maker)
+
+    # ------------------------------------------------------------ ndim/shape of a SEQUENCE of device arrays
+    # grad_gradient (numpy_vjps.py:313) asks ``anp.ndim(g)`` of the tuple np.gradient returned; NumPy answers by
+    # stacking the sequence into an ndarray.  Only metadata is needed: one more axis than the (equal-shaped) members.
+    def _seq_meta(ref, of_seq):
+        def raw(a, *args, **kwargs):
+            if isinstance(a, (list, tuple)) and a and all(isinstance(getval(e), DeviceArray) for e in a) \
+                    and len({getval(e).shape for e in a}) == 1:
+                return of_seq(a)
+            return ref(a, *args, **kwargs)
+        return raw
+
+    for _prim, _of in ((anp.ndim, lambda a: 1 + getval(a[0]).ndim), (anp.shape, lambda a: (len(a),) + getval(a[0]).shape)):
+        _ref = _prim.__closure__[_prim.__code__.co_freevars.index("f_raw")].cell_contents
+        if not getattr(_ref, "_b200ag_seq", False):
+            _new = _seq_meta(_ref, _of)
+            _new._b200ag_seq = True
+            _swap_raw(_prim, _new)
+
     # ------------------------------------------------------------ creation functions
     if creation:
         def switchable(dev_fn, host_fn):
+            symbolic = dev_fn in (A.zeros, A.ones, A.full, A.empty)
+
             def create(*args, **kwargs):
                 if _host_creation_depth or any(isinstance(a, onp.ndarray) for a in args):
                     return host_fn(*args, **kwargs)
-                return dev_fn(*args, **kwargs)
+                res = dev_fn(*args, **kwargs)
+                if symbolic and res._node.op == "full":
+                    res._weak = True   # no evidence yet of where the caller computes (array._host_only_operands)
+                return res
             return create
 
+        # The raw function behind each EXISTING primitive is swapped (not a new primitive): the reference's rules for
+        # them (defvjp/defjvp of linspace and full, numpy_vjps.py:212,240-244, numpy_jvps.py:99,169-173) keep applying
+        # and names imported before install() follow.
         for name, fn in (("zeros", A.zeros), ("ones", A.ones), ("full", A.full), ("empty", A.empty),
                          ("arange", A.arange), ("linspace", A.linspace), ("eye", A.eye), ("meshgrid", A.meshgrid)):
-            wrapped = primitive(switchable(fn, getattr(onp, name)))
-            wrapped.__name__ = name
-            setattr(nw, name, wrapped)
-            setattr(anp, name, wrapped)
+            _swap_raw(getattr(nw, name), switchable(fn, getattr(onp, name)))
+
+    # ------------------------------------------------------------ np.int64(x) & co. on device values
+    # numpy_wrapper.py:18-22: the integer scalar types are subclassed with a notrace __new__; NumPy's constructor
+    # would coerce a device array through __array__.  On device operands it is the cast it stands for.
+    def _int_new(ref_new, np_type):
+        def new(cls, *args, **kwargs):
+            if len(args) == 1 and not kwargs and isinstance(args[0], DeviceArray):
+                return args[0].astype(np_type)
+            return ref_new(cls, *args, **kwargs)
+        return new
+
+    for _tname in ("int8", "int16", "int32", "int64", "integer"):
+        _cls = getattr(anp, _tname, None)
+        _new = getattr(_cls, "__new__", None)
+        if _new is not None and getattr(_new, "__closure__", None) and "f_raw" in _new.__code__.co_freevars:
+            _ref_new = _new.__closure__[_new.__code__.co_freevars.index("f_raw")].cell_contents
+            _np_type = getattr(onp, _tname)
+            if _np_type in (onp.int64, onp.int32):
+                _swap_raw(_new, _int_new(_ref_new, _np_type))
+
+    # ------------------------------------------------------------ make_diagonal (numpy_wrapper.py:171-186), r_/c_ (:150-166)
+    ref_make_diagonal = nw.make_diagonal.fun
+
+    def _make_diagonal_raw(D, offset=0, axis1=0, axis2=1):
+        if not isinstance(D, DeviceArray):
+            return ref_make_diagonal(D, offset=offset, axis1=axis1, axis2=axis2)
+        if not (offset == 0 and axis1 == -1 and axis2 == -2):
+            raise NotImplementedError("Currently make_diagonal only supports offset=0, axis1=-1, axis2=-2")
+        out = A.zeros(D.shape + (D.shape[-1],), D.dtype).copy()
+        A.diagonal(out, 0, -1, -2)[...] = D      # a strided view of `out`: one strided copy
+        return out
+
+    _swap_raw(nw.make_diagonal, _make_diagonal_raw)
+
+    def _axis_concat(ref_obj, column):
+        class _Concat:
+            """np.r_ / np.c_ with device (or boxed device) items: plain concatenation of the items along the first /
+            last axis; string directives are a host-only feature."""
+
+            def __getitem__(self, args):
+                items = args if isinstance(args, tuple) else (args,)
+                if not any(isinstance(getval(i), DeviceArray) for i in items):
+                    return ref_obj[args]
+                if any(isinstance(i, str) for i in items):
+                    raise NotImplementedError("autograd_b200: np.r_/np.c_ string directives are not supported on device items")
+                parts = []
+                for i in items:
+                    i = anp.atleast_1d(onp.r_[i] if isinstance(i, slice) else i)   # a slice item is a host range
+                    if column and anp.ndim(i) == 1:
+                        i = anp.reshape(i, (-1, 1))
+                    parts.append(i)
+                return anp.concatenate(parts, axis=-1 if column else 0)
+        return _Concat()
+
+    if not getattr(nw.r_, "_b200ag", False):
+        nw.r_ = anp.r_ = _axis_concat(nw.r_, False)
+        nw.c_ = anp.c_ = _axis_concat(nw.c_, True)
+        nw.r_._b200ag = nw.c_._b200ag = True
 
     _installed = True
 

@@ -549,7 +549,8 @@ def materialize(root: Node, store_root: bool = True) -> Mat:
     outputs = tuple((instr_index[o.nid], o.dtype.char) for o in outs)
 
     # ---- vector width: 16-byte accesses on every contiguous leaf and output when alignment allows
-    max_item = max([o.dtype.itemsize for o in outs] + [np.dtype(d[0]).itemsize for d in leaf_descs if d[1] == "C" or d[3] == "R"])
+    max_item = max([o.dtype.itemsize for o in outs] + [np.dtype(d[0]).itemsize for d in leaf_descs if d[1] == "C" or d[3] == "R"],
+                   default=16)   # a scatter of broadcast scalars has neither outputs nor contiguous leaves
     if table_descs:
         max_item = 16  # gathers are latency-bound scalar loads: no vector path
     vec = max(1, 16 // max_item)

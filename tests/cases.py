@@ -1097,3 +1097,106 @@ def grad_case_linalg_norm():
 
 
 GRAD_CASES["linalg_norm"] = grad_case_linalg_norm
+
+
+# =============================================================== gaps found by running the reference's own test files
+# (tests/test_systematic.py, test_numpy.py, test_graphs.py, test_wrappers.py ... of the reference) with device inputs
+def case_mixed_indexing():
+    """Index arrays combined with slices / integers / newaxis, and index arrays that are not on the leading axes:
+    NumPy's placement rule for the broadcast index dimensions (test_numpy.py:315-321 test_index_mixed)."""
+    r = rs(41)
+    x = r.randn(5, 6, 4)
+    cols = onp.array([1, 3])
+    rows = onp.array([[0, 2], [4, 4]])
+    check(lambda x: x[3, 2:, [1, 3]], x, tol=0, what="int, slice, list (separated: index dims first)")
+    check(lambda x, c: x[:, c], x, cols, tol=0, what="columns")
+    check(lambda x, c: x[:, :, c], x, cols, tol=0, what="last axis")
+    check(lambda x, c: x[1:4, c, ::2], x, cols, tol=0, what="slice, array, strided slice")
+    check(lambda x, r_, c: x[r_, :, c], x, rows, cols, tol=0, what="separated arrays broadcast")
+    check(lambda x, r_, c: x[:, r_, c], x, rows, cols, tol=0, what="adjacent arrays stay in place")
+    check(lambda x, c: x[..., c], x, cols, tol=0, what="ellipsis then array")
+    check(lambda x, c: x[None, :, c], x, cols, tol=0, what="newaxis")
+    check(lambda x, c: x[c, 1:3], x, cols, tol=0, what="leading array then partial slice")
+
+    def scatter(x, r_, c):
+        out = onp.zeros(x.shape) if isinstance(x, onp.ndarray) else b200.array.zeros(x.shape).copy()
+        onp.add.at(out, (slice(None), r_, c), x[:, r_, c] * 0.5)
+        onp.add.at(out, (3, slice(2, None), [1, 3]), x[3, 2:, [1, 3]])
+        onp.add.at(out, (slice(None), slice(None), c), 1.5)
+        return out
+
+    check(scatter, x, rows, cols, tol=TOL_REDUCE, what="add.at with mixed indices (duplicates)")
+
+
+OP_CASES["mixed_indexing"] = case_mixed_indexing
+
+
+def case_reference_suite_surface():
+    r = rs(42)
+    a3, a2, v = r.randn(3, 4, 4), r.randn(4, 4, 3), r.randn(7)
+    check(lambda a, b, c: onp.einsum("ijk,lji,lli->lki", a, b, c), a3, a2, a2, tol=TOL_REDUCE, what="einsum three operands, diagonal")
+    check(lambda a: onp.einsum("ii->i", a[0]), a3, tol=0, what="einsum diagonal view")
+    check(lambda a: onp.einsum("ii", a[0]), a3, tol=TOL_REDUCE, what="einsum trace")
+    check(lambda v: onp.atleast_3d(v), v, tol=0, what="atleast_3d 1-D")
+    check(lambda a: onp.atleast_3d(a[0]), a3, tol=0, what="atleast_3d 2-D")
+    check(lambda v: onp.sort(v[:1]), v, tol=0, what="sort of one element")
+
+
+OP_CASES["reference_suite_surface"] = case_reference_suite_surface
+
+
+def grad_case_reference_suite_gaps():
+    import autograd.numpy as np
+    from autograd import grad
+    from autograd.core import make_jvp
+    from autograd.test_util import check_grads
+
+    r = rs(43)
+    x3, x2, v = r.randn(5, 6, 4), r.randn(5, 5), r.randn(7)
+    cols = onp.array([1, 3, 3])
+    fns = {
+        "mixed index": (lambda x: np.sum(x[3, 2:, [1, 3]] ** 2) + np.sum(x[:, cols] ** 3) + np.sum(x[1:4, cols, ::2]), (x3,)),
+        "gradient all axes": (lambda x: np.sum(np.gradient(x)[0] ** 2) + np.sum(np.gradient(x)[1] ** 3), (x2,)),
+        "gradient one axis": (lambda x: np.sum(np.gradient(x, axis=1) ** 2), (x2,)),
+        "einsum repeated operand index": (lambda x: np.sum(np.einsum("ijk,lji,lli->lki", x[:3, :4, :4], x3[:4, :4, :3], x3[1:5, :4, :3]) ** 2), (x3,)),
+        "atleast_3d": (lambda v: np.sum(np.atleast_3d(v) ** 2), (v,)),
+        "sort": (lambda v: np.sum(np.sort(v) * np.arange(7.0)) + np.sum(np.sort(v[:1])), (v,)),
+        "r_/c_": (lambda v: np.sum(np.r_[v, v * 2.0, 1:4] ** 2) + np.sum(np.c_[v, v * v] ** 3), (v,)),
+        "make_diagonal": (lambda v: np.sum(np.make_diagonal(v, axis1=-1, axis2=-2) ** 2 * np.arange(7.0)), (v,)),
+        "int cast index": (lambda x: np.sum(x[np.int64(np.abs(x[:, 0]) * 2.0)] ** 2), (x2,)),
+    }
+    for name, (fn, args) in fns.items():
+        check_grad(fn, args, TOL_REDUCE, f"gap {name}")
+
+    # --- the cotangent of a HOST argument differentiated through device data is a host value (test_util.py:38)
+    xd = b200.asarray(x2)
+    g = grad(lambda s: np.sum(np.tanh(s * xd)))(0.5)
+    want = _ref(grad(lambda s: np.sum(np.tanh(s * x2))), 0.5)
+    assert isinstance(g, (float, onp.floating, onp.ndarray)), type(g)
+    assert_close(onp.float64(g), onp.float64(want), TOL_REDUCE, "host scalar argument")
+    gw = grad(lambda w: np.sum(np.dot(xd, w) ** 2))(x2[0])
+    assert isinstance(gw, onp.ndarray), type(gw)
+    assert_close(gw, _ref(grad(lambda w: np.sum(np.dot(x2, w) ** 2)), x2[0]), TOL_REDUCE, "host vector argument")
+    gi = grad(lambda w: np.sum(w[cols] * xd[0, :3]))(x2[1])            # sparse untake into a host accumulator
+    assert isinstance(gi, onp.ndarray), type(gi)
+    assert_close(gi, _ref(grad(lambda w: np.sum(w[cols] * x2[0, :3])), x2[1]), TOL_REDUCE, "host argument, untake")
+    check_grads(lambda s: np.sum(np.exp(s) * xd), modes=["rev", "fwd"], order=2)(0.7)
+    check_grads(lambda a, b: np.dot(a, b), modes=["rev", "fwd"], order=2)(0.3, xd)
+
+    # --- host-only code keeps host results while the backend is installed (where/abs rules call anp.zeros)
+    j = make_jvp(lambda x: make_jvp(np.abs, x)(1.3)[1], 0.4)(0.7)[1]
+    assert not isinstance(j, b200.DeviceArray), type(j)
+    gh = grad(lambda x: np.sum(np.where(x > 0, x * x, -x)))(x2)
+    assert isinstance(gh, onp.ndarray), type(gh)
+    assert isinstance(np.zeros(3) + onp.ones(3), onp.ndarray)
+    assert isinstance(np.zeros(3) + 1.0, b200.DeviceArray)
+    assert isinstance(np.zeros(3) + xd[0, :3], b200.DeviceArray)
+
+    # --- linspace with traced end points (numpy_vjps.py:240-244, numpy_jvps.py:169-173) on device scalars
+    s0 = b200.asarray(onp.array(1.2))
+    gl = grad(lambda a: np.sum(np.linspace(a, 3.4, 5) ** 2))(s0)
+    assert_close(to_host(gl), _ref(grad(lambda a: np.sum(np.linspace(a, 3.4, 5) ** 2)), onp.array(1.2)), TOL_REDUCE, "linspace start")
+    assert_close(to_host(np.linspace(s0, s0 * 3.0, 7)), onp.linspace(1.2, 1.2 * 3.0, 7), TOL_ELEMENTWISE, "device linspace")
+
+
+GRAD_CASES["reference_suite_gaps"] = grad_case_reference_suite_gaps
