@@ -1200,3 +1200,47 @@ def grad_case_reference_suite_gaps():
 
 
 GRAD_CASES["reference_suite_gaps"] = grad_case_reference_suite_gaps
+
+
+def case_shared_denominator_division_bit_exact():
+    """Quotients over one denominator share the reciprocal refinement (codegen PRELUDE b200_rcp/b200_div); the
+    result must be the SAME bits as NumPy's IEEE division for every class of operand: normal, subnormal, zero of
+    either sign, huge, infinite, NaN, quotients that underflow/overflow, negated denominators, constant denominators."""
+    r = rs(7)
+    n = 1 << 16
+    specials = onp.array([0.0, -0.0, 1.0, -1.0, onp.inf, -onp.inf, onp.nan, 5e-324, -5e-324, 2.2250738585072014e-308,
+                          1.7976931348623157e308, -1.7976931348623157e308, 1e-310, 3.0, 1.0 / 3.0, 1e300, 1e-300,
+                          6.5827683646048100446e-37, 2.0 ** -1022, 2.0 ** 1023, 2.0 ** -537, 2.0 ** 512])
+
+    def draw():
+        x = r.randn(n) * onp.exp(r.uniform(-40, 40, n))
+        wide = r.randn(n) * 2.0 ** r.randint(-1074, 1023, n).astype(onp.float64)
+        x[n // 2:] = wide[n // 2:]
+        x[: specials.size * specials.size] = 0  # overwritten below by the cross product of specials
+        return x
+
+    a, b, c, d = draw(), draw(), draw(), draw()
+    k = specials.size
+    blk = k * k + 7                      # 491: coprime with 10, so block p sees selector (p + idx) % 10
+    assert blk % 10 == 1
+    for p in range(10):
+        sl = slice(p * blk, p * blk + k * k)
+        a[sl] = onp.repeat(specials, k)
+        d[sl] = onp.tile(specials, k)
+        b[sl] = onp.tile(specials[::-1], k)
+        c[sl] = 1.5
+    sel = onp.arange(n) % 10
+
+    def f(a, b, c, d, sel):
+        # every quotient lives in ONE fused kernel (so the reciprocal really is shared); element i keeps quotient sel[i]
+        e = d * d
+        qs = [a / d, b / d, c / (-d), (-a) / d, 1.0 / d, a / e, b / e, a / 3.0, b / 3.0, c / -3.0]
+        out = qs[0]
+        for i in range(1, 10):
+            out = onp.where(sel == i, qs[i], out)
+        return out, qs[0] + qs[1] * qs[2] - qs[5] / qs[6]
+
+    check(f, a, b, c, d, sel, tol=0, what="shared-denominator division")
+
+
+OP_CASES["shared_denominator_division_bit_exact"] = case_shared_denominator_division_bit_exact
