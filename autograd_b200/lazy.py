@@ -43,7 +43,7 @@ _DEFAULT_COST = 12  # transcendental functions
 # An interior node that Python can still see (a VJP closure holds it) is written
 # out as an extra output of the fused kernel once recomputing it would cost more
 # than this; cheaper ones are simply recomputed by whoever needs them later.
-_HEAVY_VEC = int(__import__("os").environ.get("B200AG_HEAVY_VEC", "1"))
+_HEAVY_VEC = int(__import__("os").environ.get("B200AG_HEAVY_VEC", "2"))
 _ROW_TUNE = tuple(int(v) for v in __import__("os").environ.get("B200AG_ROW_TUNE", "").split(",")) \
     if __import__("os").environ.get("B200AG_ROW_TUNE") else None
 _GRID_MULT = int(__import__("os").environ.get("B200AG_GRID_MULT", "16"))

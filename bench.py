@@ -220,6 +220,28 @@ def run_b200(args):
         be.synchronize()
         _barrier(dist)
         launches = be.launch_count() - l0
+        eager_ms_local = be.event_elapsed_ms(ev0, ev1) / args.steps
+        # ---- the same evaluation replayed as a CUDA graph (autograd_b200.capture): the eager call re-traces the four
+        # nested backward passes through autograd's Python tracer on every step (~5 ms of host work, now longer than the
+        # kernel), the replay launches the recorded tape — here ONE fused kernel — without it
+        replay_ms, replay_nodes = None, None
+        try:
+            fast = b200.capture(f)
+            for _ in range(max(args.warmup, 3)):
+                fast(x)
+            be.synchronize()         # ranks left the barrier above together; no collective inside this try block
+            be.event_record(ev0)
+            for _ in range(args.steps):
+                fast(x)
+            be.event_record(ev1)
+            be.synchronize()
+            replay_ms = be.event_elapsed_ms(ev0, ev1) / args.steps
+            replay_nodes = int(list(fast.num_nodes().values())[0])
+            del fast
+            be.empty_cache()
+        except Exception as exc:   # keep the eager figure, say why
+            replay_err = f"{type(exc).__name__}: {exc}"
+            print("bench: graph replay of C2 failed:", replay_err, file=sys.stderr)
         if clocks.samples is not None and len(clocks.samples) < 3:
             # a short timed region can fall between two nvidia-smi polls: keep the same kernel running (untimed)
             # until a few samples under load exist
@@ -227,8 +249,15 @@ def run_b200(args):
             while len(clocks.samples) < 3 and time.perf_counter() < t_end:
                 f(x).materialize()
                 be.synchronize()
-    ms = be.event_elapsed_ms(ev0, ev1)
-    ms_per_step = _max_over_ranks(ms / args.steps, dist)
+    eager_ms = _max_over_ranks(eager_ms_local, dist)
+    # every rank takes part in both reductions; one failed capture anywhere disables the replay figure everywhere
+    failed = _max_over_ranks(1.0 if replay_ms is None else 0.0, dist)
+    replay_ms = _max_over_ranks(replay_ms or 0.0, dist) if not failed else None
+
+    use_replay = replay_ms is not None and replay_ms < eager_ms
+    ms_per_step = replay_ms if use_replay else eager_ms
+    if use_replay:
+        launches = replay_nodes * args.steps
     value = world / (ms_per_step * 1e-3)
 
     # ---- dominant kernel: per-launch duration on the launching stream (CUDA events around each launch)
@@ -333,6 +362,8 @@ def run_b200(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": _config(n, world), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": launches, "clocks": clocks.summary(),
+        "execution": {"timed": "CUDA-graph replay (autograd_b200.capture)" if use_replay else "eager (autograd re-traces every step)",
+                      "eager_ms_per_step": eager_ms, "replay_ms_per_step": replay_ms, "replay_graph_nodes": replay_nodes},
         "parity_max_rel_err_vs_reference": err, "mem": mem,
     }
     if dp_results is not None:
