@@ -2007,10 +2007,39 @@ def argmax(a, axis=None, out=None, keepdims=False): return argreduce(a, "max", a
 def argmin(a, axis=None, out=None, keepdims=False): return argreduce(a, "min", axis, keepdims)
 
 
+def _logsumexp_weighted(a, axis, b, keepdims, return_sign):
+    """``logsumexp(a, b=weights)`` / ``return_sign=True``: log|sum(b * exp(a))| with the usual max shift, composed
+    from device reductions and fused elementwise kernels.  SciPy's conventions (scipy/special/_logsumexp.py): the
+    shift is the max over the entries whose weight is non-zero, a non-finite shift is replaced by 0, the sign of
+    the sum is returned separately (and the log of a negative sum is NaN when it is not asked for)."""
+    a = asarray(a)
+    if a.dtype.kind != "f":
+        a = a.astype(np.float64)
+    if b is not None:
+        b = asarray(b)
+        shape = np.broadcast_shapes(a.shape, b.shape)
+        a, b = broadcast_to(a, shape), broadcast_to(b, shape)
+        shift_src = where(b != 0, a, -np.inf)
+    else:
+        shift_src = a
+    m = reduce_(shift_src, "max", axis, True)
+    m = where(elementwise("isfinite", np.isfinite, m), m, 0.0)
+    terms = elementwise("exp", np.exp, a - m)
+    if b is not None:
+        terms = b * terms
+    s = reduce_(terms, "sum", axis, keepdims)
+    if not keepdims:
+        m = reshape(m, s.shape)
+    if return_sign:
+        sgn = elementwise("sign", np.sign, s)
+        return elementwise("log", np.log, abs(s)) + m, sgn
+    return elementwise("log", np.log, s) + m
+
+
 def logsumexp(a, axis=None, b=None, keepdims=False, return_sign=False):
     """scipy.special.logsumexp on device (fused max / exp / sum / log kernel; special.py:120)."""
     if b is not None or return_sign:
-        raise NotImplementedError("autograd_b200: logsumexp supports b=None, return_sign=False only")
+        return _logsumexp_weighted(a, axis, b, keepdims, return_sign)
     a = asarray(a)
     if a.dtype.kind != "f":
         a = a.astype(np.float64)
@@ -2331,6 +2360,73 @@ def conv2d_filter_grad(g, x, w_shape, mode="valid"):
     xm, gm = x._cmat(), g._cmat()
     backend.get().conv2d_wgrad(out.ptr, xm.ptr, gm.ptr, dt, N, C, H, W, F, kh, kw)
     return DeviceArray(lazy.leaf(out))
+
+
+def convolve_nd(a, b, axes=None, dot_axes=None, mode="full"):
+    """General N-d ``autograd.scipy.signal.convolve`` on device operands (scipy/signal.py:10-76): any set of
+    convolved axes, contracted ("dot") axes and untouched axes, modes 'valid' / 'full' / 'same'.
+
+    Same formulation as the reference, so the output axis order (untouched axes of ``a``, untouched axes of ``b``,
+    convolved axes) and the 'same'-mode alignment agree: the larger operand is zero-padded, read through a
+    sliding-window view (one extra trailing axis per convolved axis; a pure stride edit — the windows are never
+    copied as such), the smaller one is reversed along the convolved axes (a negative-stride view), and the two are
+    contracted over window + dot axes by the device einsum (transposes + DMMA GEMM).  The NCHW pattern of
+    examples/convnet.py does not come here: it has dedicated kernels (conv2d / conv2d_wgrad)."""
+    if mode not in ("valid", "full", "same"):
+        raise ValueError(f"Mode {mode} undefined, it can be one of 'valid', 'full', and 'same'")
+    a, b = asarray(a), asarray(b)
+    dt = _float_result(a, b) if (a.dtype.kind == "f" or b.dtype.kind == "f") else np.result_type(a.dtype, b.dtype)
+    a = a if a.dtype == dt else a.astype(dt)
+    b = b if b.dtype == dt else b.astype(dt)
+    ca, cb = ([int(i) for i in ax] for ax in (axes if axes is not None else (range(a.ndim), range(a.ndim))))
+    da, db = ([int(i) for i in ax] for ax in (dot_axes if dot_axes is not None else ((), ())))
+    n_free_b = b.ndim - len(db) - len(cb)
+    n_free_a = a.ndim - len(da) - len(ca)
+
+    if any(b.shape[j] < a.shape[i] for i, j in zip(ca, cb)):
+        # the filter role goes to the operand that is smaller along the convolved axes: compute with swapped roles
+        # and move the untouched axes back to (a's, b's, convolved) order
+        if mode == "valid" and not all(b.shape[j] <= a.shape[i] for i, j in zip(ca, cb)):
+            raise ValueError("One array must be larger than the other along all convolved dimensions")
+        if mode == "valid" or (mode == "full" and b.size <= a.size):
+            swapped = convolve_nd(b, a, axes=(cb, ca), dot_axes=(db, da), mode=mode)
+            order = (list(range(n_free_b, n_free_b + n_free_a)) + list(range(n_free_b))
+                     + list(range(n_free_b + n_free_a, swapped.ndim)))
+            return transpose(swapped, order)
+
+    # roles: ``filt`` is reversed, ``slid`` is padded and windowed ('same' keeps a's extent, so a is the one slid over)
+    filt, slid, cf, cs, df, ds = (b, a, cb, ca, db, da) if mode == "same" else (a, b, ca, cb, da, db)
+    if mode != "valid":
+        widths = [(0, 0)] * slid.ndim
+        for i_f, i_s in zip(cf, cs):
+            k = filt.shape[i_f] - 1
+            widths[i_s] = (k, k) if mode == "full" else (k - k // 2, k // 2)
+        slid = pad(slid, widths)
+    sm = slid._cmat()
+    win_shape, win_strides = list(sm.shape), list(sm.strides)
+    for i_f, i_s in zip(cf, cs):
+        win_shape.append(abs(sm.shape[i_s] - filt.shape[i_f]) + 1)     # output positions along this axis
+        win_strides.append(sm.strides[i_s])
+        win_shape[i_s] = filt.shape[i_f]                                # extent of one window
+    windows = DeviceArray(lazy.leaf(Mat(sm.buf, tuple(win_shape), tuple(win_strides), sm.offset, sm.dtype)))
+    rev = [slice(None)] * filt.ndim
+    for i_f in cf:
+        rev[i_f] = slice(None, None, -1)
+    filt = filt[tuple(rev)]
+
+    def contract(x, y, x_axes, y_axes):
+        # einsum in sublist form: contracted pairs share a label, every other axis keeps its own (x's first)
+        lx, ly = list(range(x.ndim)), list(range(x.ndim, x.ndim + y.ndim))
+        for k, (i, j) in enumerate(zip(x_axes, y_axes)):
+            lx[i] = ly[j] = x.ndim + y.ndim + k
+        return einsum(x, lx, y, ly)
+
+    if mode == "same":
+        out = contract(windows, filt, list(cs) + list(ds), list(cf) + list(df))
+        # einsum order: a's untouched axes, output positions, b's untouched axes -> (a's, b's, positions)
+        na, nc = a.ndim - len(da) - len(ca), len(ca)
+        return transpose(out, list(range(na)) + list(range(na + nc, out.ndim)) + list(range(na, na + nc)))
+    return contract(filt, windows, list(cf) + list(df), list(cs) + list(ds))
 
 
 # =================================================================== dispatch tables

@@ -213,10 +213,10 @@ def install(creation: bool = True):
     scipy_logsumexp = aspecial.logsumexp.fun
 
     def _logsumexp_raw(x, axis=None, b=None, keepdims=False, return_sign=False):
-        if isinstance(x, DeviceArray):
-            if b is not None and not (isinstance(b, float) and b == 1.0):
-                raise NotImplementedError("autograd_b200: logsumexp with weights b is not implemented on device")
-            return A.logsumexp(x, axis=axis, keepdims=keepdims, return_sign=return_sign)
+        if isinstance(x, DeviceArray) or isinstance(b, DeviceArray):
+            if b is not None and isinstance(b, (int, float)) and b == 1.0:
+                b = None                                  # the VJP's default (special.py:123): the fused kernel applies
+            return A.logsumexp(x, axis=axis, b=b, keepdims=keepdims, return_sign=return_sign)
         return scipy_logsumexp(x, axis=axis, b=b, keepdims=keepdims, return_sign=return_sign)
 
     # same primitive object, new raw function: the reference's own VJP/JVP (special.py:123-147) keep applying
@@ -234,13 +234,18 @@ def install(creation: bool = True):
             return False
         return ok and onp.ndim(A_) == 4 and onp.ndim(B) == 4
 
+    def _fast_conv(A_, B, axes, dot_axes, mode):
+        if not _is_nchw(A_, B, axes, dot_axes) or mode not in ("valid", "full"):
+            return False
+        a_shape, b_shape = anp.shape(A_), anp.shape(B)
+        # conv2d slides B over A: A must be the larger one along both convolved axes (else the reference swaps roles)
+        return all(b_shape[i] <= a_shape[i] for i in (2, 3)) if mode == "valid" else True
+
     def _convolve_raw(A_, B, axes=None, dot_axes=None, mode="full"):
         if isinstance(A_, DeviceArray) or isinstance(B, DeviceArray):
-            if not _is_nchw(A_, B, axes, dot_axes) or mode not in ("valid", "full"):
-                raise NotImplementedError(
-                    "autograd_b200: device convolve supports A[N,C,H,W] * B[C,F,kh,kw] with "
-                    "axes=([2,3],[2,3]), dot_axes=([1],[0]), mode 'valid' or 'full'")
-            return A.conv2d(A.asarray(A_), A.asarray(B), mode=mode, flip=True)
+            if _fast_conv(A_, B, axes, dot_axes, mode):
+                return A.conv2d(A.asarray(A_), A.asarray(B), mode=mode, flip=True)
+            return A.convolve_nd(A_, B, axes=axes, dot_axes=dot_axes, mode=mode)   # any axes / mode: windows + einsum
         return ref_convolve_raw(A_, B, axes=axes, dot_axes=dot_axes, mode=mode)
 
     convolve = asignal.convolve
@@ -249,7 +254,9 @@ def install(creation: bool = True):
     conv_filter_grad = primitive(A.conv2d_filter_grad)
 
     def convolve_vjp(argnum, ans, A_, B, axes=None, dot_axes=None, mode="full"):
-        if not _on_device(ans, A_, B):
+        # the reference rule is itself written with convolve/pad/transpose, so it runs on device values as is; the
+        # dedicated input-/filter-gradient kernels below serve the NCHW pattern of examples/convnet.py
+        if not _on_device(ans, A_, B) or not _fast_conv(A_, B, axes, dot_axes, mode) or (argnum == 1 and mode != "valid"):
             return asignal.grad_convolve(argnum, ans, A_, B, axes=axes, dot_axes=dot_axes, mode=mode)
         a_shape = anp.shape(A_)
         if argnum == 0:

@@ -1244,3 +1244,65 @@ def case_shared_denominator_division_bit_exact():
 
 
 OP_CASES["shared_denominator_division_bit_exact"] = case_shared_denominator_division_bit_exact
+
+
+def case_convolve_general():
+    """autograd.scipy.signal.convolve beyond the NCHW pattern (scipy/signal.py:10-76; reference tests
+    tests/test_scipy.py:267-330): 1-D / 2-D / N-d convolved axes, contracted and untouched axes in any position,
+    operands in either size order, modes valid / full / same — values and both VJPs against the reference on NumPy."""
+    from autograd.scipy.signal import convolve
+
+    import autograd.numpy as np
+
+    r = rs(51)
+    configs = [
+        ((5,), (3,), None, None),
+        ((3,), (7,), None, None),                                   # filter larger than signal: roles swap
+        ((6, 5), (3, 2), None, None),
+        ((3, 5), (3, 4), ([1], [0]), None),                         # untouched axes on both sides
+        ((2, 5, 4, 3), (3, 4, 2), ([1, 2], [1, 0]), None),
+        ((2, 4, 2, 3, 2), (2, 5, 4, 3), ([1, 3], [2, 3]), ([0], [0])),
+        ((4, 3, 9, 8), (3, 5, 3, 3), ([2, 3], [2, 3]), ([1], [0])),  # NCHW (dedicated kernels for valid/full)
+        ((4, 3, 3, 3), (3, 5, 6, 7), ([2, 3], [2, 3]), ([1], [0])),  # NCHW with the filter operand LARGER
+    ]
+    for a_shape, b_shape, axes, dot_axes in configs:
+        A, B = r.randn(*a_shape), r.randn(*b_shape)
+        for mode in ("valid", "full", "same"):
+            if mode == "same" and axes is None and len(a_shape) == 1 and b_shape[0] > a_shape[0]:
+                pass  # still defined: 'same' keeps A's extent
+            kw = dict(axes=axes, dot_axes=dot_axes, mode=mode)
+            what = f"convolve {a_shape}*{b_shape} axes={axes} dot={dot_axes} {mode}"
+            check(lambda A, B: convolve(A, B, **kw), A, B, tol=TOL_REDUCE, what=what)
+            loss = lambda A, B: np.sum(np.sin(convolve(A, B, **kw)))
+            for argnum in (0, 1):
+                check_grad(loss, (A, B), TOL_REDUCE, f"{what} vjp arg{argnum}", argnum)
+
+
+OP_CASES["convolve_general"] = case_convolve_general
+
+
+def case_logsumexp_weighted():
+    """scipy.special.logsumexp with weights ``b`` / ``return_sign`` (reference tests test_scipy.py:237-255) and the
+    reference VJP/JVP (scipy/special.py:123-147) running on device values."""
+    from autograd.scipy.special import logsumexp
+
+    import autograd.numpy as np
+    from autograd import grad
+
+    r = rs(52)
+    for shape in ((4,), (3, 4), (2, 3, 4)):
+        x, w = r.randn(*shape) * 3, onp.exp(r.randn(*shape))
+        for axis in (None, 0, len(shape) - 1):
+            for keepdims in (False, True):
+                kw = dict(axis=axis, keepdims=keepdims)
+                check(lambda x, w: logsumexp(x, b=w, **kw), x, w, tol=TOL_REDUCE, what=f"lse b {shape} {kw}")
+                check_grad(lambda x, w: np.sum(logsumexp(x, b=w, **kw) ** 2), (x, w), TOL_REDUCE, f"lse b grad {shape} {kw}")
+    x, w = r.randn(5, 6), r.randn(5, 6)
+    w[0, :] = 0.0                                       # a row without any weight: -inf, shift falls back to 0
+    w[1, 2] = 0.0
+    x[1, 2] = 50.0                                      # the largest entry carries zero weight: not the shift
+    check(lambda x, w: logsumexp(x, b=w, axis=1, return_sign=True), x, w, tol=TOL_REDUCE, what="lse signed weights")
+    check(lambda x: logsumexp(x, axis=0, b=2.5), x, tol=TOL_REDUCE, what="lse scalar weight")
+
+
+OP_CASES["logsumexp_weighted"] = case_logsumexp_weighted
