@@ -194,6 +194,8 @@ class DeviceArray:
             if ufunc is np.matmul:  # a generalized ufunc, not an elementwise one
                 return matmul(*inputs)
             op = UFUNC_OPS.get(ufunc)
+            if op is None and ufunc in UFUNC_ORDER_OPS and len(inputs) == 2 and not kwargs:
+                return order_function(UFUNC_ORDER_OPS[ufunc], inputs[0], inputs[1])
             if op is None:
                 raise TypeError(f"autograd_b200: numpy.{ufunc.__name__} has no device implementation")
             out = kwargs.pop("out", None)
@@ -702,6 +704,21 @@ def elementwise(opname, ufunc, *inputs) -> DeviceArray:
         return ufunc(*host)
     args = [_operand(x) for x in inputs]
     return DeviceArray(lazy.make_op(opname, ufunc, args))
+
+
+def order_function(opname, order, x) -> DeviceArray:
+    """Special functions of an integer order and a device argument — ``jn/jv``, ``yn``, ``iv``, ``ive``,
+    ``polygamma`` — as they appear in the reference's derivative rules (autograd/scipy/special.py:43-48,76-90:
+    ``g * polygamma(1, x)``, ``(j0(x) - jn(2, x)) / 2`` ...).  The order is a host scalar baked into the kernel."""
+    if isinstance(order, DeviceArray) or np.ndim(order) != 0:
+        raise TypeError(f"autograd_b200: {opname[3:]}(order, x) needs a host scalar order on device arguments")
+    n = float(order)
+    if n != int(n) or abs(n) > 1e6 or (opname == "sp_polygamma" and n < 0):
+        raise TypeError(f"autograd_b200: {opname[3:]} of order {order!r} has no device implementation (integer orders only)")
+    x = asarray(x)
+    if x.dtype.kind != "f":
+        x = x.astype(np.float64)
+    return DeviceArray(lazy.make_op(opname, np.copysign, [Const(n, None), x._node]))
 
 
 def where(cond, x=None, y=None):
@@ -2461,8 +2478,10 @@ try:   # scipy.special's ufuncs arrive through __array_ufunc__ like NumPy's (aut
         _uf = getattr(_sps, _name, None)
         if isinstance(_uf, np.ufunc):
             UFUNC_OPS[_uf] = _op
+    UFUNC_ORDER_OPS = {getattr(_sps, _n): _o for _n, _o in (("jv", "sp_jn"), ("yn", "sp_yn"), ("iv", "sp_iv"), ("ive", "sp_ive"))
+                       if isinstance(getattr(_sps, _n, None), np.ufunc)}
 except ImportError:   # SciPy is an optional dependency of the reference (pyproject.toml:55-56)
-    pass
+    UFUNC_ORDER_OPS = {}
 UFUNC_REDUCE = {np.add: "sum", np.multiply: "prod", np.maximum: "max", np.minimum: "min",
                 np.logical_and: "all", np.logical_or: "any"}
 

@@ -358,6 +358,41 @@ def install(creation: bool = True):
             _prim = getattr(anorm, _name)
             _swap_raw(_prim, _norm_raw(_name, _prim.fun))
 
+    # ------------------------------------------------------------ scipy.special functions that are not ufuncs
+    # polygamma / multigammaln are Python functions that coerce their argument (scipy/special/_basic.py); rgamma is a
+    # ufunc without a CUDA twin.  On device operands they become device elementwise ops / compositions; the
+    # reference's rules (special.py:42-54) are kept and now close over themselves: gammaln -> psi -> polygamma(1, .)
+    # -> polygamma(2, .) ...
+    try:
+        import scipy.special as _sps_mod
+    except ImportError:
+        _sps_mod = None
+    if _sps_mod is not None:
+        ref_polygamma, ref_multigammaln, ref_rgamma = aspecial.polygamma.fun, aspecial.multigammaln.fun, aspecial.rgamma.fun
+
+        def _polygamma_raw(n, x):
+            if isinstance(x, DeviceArray):
+                return A.order_function("sp_polygamma", n, x)
+            return ref_polygamma(n, x)
+
+        def _multigammaln_raw(a, d):
+            if isinstance(a, DeviceArray):
+                d = int(d)
+                out = d * (d - 1) * 0.25 * onp.log(onp.pi)     # scipy/special/_spfun_stats.py: multigammaln
+                for j in range(d):
+                    out = out + _sps_mod.gammaln(a - j / 2.0)
+                return out
+            return ref_multigammaln(a, d)
+
+        def _rgamma_raw(x, *args, **kw):
+            if isinstance(x, DeviceArray):
+                return 1.0 / _sps_mod.gamma(x)
+            return ref_rgamma(x, *args, **kw)
+
+        _swap_raw(aspecial.polygamma, _polygamma_raw)
+        _swap_raw(aspecial.multigammaln, _multigammaln_raw)
+        _swap_raw(aspecial.rgamma, _rgamma_raw)
+
     # ------------------------------------------------------------ np.select on device values
     # numpy_wrapper.py:110-112 builds the result element by element from an object array of boxes; on device operands
     # the same "first true condition wins" is composed from the traced ``where`` primitive instead.

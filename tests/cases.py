@@ -1306,3 +1306,42 @@ def case_logsumexp_weighted():
 
 
 OP_CASES["logsumexp_weighted"] = case_logsumexp_weighted
+
+
+def case_scipy_special_integer_orders():
+    """jn / yn / iv / ive / polygamma of a host integer order on device arguments — the functions the reference's
+    derivative rules of j1, y1, i1, psi, gammaln call (autograd/scipy/special.py:43-48,76-90) — values against SciPy,
+    then first and second derivatives against the reference on NumPy."""
+    import scipy.special as sps
+    from autograd.scipy import special as asp
+
+    import autograd.numpy as np
+
+    r = rs(91)
+    x = r.randn(2000) * 6.0
+    pos = onp.abs(x) + 0.05
+    tol = 1e-12
+    for n in (0, 1, 2, 3, 7, -2, -3):
+        check(lambda a, n=n: sps.jv(n, a), x, tol=tol, what=f"jv({n}, x)")
+        check(lambda a, n=n: sps.yn(n, a), pos, tol=tol, what=f"yn({n}, x)")
+        check(lambda a, n=n: sps.iv(n, a), x, tol=tol, what=f"iv({n}, x)")
+        check(lambda a, n=n: sps.ive(n, a), x * 40, tol=tol, what=f"ive({n}, x)")
+    check(lambda a: sps.ive(2, a), onp.array([0.0, 1e-8, 750.0, 5000.0, -5000.0, 1e7, onp.inf, onp.nan])[:6], tol=tol, what="ive range")
+    for n in (1, 2, 3, 5):
+        check(lambda a, n=n: asp.polygamma(n, a), pos * 5, tol=tol, what=f"polygamma({n}, x>0)")
+        check(lambda a, n=n: asp.polygamma(n, a), -pos * 2 - 0.0137, tol=1e-10, what=f"polygamma({n}, x<0)")
+    check(lambda a: asp.polygamma(1, a), onp.array([1.0, 0.5, 1e-3, 50.0, 1e5, 0.0, -1.0]), tol=tol, what="trigamma edges")
+    check(lambda a: asp.multigammaln(a, 3), pos + 1.5, tol=tol, what="multigammaln")
+    check(lambda a: asp.rgamma(a), x, tol=tol, what="rgamma")
+    small = pos[:40] * 3
+    for name, arg in (("j1", small), ("y1", small), ("i1", small[:40] * 0.5), ("j0", small), ("i0", small * 0.5), ("gammaln", small),
+                      ("psi", small), ("gamma", small * 0.5)):
+        fn = getattr(asp, name)
+        check_grad(lambda a, fn=fn: np.sum(fn(a) ** 2), (arg,), TOL_REDUCE, f"d {name}")
+        from autograd import grad
+        check_grad(lambda a, fn=fn: np.sum(grad(lambda b: np.sum(fn(b)))(a) * np.cos(a)), (arg,), TOL_REDUCE, f"d2 {name}")
+    check_grad(lambda a: np.sum(asp.jn(3, a) * asp.yn(2, a) + asp.iv(2, a) + asp.ive(3, a) + asp.polygamma(2, a)), (small,),
+               TOL_REDUCE, "d jn/yn/iv/ive/polygamma")
+
+
+OP_CASES["scipy_special_integer_orders"] = case_scipy_special_integer_orders

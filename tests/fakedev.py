@@ -50,6 +50,13 @@ _OPS1.update({
 })
 
 
+_OPS2.update({
+    "sp_jn": lambda n, x: _sps.jv(n, x), "sp_yn": lambda n, x: _sps.yn(n.astype(np.int64), x),
+    "sp_iv": lambda n, x: _sps.iv(n, x), "sp_ive": lambda n, x: _sps.ive(n, x),
+    "sp_polygamma": lambda n, x: _sps.polygamma(n.astype(np.int64), x),
+})
+
+
 class FakeBackend:
     name = "fake-host"
     sm_count = 148
