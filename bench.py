@@ -272,16 +272,17 @@ def run_b200(args):
     achieved = ALGO_BYTES_PER_POINT * n / (kern_ms * 1e-3) / 1e9
     prog = durs[0][0] if durs else None
     # DRAM traffic per launch from the committed ncu capture of this very command (profiles/r01_c2_fused_ncu_raw.csv:
-    # dram__bytes_read.sum 2.1477 GB + dram__bytes_write.sum 2.1086 GB at 2^28 points), scaled to --n
-    traffic = (2.147744e9 + 2.108638e9) * n / float(1 << 28)
+    # dram__bytes_read.sum 2.1476 GB + dram__bytes_write.sum 2.1058 GB at 2^28 points), scaled to --n
+    traffic = (2.147620e9 + 2.105774e9) * n / float(1 << 28)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": "ncu --set full, profiles/r01_c2_fused_ncu_raw.csv",
-                "fp64_pipe_active_pct_ncu": 70.9,
+                "fp64_pipe_active_pct_ncu": 77.0,
                 "peak_source": peak_src, "kernel": "fused elementwise (generated, NVRTC sm_100a)",
                 "kernel_ms": kern_ms, "kernel_ops_fused": len(prog.instrs) if prog else None,
                 "kernel_share_of_step": kern_ms / ms_per_step,
-                "note": "algorithmic bytes = 16 B/point (read x, write y); the body is ~350 FP64 ops/point, so the "
-                        "kernel sits on the FP64 pipe, not on HBM"}
+                "note": "algorithmic bytes = 16 B/point (read x, write y); the body is 348 recorded ufunc calls = 242 FP64 "
+                        "instructions per point after value numbering and reciprocal sharing, so the kernel sits on the "
+                        "FP64 pipe (77 % active in ncu), not on HBM"}
 
     # ---- end to end through the public API with HOST buffers: H2D + grad + D2H inside the timed region
     for _ in range(2):
