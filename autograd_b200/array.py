@@ -1517,6 +1517,37 @@ def argsort(a, axis=-1, kind=None, order=None, **kw):
     return _sorted(a, axis, False, True)[1]
 
 
+def _check_kth(a, kth, axis):
+    n = asarray(a).shape[axis] if asarray(a).ndim else 1
+    for k in np.atleast_1d(np.asarray(kth)):
+        if not -n <= int(k) < n:
+            raise ValueError(f"kth(={int(k)}) out of bounds ({n})")
+
+
+def partition(a, kth, axis=-1, kind="introselect", order=None):
+    """np.partition.  Any arrangement with the kth element in its sorted position, nothing larger before it and
+    nothing smaller after it is a valid result; the device returns the fully sorted array (one such arrangement:
+    the kth element and the two SETS on either side equal NumPy's, the order inside the sets is introselect's
+    business and differs).  grad_partition (numpy_vjps.py:787-792) only needs ``partition`` and ``argpartition``
+    to describe the same permutation, which they do."""
+    if order is not None:
+        raise NotImplementedError("autograd_b200: structured-array sort order is not supported")
+    if axis is None:
+        a, axis = reshape(asarray(a), (-1,)), 0
+    _check_kth(a, kth, axis)
+    return _sorted(a, axis, True, False)[0]
+
+
+def argpartition(a, kth, axis=-1, kind="introselect", order=None):
+    """np.argpartition: the permutation of :func:`partition` (the stable argsort)."""
+    if order is not None:
+        raise NotImplementedError("autograd_b200: structured-array sort order is not supported")
+    if axis is None:
+        a, axis = reshape(asarray(a), (-1,)), 0
+    _check_kth(a, kth, axis)
+    return _sorted(a, axis, False, True)[1]
+
+
 def kron(a, b):
     a, b = asarray(a), asarray(b)
     nd = max(a.ndim, b.ndim)
@@ -2513,7 +2544,7 @@ FUNCTIONS = {
     np.astype: lambda a, dtype, copy=True, **kw: asarray(a).astype(dtype),
     np.meshgrid: meshgrid, np.linspace: linspace,
     np.tril: tril, np.triu: triu, np.diag: diag, np.diagonal: diagonal, np.trace: trace, np.diff: diff,
-    np.cumsum: cumsum, np.cumprod: cumprod, np.sort: sort, np.argsort: argsort, np.kron: kron, np.rot90: rot90,
+    np.cumsum: cumsum, np.cumprod: cumprod, np.sort: sort, np.argsort: argsort, np.partition: partition, np.argpartition: argpartition, np.kron: kron, np.rot90: rot90,
     np.rollaxis: rollaxis, np.average: average, np.select: select, np.sinc: sinc, np.cross: cross,
     np.gradient: gradient, np.angle: angle, np.real_if_close: real_if_close, np.linalg.norm: norm,
 }

@@ -1345,3 +1345,27 @@ def case_scipy_special_integer_orders():
 
 
 OP_CASES["scipy_special_integer_orders"] = case_scipy_special_integer_orders
+
+
+def case_partition():
+    """np.partition / argpartition: the kth element is in sorted position and the two sides hold the same SETS as
+    NumPy's result (the order inside the sides is unspecified by NumPy); grad_partition agrees with the reference."""
+    import autograd.numpy as np
+
+    r = rs(53)
+    x = r.randn(37)
+    for kth in (0, 5, 18, 36, -3):
+        want = onp.partition(x, kth)
+        got = to_host(onp.partition(to_dev(x), kth))
+        k = kth % x.size
+        assert got[k] == want[k]
+        assert onp.array_equal(onp.sort(got[:k]), onp.sort(want[:k])) and onp.array_equal(onp.sort(got[k:]), onp.sort(want[k:]))
+        perm = to_host(onp.argpartition(to_dev(x), kth))
+        assert perm.dtype == onp.int64 and onp.array_equal(x[perm], got)
+    m = r.randn(4, 9)
+    got = to_host(onp.partition(to_dev(m), 3, axis=1))
+    assert onp.array_equal(got[:, 3], onp.partition(m, 3, axis=1)[:, 3])
+    check_grad(lambda v: np.sum(np.partition(v, 5) * np.arange(37.0)), (x,), TOL_REDUCE, "grad_partition")
+
+
+OP_CASES["partition"] = case_partition
