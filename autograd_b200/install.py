@@ -473,7 +473,9 @@ def install(creation: bool = True):
             symbolic = dev_fn in (A.zeros, A.ones, A.full, A.empty)
 
             def create(*args, **kwargs):
-                if _host_creation_depth or any(isinstance(a, onp.ndarray) for a in args):
+                # a host ARRAY argument is evidence that the caller computes on the host; a 0-d ndarray is what
+                # ArrayVSpace.randn() hands out for a scalar (test_util.py:46) and counts as the scalar it holds
+                if _host_creation_depth or any(isinstance(a, onp.ndarray) and a.ndim > 0 for a in args):
                     return host_fn(*args, **kwargs)
                 res = dev_fn(*args, **kwargs)
                 if symbolic and res._node.op == "full":

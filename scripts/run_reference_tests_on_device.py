@@ -8,10 +8,9 @@ registration are what these tests exercise); with ``--cuda`` the production back
 
     python scripts/run_reference_tests_on_device.py [--cuda] [--ref /root/reference] [pytest args / test files]
 
-Last run (round 1, fake device): 368 passed, 13 skipped, 47 failed — 43 of the failures are the complex-dtype
+Last run (round 1, fake device): 369 passed, 13 skipped, 46 failed — 43 of the failures are the complex-dtype
 variants of test_systematic.py / test_graphs.py (complex dtypes are out of scope), the others
-are float16 storage, ``isinstance(x, np.ndarray)`` on a device array and the
-zero-length ``linspace(x, y, 0)`` second-order check.
+are float16 storage, and ``isinstance(x, np.ndarray)`` on a device array.
 """
 import argparse
 import glob
