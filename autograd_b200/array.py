@@ -2320,7 +2320,7 @@ def einsum(*operands, **kwargs):
     for sub, o in zip(ins, ops):
         for ch, n in zip(sub, o.shape):
             if n != 1:
-                if sizes.get(ch, n) != n:
+                if sizes.get(ch, 1) not in (1, n):    # a size-1 axis broadcasts against any extent (NumPy einsum)
                     raise ValueError(f"einsum: size mismatch for index {ch!r}")
                 sizes[ch] = n
             sizes.setdefault(ch, n)

@@ -1136,6 +1136,9 @@ def case_reference_suite_surface():
     a3, a2, v = r.randn(3, 4, 4), r.randn(4, 4, 3), r.randn(7)
     check(lambda a, b, c: onp.einsum("ijk,lji,lli->lki", a, b, c), a3, a2, a2, tol=TOL_REDUCE, what="einsum three operands, diagonal")
     check(lambda a: onp.einsum("ii->i", a[0]), a3, tol=0, what="einsum diagonal view")
+    # a size-1 axis broadcasts against the other operand's extent (examples/bayesian_neural_net.py:31 "mnd,mdo->mno")
+    check(lambda a, b: onp.einsum("mnd,mdo->mno", a[:1], b), r.randn(2, 5, 4), r.randn(3, 4, 2), tol=TOL_REDUCE, what="einsum broadcast batch")
+    check(lambda a, b: onp.einsum("mnd,mdo->mno", a, b[:1]), r.randn(3, 5, 4), r.randn(2, 4, 2), tol=TOL_REDUCE, what="einsum broadcast batch rhs")
     check(lambda a: onp.einsum("ii", a[0]), a3, tol=TOL_REDUCE, what="einsum trace")
     check(lambda v: onp.atleast_3d(v), v, tol=0, what="atleast_3d 1-D")
     check(lambda a: onp.atleast_3d(a[0]), a3, tol=0, what="atleast_3d 2-D")
