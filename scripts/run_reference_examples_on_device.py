@@ -58,8 +58,7 @@ def main():
         b200.backend.set_backend(FakeBackend(compile_generated=False))
     b200.install()
     import autograd.numpy as np
-    from autograd import grad, value_and_grad, hessian_vector_product, jacobian
-    from autograd.misc.flatten import flatten
+    from autograd import grad
 
     import cases
 
