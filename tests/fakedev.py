@@ -297,9 +297,35 @@ class FakeBackend:
                 else:
                     raise NotImplementedError(op)
                 vals.append(np.asarray(r).astype(out_dt))
+        self._check_value_numbers(program, vals)
         for (j, ch), optr in zip(program.outputs, out_ptrs):
             el, e0 = self._elems(optr, np.dtype(ch))
             el[e0: e0 + n] = np.broadcast_to(vals[j], (n,))
+
+    @staticmethod
+    def _check_value_numbers(program, vals):
+        """The CUDA generator emits instruction j as ``[-]v{rep[j]}`` when codegen._value_numbers says so.  This
+        interpreter evaluates every recorded instruction on its own, so it can check that claim on every program of
+        the CPU suite: the aliased value must be the SAME BITS (signed zeros included; NaNs compare equal)."""
+        from autograd_b200 import codegen
+
+        rep, sgn, _den_of, _den_uses = codegen._value_numbers(program.instrs)
+        for j, r in enumerate(rep):
+            if r == j:
+                continue
+            a = np.asarray(vals[j])
+            b = np.asarray(vals[r])
+            if sgn[j] < 0:
+                b = -b
+            a, b = np.broadcast_arrays(a, b)
+            if a.dtype.kind == "f":
+                nan = np.isnan(a)
+                assert np.array_equal(nan, np.isnan(b)), f"value numbering: NaN pattern of instr {j} vs {r} differs"
+                ai = np.where(nan, 0, a).view(f"i{a.dtype.itemsize}")
+                bi = np.where(nan, 0, b).view(f"i{b.dtype.itemsize}")
+                assert np.array_equal(ai, bi), f"value numbering: instr {j} ({program.instrs[j][0]}) is not bit-identical to {'-' if sgn[j] < 0 else ''}v{r}"
+            else:
+                assert np.array_equal(a, b), f"value numbering: instr {j} differs from v{r}"
 
     def _nvrtc_check(self, program):
         import ctypes as C

@@ -81,3 +81,49 @@ def test_costly_small_subexpressions_are_computed_once(fake_dev, monkeypatch):
         got = (onp.tanh(onp.exp(s) / onp.cosh(s)) * b).get()
         assert sizes == expect
         cases.assert_close(got, want, cases.TOL_ELEMENTWISE, "broadcast sub-expression")
+
+
+def test_c2_kernel_shares_reciprocals_and_prefetches(fake_dev):
+    """Structure of the generated C2 kernel (egrad^4 of tanh, examples/tanh.py:22-33): after value numbering the 41
+    recorded divides are ~22 distinct quotients over 3 denominators, each denominator refined once (b200_rcp), the
+    quotients taken with b200_div, an exact-division twin of the body for out-of-range elements, and the heavy-body
+    loop that prefetches the next iteration's operand."""
+    import autograd_b200 as b200
+    from autograd_b200 import codegen
+
+    from examples import workloads as w
+
+    x = b200.asarray(onp.linspace(-7.0, 7.0, 1 << 13))
+    w.tanh_nth_derivative(4)(x).get()
+    prog = max(fake_dev.programs.values(), key=lambda p: len(p.instrs))
+    ops = [i[0] for i in prog.instrs]
+    assert len(ops) > 300 and ops.count("divide") > 30
+    rep, sgn, den_of, den_uses = codegen._value_numbers(prog.instrs)
+    assert sum(1 for j, r in enumerate(rep) if r == j) < 0.6 * len(ops)          # > 40 % of the body is redundant
+    shared = {d: c for d, c in den_uses.items() if c >= 2}
+    assert 2 <= len(shared) <= 4 and sum(shared.values()) >= 18
+    src, name, _ = codegen.generate(prog)
+    body = src[src.index("__device__ __forceinline__ void body("):src.index('extern "C"')]
+    assert body.count("b200_rcp(") == len(shared)
+    assert body.count("b200_div(") == sum(shared.values())
+    assert "body_exact(" in body and "__noinline__ Outs body_exact" in src
+    kern = src[src.index('extern "C"'):]
+    assert "nx0 = *reinterpret_cast" in kern and "__launch_bounds__(256, 2)" in kern
+
+
+def test_scatter_bodies_never_share_reciprocals(fake_dev):
+    """A body with atomics (np.add.at fused with its index/value expressions) cannot be re-run by the exact twin, so
+    it keeps plain divisions even when quotients share a denominator."""
+    import autograd_b200 as b200
+    from autograd_b200 import codegen
+
+    r = onp.random.RandomState(3)
+    t = b200.array.zeros((8, 8)).copy()
+    i, j = b200.asarray(r.randint(0, 8, 50)), b200.asarray(r.randint(0, 8, 50))
+    a, d = b200.asarray(r.randn(50)), b200.asarray(r.rand(50) + 1.0)
+    onp.add.at(t, (i, j), a / d + (a * a) / d)
+    progs = [p for p in fake_dev.programs.values() if any(ins[0] == "scatter" for ins in p.instrs)]
+    assert progs
+    for p in progs:
+        generated = codegen.generate(p)[0].split("struct Params")[1]      # everything after the fixed prelude
+        assert "body_exact" not in generated and "b200_div(" not in generated and " / " in generated
