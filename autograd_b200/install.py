@@ -393,6 +393,88 @@ def install(creation: bool = True):
         _swap_raw(aspecial.multigammaln, _multigammaln_raw)
         _swap_raw(aspecial.rgamma, _rgamma_raw)
 
+    # ------------------------------------------------------------ scipy.stats densities other than norm, beta functions
+    # autograd/scipy/stats/{gamma,chi2,poisson,t,beta,dirichlet}.py wrap scipy.stats methods that coerce to ndarray; on
+    # device operands the log-densities are composed from device ufuncs with SciPy's own formulas
+    # (scipy/stats/_continuous_distns.py: gamma_gen._logpdf, chi2_gen._logpdf, t_gen._logpdf, beta_gen._logpdf;
+    # _discrete_distns.py: poisson_gen._logpmf; _multivariate.py: dirichlet_gen._logpdf).  The reference's VJPs are kept.
+    # Cumulative distribution functions need the incomplete gamma / beta functions and stay host-only.
+    try:
+        import scipy.special as _sp
+        import autograd.scipy.stats as astats
+    except ImportError:
+        astats = None
+    if astats is not None:
+        def _dev(*vals):
+            return any(isinstance(v, DeviceArray) for v in vals)
+
+        def _xlogy(x, y):            # x * log(y) with 0 * log(0) = 0 (scipy.special.xlogy)
+            return onp.where(x == 0, 0.0, x * onp.log(onp.where(x == 0, 1.0, y)))
+
+        def _xlog1py(x, y):
+            return onp.where(x == 0, 0.0, x * onp.log1p(onp.where(x == 0, 0.0, y)))
+
+        def _betaln(a, b):
+            return _sp.gammaln(a) + _sp.gammaln(b) - _sp.gammaln(a + b)
+
+        def _gamma_logpdf(x, a):
+            return onp.where(x < 0, -onp.inf, _xlogy(a - 1.0, x) - x - _sp.gammaln(a))
+
+        def _chi2_logpdf(x, df):
+            return onp.where(x < 0, -onp.inf, _xlogy(df / 2.0 - 1.0, x) - x / 2.0 - _sp.gammaln(df / 2.0)
+                             - (onp.log(2.0) * df) / 2.0)
+
+        def _poisson_logpmf(k, mu):
+            ok = (k >= 0) & (onp.floor(k) == k)
+            return onp.where(ok, _xlogy(k, mu) - _sp.gammaln(k + 1.0) - mu, -onp.inf)
+
+        def _t_logpdf(x, df, loc=0.0, scale=1.0):
+            y = (x - loc) / scale
+            return (_sp.gammaln(0.5 * df + 0.5) - _sp.gammaln(0.5 * df) - 0.5 * (onp.log(df) + onp.log(onp.pi))
+                    - (df + 1.0) / 2.0 * onp.log1p(y * y / df) - onp.log(scale))
+
+        def _beta_logpdf(x, a, b):
+            inside = (x >= 0) & (x <= 1)
+            return onp.where(inside, _xlog1py(b - 1.0, -x) + _xlogy(a - 1.0, x) - _betaln(a, b), -onp.inf)
+
+        def _dirichlet_logpdf(x, alpha):
+            if anp.shape(x)[0] != anp.shape(alpha)[0]:
+                raise NotImplementedError("autograd_b200: dirichlet with the last component of x left out is not "
+                                          "implemented on device")
+            ln_b = onp.sum(_sp.gammaln(alpha)) - _sp.gammaln(onp.sum(alpha))
+            a1 = alpha - 1.0
+            if onp.ndim(x) > 1:
+                a1 = onp.reshape(a1, (-1,) + (1,) * (onp.ndim(x) - 1))
+            return -ln_b + onp.sum(_xlogy(a1, x), axis=0)
+
+        def _density_raw(ref, log_density, exponentiate):
+            def raw(*args, **kwargs):
+                if not _dev(*args, *kwargs.values()):
+                    return ref(*args, **kwargs)
+                out = log_density(*args, **kwargs)
+                return onp.exp(out) if exponentiate else out
+            return raw
+
+        for _mod, _log_name, _lin_name, _fn in (("gamma", "logpdf", "pdf", _gamma_logpdf), ("chi2", "logpdf", "pdf", _chi2_logpdf),
+                                                ("poisson", "logpmf", "pmf", _poisson_logpmf), ("t", "logpdf", "pdf", _t_logpdf),
+                                                ("beta", "logpdf", "pdf", _beta_logpdf), ("dirichlet", "logpdf", "pdf", _dirichlet_logpdf)):
+            _m = getattr(astats, _mod, None)
+            if _m is None:
+                continue
+            _swap_raw(getattr(_m, _log_name), _density_raw(getattr(_m, _log_name).fun, _fn, False))
+            _swap_raw(getattr(_m, _lin_name), _density_raw(getattr(_m, _lin_name).fun, _fn, True))
+
+        _ref_betaln, _ref_beta = aspecial.betaln.fun, aspecial.beta.fun
+
+        def _betaln_raw(a, b, *args, **kw):
+            return _betaln(a, b) if _dev(a, b) else _ref_betaln(a, b, *args, **kw)
+
+        def _beta_raw(a, b, *args, **kw):
+            return onp.exp(_betaln(a, b)) if _dev(a, b) else _ref_beta(a, b, *args, **kw)   # positive arguments
+
+        _swap_raw(aspecial.betaln, _betaln_raw)
+        _swap_raw(aspecial.beta, _beta_raw)
+
     # ------------------------------------------------------------ np.select on device values
     # numpy_wrapper.py:110-112 builds the result element by element from an object array of boxes; on device operands
     # the same "first true condition wins" is composed from the traced ``where`` primitive instead.

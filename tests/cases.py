@@ -1372,3 +1372,53 @@ def case_partition():
 
 
 OP_CASES["partition"] = case_partition
+
+
+def grad_case_scipy_stats_densities():
+    """autograd.scipy.stats gamma / chi2 / poisson / t / beta / dirichlet densities and special.beta / betaln on device
+    operands: values against scipy.stats on the host, gradients against the reference rules on NumPy
+    (autograd/scipy/stats/*.py; reference tests tests/test_scipy.py:48-224)."""
+    import autograd.scipy.stats as st
+    from autograd.scipy import special as asp
+
+    import autograd.numpy as np
+
+    r = rs(61)
+    x = r.randn(40) ** 2 + 0.3
+    a = r.randn(40) ** 2 + 1.1
+    b = r.randn(40) ** 2 + 1.1
+    u = r.rand(40) * 0.96 + 0.02
+    k = onp.round(r.randn(40) ** 2 * 3)
+    loc, scale, df = r.randn(40), r.randn(40) ** 2 + 0.5, r.randn(40) ** 2 + 2.1
+    tol = 1e-12
+    check(lambda x, a: (st.gamma.logpdf(x, a), st.gamma.pdf(x, a)), x, a, tol=tol, what="gamma")
+    check(lambda x: (st.chi2.logpdf(x, 3), st.chi2.pdf(x, 3)), x, tol=tol, what="chi2")
+    check(lambda k, mu: (st.poisson.logpmf(k, mu), st.poisson.pmf(k, mu)), k, a, tol=tol, what="poisson")
+    check(lambda k, mu: st.poisson.logpmf(k + 0.5, mu), k, a, tol=tol, what="poisson non-integer k")
+    check(lambda x, df, loc, scale: (st.t.logpdf(x, df, loc, scale), st.t.pdf(x, df, loc, scale)), loc * 2, df, loc, scale,
+          tol=tol, what="t")
+    check(lambda u, a, b: (st.beta.logpdf(u, a, b), st.beta.pdf(u, a, b)), u, a, b, tol=tol, what="beta")
+    check(lambda a, b: (asp.betaln(a, b), asp.beta(a, b)), a, b, tol=tol, what="betaln / beta")
+    xs = r.rand(5, 7) + 0.1
+    xs = xs / xs.sum(0)
+    alpha = r.rand(5) * 3 + 0.5
+    check(lambda x, al: (st.dirichlet.logpdf(x, al), st.dirichlet.pdf(x, al)), xs, alpha, tol=1e-11, what="dirichlet")
+    check(lambda x, al: st.dirichlet.logpdf(x, al), xs[:, 0].copy(), alpha, tol=1e-11, what="dirichlet one point")
+
+    for argnum in (0, 1):
+        check_grad(lambda x, a: np.sum(st.gamma.logpdf(x, a) + st.gamma.pdf(x, a)), (x, a), TOL_REDUCE, f"gamma d{argnum}", argnum)
+    check_grad(lambda x: np.sum(st.chi2.logpdf(x, 4) * np.cos(x)), (x,), TOL_REDUCE, "chi2 dx")
+    check_grad(lambda mu, k: np.sum(st.poisson.logpmf(k, mu) + st.poisson.pmf(k, mu)), (a, k), TOL_REDUCE, "poisson dmu")
+    for argnum in (0, 1, 2, 3):
+        check_grad(lambda x, df, loc, scale: np.sum(st.t.logpdf(x, df, loc, scale) + st.t.pdf(x, df, loc, scale)),
+                   (loc * 2, df, loc, scale), TOL_REDUCE, f"t d{argnum}", argnum)
+    for argnum in (0, 1, 2):
+        check_grad(lambda u, a, b: np.sum(st.beta.logpdf(u, a, b)), (u, a, b), TOL_REDUCE, f"beta d{argnum}", argnum)
+        if argnum:
+            check_grad(lambda u, a, b: np.sum(asp.betaln(a, b) * u + asp.beta(a, b)), (u, a, b), TOL_REDUCE, f"betaln d{argnum}", argnum)
+    x1 = xs[:, 0].copy()                        # the reference rule handles one point (dirichlet.py:12-15)
+    check_grad(lambda al, x: st.dirichlet.logpdf(x, al) + st.dirichlet.pdf(x, al), (alpha, x1), TOL_REDUCE, "dirichlet dalpha")
+    check_grad(lambda x, al: st.dirichlet.logpdf(x, al), (x1, alpha), TOL_REDUCE, "dirichlet dx")
+
+
+GRAD_CASES["scipy_stats_densities"] = grad_case_scipy_stats_densities
