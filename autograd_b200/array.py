@@ -2505,7 +2505,8 @@ try:   # scipy.special's ufuncs arrive through __array_ufunc__ like NumPy's (aut
                        ("erfcx", "sp_erfcx"), ("gammaln", "sp_gammaln"), ("gamma", "sp_gamma"), ("psi", "sp_digamma"),
                        ("digamma", "sp_digamma"), ("ndtr", "sp_ndtr"), ("ndtri", "sp_ndtri"), ("log_ndtr", "sp_log_ndtr"),
                        ("expit", "sp_expit"), ("logit", "sp_logit"), ("j0", "sp_j0"), ("j1", "sp_j1"), ("y0", "sp_y0"),
-                       ("y1", "sp_y1"), ("i0", "sp_i0"), ("i1", "sp_i1")):
+                       ("y1", "sp_y1"), ("i0", "sp_i0"), ("i1", "sp_i1"), ("gammainc", "sp_gammainc"),
+                       ("gammaincc", "sp_gammaincc"), ("betainc", "sp_betainc")):
         _uf = getattr(_sps, _name, None)
         if isinstance(_uf, np.ufunc):
             UFUNC_OPS[_uf] = _op

@@ -398,7 +398,6 @@ def install(creation: bool = True):
     # device operands the log-densities are composed from device ufuncs with SciPy's own formulas
     # (scipy/stats/_continuous_distns.py: gamma_gen._logpdf, chi2_gen._logpdf, t_gen._logpdf, beta_gen._logpdf;
     # _discrete_distns.py: poisson_gen._logpmf; _multivariate.py: dirichlet_gen._logpdf).  The reference's VJPs are kept.
-    # Cumulative distribution functions need the incomplete gamma / beta functions and stay host-only.
     try:
         import scipy.special as _sp
         import autograd.scipy.stats as astats
@@ -463,6 +462,40 @@ def install(creation: bool = True):
                 continue
             _swap_raw(getattr(_m, _log_name), _density_raw(getattr(_m, _log_name).fun, _fn, False))
             _swap_raw(getattr(_m, _lin_name), _density_raw(getattr(_m, _lin_name).fun, _fn, True))
+
+        # cumulative distribution functions: regularized incomplete gamma / beta device functions (codegen PRELUDE)
+        def _gamma_cdf(x, a):
+            return onp.where(x < 0, 0.0, _sp.gammainc(a, onp.maximum(x, 0.0)))
+
+        def _chi2_cdf(x, df):
+            return onp.where(x < 0, 0.0, _sp.gammainc(df / 2.0, onp.maximum(x, 0.0) / 2.0))
+
+        def _poisson_cdf(k, mu):
+            return onp.where(k < 0, 0.0, _sp.gammaincc(onp.floor(onp.maximum(k, 0.0)) + 1.0, mu))
+
+        def _beta_cdf(x, a, b):
+            return _sp.betainc(a, b, onp.minimum(onp.maximum(x, 0.0), 1.0))
+
+        def _t_cdf(x, df, loc=0.0, scale=1.0):
+            y = (x - loc) / scale
+            tail = _sp.betainc(0.5, df / 2.0, y * y / (df + y * y))     # = 1 - I_{df/(df+y^2)}(df/2, 1/2), no cancellation
+            return 0.5 + 0.5 * onp.sign(y) * tail
+
+        for _mod, _name, _fn, _log in (("gamma", "cdf", _gamma_cdf, False), ("chi2", "cdf", _chi2_cdf, False),
+                                       ("poisson", "cdf", _poisson_cdf, False), ("beta", "cdf", _beta_cdf, False),
+                                       ("t", "cdf", _t_cdf, False), ("t", "logcdf", _t_cdf, True)):
+            _m = getattr(astats, _mod, None)
+            _prim = getattr(_m, _name, None) if _m is not None else None
+            if _prim is None:
+                continue
+
+            def _cdf_raw(*args, _ref=_prim.fun, _fn=_fn, _log=_log, **kwargs):
+                if not _dev(*args, *kwargs.values()):
+                    return _ref(*args, **kwargs)
+                out = _fn(*args, **kwargs)
+                return onp.log(out) if _log else out
+
+            _swap_raw(_prim, _cdf_raw)
 
         _ref_betaln, _ref_beta = aspecial.betaln.fun, aspecial.beta.fun
 

@@ -1422,3 +1422,53 @@ def grad_case_scipy_stats_densities():
 
 
 GRAD_CASES["scipy_stats_densities"] = grad_case_scipy_stats_densities
+
+
+def grad_case_scipy_incomplete_functions_and_cdfs():
+    """scipy.special.gammainc / gammaincc / betainc as device functions (series + Lentz continued fraction) and the CDFs
+    of autograd.scipy.stats gamma / chi2 / poisson / beta / t composed from them: values against SciPy, derivatives
+    against the reference rules (autograd/scipy/special.py:57-63, stats/*.py)."""
+    import scipy.special as sps
+    import autograd.scipy.stats as st
+    from autograd.scipy import special as asp
+
+    import autograd.numpy as np
+
+    r = rs(62)
+    n = 400
+    a = r.rand(n) * 30 + 0.05
+    b = r.rand(n) * 30 + 0.05
+    x = r.rand(n) * 60
+    u = r.rand(n)
+    tol = 1e-12
+    check(lambda a, x: (sps.gammainc(a, x), sps.gammaincc(a, x)), a, x, tol=tol, what="gammainc / gammaincc")
+    check(lambda x: (sps.gammainc(1, x), sps.gammaincc(2.5, x)), x, tol=tol, what="gammainc scalar a")
+    check(lambda a, b, u: sps.betainc(a, b, u), a, b, u, tol=tol, what="betainc")
+    edge_a = onp.array([0.5, 1.0, 2.0, 3.0, 1.0, 5.0])
+    edge_x = onp.array([0.0, 0.0, 1e-300, onp.inf, 1e-12, 1e3])
+    check(lambda a, x: (sps.gammainc(a, x), sps.gammaincc(a, x)), edge_a, edge_x, tol=tol, what="gammainc edges")
+    check(lambda a, u: sps.betainc(a, a + 0.5, u), edge_a, onp.array([0.0, 1.0, 1e-12, 1 - 1e-12, 0.5, 0.999]), tol=tol, what="betainc edges")
+
+    xs = r.randn(60) ** 2 + 0.05
+    aa = r.randn(60) ** 2 + 1.1
+    bb = r.randn(60) ** 2 + 1.1
+    uu = r.rand(60) * 0.98 + 0.01
+    kk = onp.round(r.randn(60) ** 2 * 3)
+    loc, scale, df = r.randn(60), r.randn(60) ** 2 + 0.5, r.randn(60) ** 2 + 2.1
+    check(lambda x, a: st.gamma.cdf(x, a), xs, aa, tol=tol, what="gamma.cdf")
+    check(lambda x: st.chi2.cdf(x, 3), xs, tol=tol, what="chi2.cdf")
+    check(lambda k, mu: st.poisson.cdf(k, mu), kk, aa, tol=tol, what="poisson.cdf")
+    check(lambda u, a, b: st.beta.cdf(u, a, b), uu, aa, bb, tol=tol, what="beta.cdf")
+    check(lambda x, df, loc, scale: (st.t.cdf(x, df, loc, scale), st.t.logcdf(x, df, loc, scale)), loc * 2.5, df, loc, scale,
+          tol=tol, what="t.cdf / logcdf")
+    check_grad(lambda x, a: np.sum(asp.gammainc(a, x) - 2.0 * asp.gammaincc(a, x)), (xs, aa), TOL_REDUCE, "gammainc dx")
+    check_grad(lambda u, a, b: np.sum(asp.betainc(a, b, u)), (uu, aa, bb), TOL_REDUCE, "betainc dx")
+    check_grad(lambda x, a: np.sum(st.gamma.cdf(x, a) + st.chi2.cdf(x, 4)), (xs, aa), TOL_REDUCE, "gamma/chi2 cdf dx")
+    check_grad(lambda mu, k: np.sum(st.poisson.cdf(k, mu)), (aa, kk), TOL_REDUCE, "poisson cdf dmu")
+    check_grad(lambda u, a, b: np.sum(st.beta.cdf(u, a, b)), (uu, aa, bb), TOL_REDUCE, "beta cdf dx")
+    for argnum in (0, 2):
+        check_grad(lambda x, df, loc, scale: np.sum(st.t.cdf(x, df, loc, scale) + st.t.logcdf(x, df, loc, scale)),
+                   (loc * 2.5, df, loc, scale), TOL_REDUCE, f"t cdf d{argnum}", argnum)
+
+
+GRAD_CASES["scipy_incomplete_functions_and_cdfs"] = grad_case_scipy_incomplete_functions_and_cdfs

@@ -54,7 +54,9 @@ _OPS2.update({
     "sp_jn": lambda n, x: _sps.jv(n, x), "sp_yn": lambda n, x: _sps.yn(n.astype(np.int64), x),
     "sp_iv": lambda n, x: _sps.iv(n, x), "sp_ive": lambda n, x: _sps.ive(n, x),
     "sp_polygamma": lambda n, x: _sps.polygamma(n.astype(np.int64), x),
+    "sp_gammainc": _sps.gammainc, "sp_gammaincc": _sps.gammaincc,
 })
+_OPS3 = {"sp_betainc": _sps.betainc}
 
 
 class FakeBackend:
@@ -294,6 +296,8 @@ class FakeBackend:
                     r = _OPS1[op](args[0])
                 elif op in _OPS2:
                     r = _OPS2[op](args[0], args[1])
+                elif op in _OPS3:
+                    r = _OPS3[op](args[0], args[1], args[2])
                 else:
                     raise NotImplementedError(op)
                 vals.append(np.asarray(r).astype(out_dt))
