@@ -389,6 +389,16 @@ def install(creation: bool = True):
                 return 1.0 / _sps_mod.gamma(x)
             return ref_rgamma(x, *args, **kw)
 
+        ref_gammasgn = aspecial.gammasgn.fun
+
+        def _gammasgn_raw(x, *args, **kw):
+            if isinstance(x, DeviceArray):      # sign of Gamma(x): +1 right of 0, alternating between the poles, NaN at them
+                fl = onp.floor(x)
+                neg = onp.where(x == fl, onp.nan, onp.where(onp.remainder(fl, 2.0) == 0, 1.0, -1.0))
+                return onp.where(x != x, onp.nan, onp.where(x > 0, 1.0, onp.where(x == 0, onp.copysign(1.0, x), neg)))
+            return ref_gammasgn(x, *args, **kw)
+
+        _swap_raw(aspecial.gammasgn, _gammasgn_raw)
         _swap_raw(aspecial.polygamma, _polygamma_raw)
         _swap_raw(aspecial.multigammaln, _multigammaln_raw)
         _swap_raw(aspecial.rgamma, _rgamma_raw)

@@ -1336,6 +1336,8 @@ def case_scipy_special_integer_orders():
     check(lambda a: asp.polygamma(1, a), onp.array([1.0, 0.5, 1e-3, 50.0, 1e5, 0.0, -1.0]), tol=tol, what="trigamma edges")
     check(lambda a: asp.multigammaln(a, 3), pos + 1.5, tol=tol, what="multigammaln")
     check(lambda a: asp.rgamma(a), x, tol=tol, what="rgamma")
+    check(lambda a: asp.gammasgn(a), onp.concatenate([x, [0.0, -0.0, -1.0, -2.0, onp.inf, -onp.inf, onp.nan, 1e-300, -1e-300]]),
+          tol=0, what="gammasgn")
     small = pos[:40] * 3
     for name, arg in (("j1", small), ("y1", small), ("i1", small[:40] * 0.5), ("j0", small), ("i0", small * 0.5), ("gammaln", small),
                       ("psi", small), ("gamma", small * 0.5)):
