@@ -127,3 +127,43 @@ def test_scatter_bodies_never_share_reciprocals(fake_dev):
     for p in progs:
         generated = codegen.generate(p)[0].split("struct Params")[1]      # everything after the fixed prelude
         assert "body_exact" not in generated and "b200_div(" not in generated and " / " in generated
+
+
+def test_roll_push_down_is_exact_and_fuses_sweeps(fake_dev, monkeypatch):
+    """Experimental B200AG_ROLL_PUSH: np.roll of a small pending expression is pushed down to its leaves, so two
+    Jacobi sweeps (fluidsim.py:21-30) become one kernel; values and gradients stay bit-identical to the unfused path."""
+    import autograd_b200 as b200
+    from autograd import value_and_grad
+    from autograd_b200 import array as A
+
+    from examples import workloads as w
+
+    rows = cols = 16
+    p, s0, tg = w.fluid_data(rows, cols)
+    with b200.host_arrays():
+        want_v, want_g = value_and_grad(w.fluid_objective)(p, s0, tg, rows, cols, 2)
+    launches = {}
+    results = {}
+    for limit in (0, 12):
+        monkeypatch.setattr(A, "_ROLL_PUSH_NODES", limit)
+        n0 = fake_dev.launch_count()
+        v, g = value_and_grad(w.fluid_objective)(b200.asarray(p), b200.asarray(s0), b200.asarray(tg), rows, cols, 2)
+        results[limit] = (float(v.get()), g.get())
+        launches[limit] = fake_dev.launch_count() - n0
+    assert results[12][0] == results[0][0] == want_v
+    assert onp.array_equal(results[12][1], results[0][1])
+    cases.assert_close(results[12][1], want_g, cases.TOL_REDUCE, "fluid gradient with roll push-down")
+    assert launches[12] < launches[0]
+
+    # rolls of broadcast operands, negative shifts, several axes at once, a gather underneath
+    monkeypatch.setattr(A, "_ROLL_PUSH_NODES", 12)
+    r = onp.random.RandomState(5)
+    a, b = r.randn(6, 7), r.randn(1, 7)
+    idx = r.randint(0, 6, (6, 7))
+
+    def f(a, b, idx):
+        e = a * 2.0 + b
+        g = a[idx, idx % 7]
+        return onp.roll(e, (2, -3), axis=(0, 1)) + onp.roll(onp.roll(e, 1, 0), -1, 1) * onp.roll(g + b, 5, axis=1) + onp.roll(e, 4)
+
+    cases.check(f, a, b, idx, tol=0, what="roll push-down semantics")
