@@ -52,7 +52,7 @@ EXPAND_WORK = 3.0e7     # repeated op-units (elements x cost) that justify one e
 KEEP_COST = 96
 # Re-materialising nodes that keep being recomputed was measured on C4 (fluidsim): +1 % speed for +65 % retained
 # memory (the 200-step tape would no longer fit 180 GB), so it is off; the hook stays for experiments.
-REUSE_LIMIT = 1 << 30
+REUSE_LIMIT = int(__import__("os").environ.get("B200AG_REUSE_LIMIT", str(1 << 30)))
 # Hard caps that force a flush while a graph is still being built.
 MAX_NODES = 1500
 MAX_LEAVES = 48
