@@ -14,6 +14,7 @@ without the built library raises.
 
 from . import array, backend, lazy
 from .array import DeviceArray, asarray, to_device
+from .complex_array import ComplexDeviceArray
 from .graph import capture
 from .install import host_arrays, install, is_installed
 from .pipeline import map_elementwise
@@ -24,8 +25,8 @@ def synchronize() -> None:
 
 
 def to_host(x):
-    return x.get() if isinstance(x, DeviceArray) else x
+    return x.get() if isinstance(x, (DeviceArray, ComplexDeviceArray)) else x
 
 
-__all__ = ["map_elementwise", "capture", "host_arrays", "DeviceArray", "asarray", "to_device", "to_host", "install", "is_installed", "synchronize", "array",
+__all__ = ["ComplexDeviceArray", "map_elementwise", "capture", "host_arrays", "DeviceArray", "asarray", "to_device", "to_host", "install", "is_installed", "synchronize", "array",
            "backend", "lazy"]

@@ -26,6 +26,17 @@ def _is_box(x) -> bool:
     return _Box is not None and isinstance(x, _Box)
 
 
+# set by autograd_b200.complex_array (complex values are pairs of real device arrays composed from the ops of this module)
+_Complex = None
+_complex_ufunc = None
+_complex_full = None
+_complex_where = None
+
+
+class _ComplexOperand(TypeError):
+    """Raised by ``_operand`` for a complex operand; ``elementwise`` reroutes the call to complex_array.ufunc_call."""
+
+
 class DeviceArray:
     __slots__ = ("_node", "_weak", "__weakref__")
     __array_priority__ = 1000.0
@@ -188,7 +199,7 @@ class DeviceArray:
     # ------------------------------------------------------------ NumPy protocols
     def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
         for x in inputs:
-            if _is_box(x):
+            if _is_box(x) or (_Complex is not None and type(x) is _Complex):
                 return NotImplemented
         if method == "__call__":
             if ufunc is np.matmul:  # a generalized ufunc, not an elementwise one
@@ -248,6 +259,8 @@ class DeviceArray:
         return NotImplemented
 
     def __array_function__(self, func, types, args, kwargs):
+        if _Complex is not None and _Complex in types:
+            return NotImplemented              # ComplexDeviceArray.__array_function__ answers
         impl = FUNCTIONS.get(func)
         if impl is None:
             if func in DECOMPOSE:
@@ -257,7 +270,7 @@ class DeviceArray:
 
     # ------------------------------------------------------------ operators used by VJP closures
     def _binop(self, opname, ufunc, other, reflected=False):
-        if _is_box(other):
+        if _is_box(other) or (_Complex is not None and type(other) is _Complex):
             return NotImplemented
         return elementwise(opname, ufunc, other, self) if reflected else elementwise(opname, ufunc, self, other)
 
@@ -514,6 +527,8 @@ def asarray(x, dtype=None) -> DeviceArray:
     """Device version of ``np.asarray``: uploads host data, passes DeviceArrays through."""
     if isinstance(x, DeviceArray):
         return x if dtype is None else x.astype(dtype)
+    if _Complex is not None and type(x) is _Complex:
+        return x if dtype is None else x.astype(dtype)      # a complex value (pair of device arrays) passes through
     if isinstance(x, (list, tuple)) and any(isinstance(e, DeviceArray) for e in x):
         return stack([asarray(e) for e in x]) if dtype is None else stack([asarray(e) for e in x]).astype(dtype)
     host = np.asarray(x) if dtype is None else np.asarray(x, dtype=dtype)
@@ -561,6 +576,8 @@ def full(shape, fill_value, dtype=None, **_ignored):
     if dtype is None:
         dtype = np.asarray(fill_value).dtype
     dtype = np.dtype(dtype)
+    if dtype.kind == "c" and _complex_full is not None:
+        return _complex_full(_shape_tuple(shape), fill_value, dtype)
     backend.dtype_code(dtype)
     value = np.asarray(fill_value).astype(dtype).item()
     return DeviceArray(lazy.make_full(value, _shape_tuple(shape), dtype))
@@ -652,11 +669,15 @@ def _operand(x):
         return x._node
     if isinstance(x, np.generic):
         if x.dtype not in lazy.SUPPORTED:
+            if x.dtype.kind == "c":
+                raise _ComplexOperand("autograd_b200: complex operand")
             return Const(x.item(), None)
         return Const(x.item(), x.dtype)
     if isinstance(x, (bool, int, float)):
         return Const(x, None)
     if isinstance(x, np.ndarray):
+        if x.dtype.kind == "c":
+            raise _ComplexOperand("autograd_b200: complex operand")
         if x.ndim == 0:
             return _operand(x[()])
         if x.size > 1 and all(s == 0 for s in x.strides):
@@ -666,8 +687,8 @@ def _operand(x):
         return _upload(x)._node
     if isinstance(x, (list, tuple)):
         return asarray(x)._node
-    if isinstance(x, complex):
-        raise TypeError("autograd_b200: complex operands are not supported on the device")
+    if isinstance(x, complex) or (_Complex is not None and type(x) is _Complex):
+        raise _ComplexOperand("autograd_b200: complex operand")
     raise TypeError(f"autograd_b200: cannot use operand of type {type(x).__name__} in a device computation")
 
 
@@ -702,7 +723,12 @@ def elementwise(opname, ufunc, *inputs) -> DeviceArray:
     host = _host_only_operands(inputs)
     if host is not None:
         return ufunc(*host)
-    args = [_operand(x) for x in inputs]
+    try:
+        args = [_operand(x) for x in inputs]
+    except _ComplexOperand:
+        if _complex_ufunc is None:
+            raise
+        return _complex_ufunc(ufunc, inputs)     # complex values are pairs of real device arrays (complex_array.py)
     return DeviceArray(lazy.make_op(opname, ufunc, args))
 
 
@@ -727,7 +753,12 @@ def where(cond, x=None, y=None):
     host = _host_only_operands((cond, x, y))
     if host is not None:
         return np.where(*host)
-    c, a, b = _operand(cond), _operand(x), _operand(y)
+    try:
+        c, a, b = _operand(cond), _operand(x), _operand(y)
+    except _ComplexOperand:
+        if _complex_where is None:
+            raise
+        return _complex_where(cond, x, y)
     if type(c) is Const:
         return asarray(x if c.value else y)
     dts = []

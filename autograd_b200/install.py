@@ -27,7 +27,9 @@ from functools import partial
 import numpy as onp
 
 from . import array as A
+from . import complex_array as CA
 from .array import DeviceArray
+from .complex_array import ComplexDeviceArray
 
 _installed = False
 DeviceArrayBox = None
@@ -55,7 +57,7 @@ def _unbox(x):
 
 def _on_device(*xs) -> bool:
     for x in xs:
-        if isinstance(_unbox(x), DeviceArray):
+        if isinstance(_unbox(x), (DeviceArray, ComplexDeviceArray)):
             return True
     return False
 
@@ -133,6 +135,52 @@ def install(creation: bool = True):
     _DeviceVSpace.__name__ = "DeviceVSpace"
     VSpace.register(DeviceArray, lambda x: _DeviceVSpace(x))
     DeviceVSpace = _DeviceVSpace
+
+    # ------------------------------------------------------------ complex values: a pair of real device arrays
+    # (complex_array.py).  Box = ArrayBox routing; vector space = ComplexArrayVSpace's contract (numpy_vspaces.py:40-66).
+    class _ComplexDeviceArrayBox(ArrayBox):
+        __slots__ = []
+
+        def __iter__(self):
+            for i in range(len(self)):
+                yield self[i]
+
+    _ComplexDeviceArrayBox.__name__ = "ComplexDeviceArrayBox"
+    _ComplexDeviceArrayBox.register(ComplexDeviceArray)
+
+    class _ComplexDeviceVSpace(_DeviceVSpace):
+        iscomplex = True
+
+        @property
+        def size(self):
+            return A.prod(self.shape) * 2
+
+        def zeros(self):
+            return CA.full(self.shape, 0.0, self.dtype)
+
+        def ones(self):
+            return CA.full(self.shape, 1.0 + 1.0j, self.dtype)
+
+        def standard_basis(self):
+            for idxs in onp.ndindex(*self.shape):
+                for v in (1.0, 1.0j):
+                    vect = onp.zeros(self.shape, dtype=self.dtype)
+                    vect[idxs] = v
+                    yield CA.as_complex(vect)
+
+        def randn(self):
+            return CA.as_complex((onp.array(onp.random.randn(*self.shape)) + 1.0j * onp.array(onp.random.randn(*self.shape)))
+                                 .astype(self.dtype))
+
+        def _inner_prod(self, x, y):
+            x, y = CA.as_complex(x), CA.as_complex(y)          # Re <conj(x), y>
+            return A.dot(A.ravel(x.re), A.ravel(y.re)) + A.dot(A.ravel(x.im), A.ravel(y.im))
+
+        def _covector(self, x):
+            return CA.as_complex(x).conj()
+
+    _ComplexDeviceVSpace.__name__ = "ComplexDeviceVSpace"
+    VSpace.register(ComplexDeviceArray, lambda x: _ComplexDeviceVSpace(x))
 
     # ------------------------------------------------------------ broadcast-back of reduction cotangents
     ref_repeat = nv.repeat_to_match_shape
@@ -313,7 +361,8 @@ def install(creation: bool = True):
     ref_parse = nw._parse_einsum_input
 
     def _parse_raw(*args):
-        stand_ins = [onp.broadcast_to(onp.zeros((), a.dtype), a.shape) if isinstance(a, DeviceArray) else a for a in args]
+        stand_ins = [onp.broadcast_to(onp.zeros((), a.dtype), a.shape) if isinstance(a, (DeviceArray, ComplexDeviceArray)) else a
+                     for a in args]
         return ref_parse(stand_ins)
 
     parse_einsum_input = notrace_primitive(_parse_raw)

@@ -1474,3 +1474,97 @@ def grad_case_scipy_incomplete_functions_and_cdfs():
 
 
 GRAD_CASES["scipy_incomplete_functions_and_cdfs"] = grad_case_scipy_incomplete_functions_and_cdfs
+
+
+def _cdev(z):
+    """Host complex ndarray -> ComplexDeviceArray (pair of real device arrays)."""
+    from autograd_b200 import complex_array as CA
+
+    return CA.as_complex(z)
+
+
+def _ccheck(fn, *host_args, tol=1e-11, what=""):
+    with onp.errstate(all="ignore"):
+        want = fn(*host_args)
+    dev_args = [_cdev(a) if isinstance(a, onp.ndarray) and a.dtype.kind == "c" else to_dev(a) for a in host_args]
+    got = fn(*dev_args)
+    for g, w in zip(leaves(got), leaves(want)):
+        g = g.get() if hasattr(g, "get") else g
+        g, w = onp.asarray(g), onp.asarray(w)
+        assert g.shape == w.shape and g.dtype == w.dtype, f"{what}: {g.shape} {g.dtype} vs {w.shape} {w.dtype}"
+        scale = max(float(onp.max(onp.abs(w))), 1e-300) if w.size else 1.0
+        err = float(onp.max(onp.abs(g - w))) if w.size else 0.0
+        assert err <= tol * scale, f"{what}: max abs err {err:.3e} > {tol:g} * {scale:.3e}"
+
+
+def case_complex_values():
+    """Complex values on the device are pairs of real device arrays (complex_array.py) whose ufuncs are composed from
+    the real ones with NumPy's complex formulas: values against NumPy on the same inputs."""
+    r = rs(71)
+    z = r.randn(5, 4) + 1j * r.randn(5, 4)
+    w = r.randn(5, 4) + 0.5j * r.randn(5, 4)
+    x = r.randn(5, 4)
+    for name in ("exp", "log", "sqrt", "sin", "cos", "tan", "sinh", "cosh", "tanh", "exp2", "expm1", "log2", "log10", "log1p",
+                 "arcsinh", "arccosh", "arctanh", "square", "reciprocal", "negative", "conjugate", "absolute"):
+        fn = getattr(onp, name)
+        _ccheck(lambda a, fn=fn: fn(a), z, what=f"complex {name}")
+    for name in ("add", "subtract", "multiply", "divide", "power"):
+        fn = getattr(onp, name)
+        _ccheck(lambda a, b, fn=fn: fn(a, b), z, w, what=f"complex {name}")
+        _ccheck(lambda a, b, fn=fn: fn(a, b), z, x * x + 0.5, what=f"complex-real {name}")
+        _ccheck(lambda a, b, fn=fn: fn(b, a), z, x * x + 0.5, what=f"real-complex {name}")
+    _ccheck(lambda a: (a * 2.0, a + 1.5j, (0.5 - 2j) * a, a / (1 + 1j), a ** 3, a ** -2, 2.0 ** a, a ** (0.5 + 0.25j)), z, what="complex scalars")
+    _ccheck(lambda a, b: (a * 1j, b + 0j, b * (1 + 2j)), z, x, what="promotion of real device arrays")
+    _ccheck(lambda a: (onp.real(a), onp.imag(a), onp.angle(a), onp.conj(a), onp.abs(a), a.T, a.reshape(4, 5), a[1:, ::2],
+                       onp.transpose(a), onp.ravel(a), onp.concatenate([a, a * 2.0], axis=1), onp.where(onp.real(a) > 0, a, 1j)), z,
+            what="complex structure")
+    _ccheck(lambda a: (onp.sum(a), onp.sum(a, axis=0), onp.mean(a, axis=1, keepdims=True), onp.prod(a, axis=0), onp.prod(a),
+                       onp.var(a), onp.std(a, axis=0), onp.max(a), onp.min(a, axis=1)), z, what="complex reductions")
+    _ccheck(lambda a, b: (onp.dot(a, b.T), onp.matmul(a.T, b), onp.tensordot(a, b, axes=([0], [0])), onp.outer(a[0], b[1]),
+                          onp.inner(a[0], b[0]), onp.einsum("ij,kj->ik", a, b), onp.kron(a[:2, :2], b[:2, :3])), z, w,
+            tol=1e-10, what="complex contractions")
+    _ccheck(lambda a, b: (onp.dot(a, b.T), onp.dot(b, a.T)), z, x, tol=1e-10, what="complex-real contractions")
+    edge = onp.array([0j, 1 + 0j, -1 + 0j, 1j, -1j, 3 - 4j, -2 + 1e-3j, 1e-8 + 1e-8j])
+    _ccheck(lambda a: (onp.sqrt(a), onp.abs(a), onp.exp(a), a * a, onp.conj(a) / (a + 1.5)), edge, what="complex edge values")
+
+
+OP_CASES["complex_values"] = case_complex_values
+
+
+def grad_case_complex():
+    """Reverse and forward mode through complex device values (ComplexDeviceVSpace mirrors ComplexArrayVSpace,
+    numpy_vspaces.py:40-66): gradients against the reference on NumPy, and autograd's own check_grads on device values
+    (the complex halves of the reference's tests/test_systematic.py, tests/test_complex.py)."""
+    import autograd.numpy as np
+    from autograd import grad
+    from autograd.test_util import check_grads
+
+    r = rs(72)
+    zh = r.randn(4, 3) + 0.3j * r.randn(4, 3)
+    xh = r.randn(4, 3)
+
+    def real_loss(z, x):
+        u = np.exp(z * 0.5) * np.sin(z) + x * z
+        v = np.dot(u, np.conj(u).T)
+        return np.real(np.sum(v * v)) + np.sum(np.abs(z) ** 2) + np.sum(np.angle(z + 3.0))
+
+    want = _ref(grad(real_loss, 0), zh, xh)
+    got = grad(real_loss, 0)(_cdev(zh), to_dev(xh)).get()
+    got, want = onp.asarray(got), onp.asarray(want)
+    assert got.dtype == want.dtype == onp.complex128
+    assert_close(got.real.copy(), want.real.copy(), TOL_REDUCE, "complex grad wrt z (real part)")
+    assert_close(got.imag.copy(), want.imag.copy(), TOL_REDUCE, "complex grad wrt z (imaginary part)")
+    want = _ref(grad(real_loss, 1), zh, xh)
+    got = grad(real_loss, 1)(_cdev(zh), to_dev(xh))
+    assert isinstance(got, b200.DeviceArray)                      # a real argument gets a real gradient (match_complex)
+    assert_close(got.get(), want, TOL_REDUCE, "complex grad wrt real x")
+    z = _cdev(zh)
+    for fn in (np.exp, np.log, np.sqrt, np.tanh, np.arcsinh, np.abs, np.angle, np.real, np.imag, np.conj):
+        check_grads(fn, modes=["rev", "fwd"], order=2)(z)
+    check_grads(lambda a, b: a * b + a / b, modes=["rev", "fwd"], order=2)(z, _cdev(zh[::-1].copy() + 2.0))
+    check_grads(lambda a, b: np.dot(a, b.T), modes=["rev", "fwd"], order=2)(z, to_dev(xh))
+    check_grads(lambda a: np.sum(a, axis=0) * np.prod(a, axis=1)[:3] + np.mean(a), modes=["rev"], order=1)(z)
+    check_grads(lambda a: np.max(a, axis=0), modes=["rev"], order=1)(z)
+
+
+GRAD_CASES["complex"] = grad_case_complex
