@@ -213,6 +213,31 @@ def main():
         X, y = rs.randn(12, 1), rs.randn(12)
         compare("gp", grad(log_marginal_likelihood), (rs.randn(num_params) * 0.1, X, y))
 
+    @probe
+    def define_gradient():
+        import define_gradient as m            # a user-defined primitive with its own VJP (extension API on device values)
+
+        def example_func(y):
+            return np.sum(m.logsumexp(y ** 2))
+        compare("define_gradient", grad(example_func), (rs.randn(10),))
+        compare("define_gradient 2nd", grad(lambda y: np.sum(grad(example_func)(y) ** 2)), (rs.randn(10),))
+
+    @probe
+    def fixed_points():
+        import fixed_points as m
+        compare("fixed_points sqrt", grad(m.sqrt), (onp.array(2.0),), tol=1e-6)       # fixed_point primitive, scalar iterate
+
+    @probe
+    def logistic_regression():
+        # the example is a script: restate its three functions on its own toy data (logistic_regression.py:6-22)
+        inputs = onp.array([[0.52, 1.12, 0.77], [0.88, -1.08, 0.15], [0.52, 0.06, -1.30], [0.74, -2.49, 1.39]])
+        targets = onp.array([1.0, 1.0, 0.0, 1.0])
+
+        def training_loss(weights, inputs, targets):
+            preds = 0.5 * (np.tanh(np.dot(inputs, weights)) + 1)
+            return -np.sum(np.log(preds * targets + (1 - preds) * (1 - targets)))
+        compare("logistic regression", grad(training_loss), (onp.array([0.1, -0.2, 0.3]), inputs, targets))
+
     names = args.names or list(probes)
     ok = bad = 0
     for n in names:
