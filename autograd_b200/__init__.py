@@ -13,6 +13,7 @@ without the built library raises.
 """
 
 from . import array, backend, lazy
+from . import linalg  # noqa: F401  (registers np.linalg.solve/inv/det/slogdet/cholesky for device arrays)
 from .array import DeviceArray, asarray, to_device
 from .complex_array import ComplexDeviceArray
 from .graph import capture

@@ -556,6 +556,44 @@ def install(creation: bool = True):
 
             _swap_raw(_prim, _cdf_raw)
 
+        # multivariate normal (autograd/scipy/stats/multivariate_normal.py): log-density and entropy through the composed
+        # device solve / slogdet of autograd_b200.linalg (SciPy's _PSD uses an eigendecomposition; for a non-singular
+        # covariance both are the same quadratic form and log-determinant)
+        def _mvn_logpdf(x, mean, cov, allow_singular=False):
+            if allow_singular:
+                raise NotImplementedError("autograd_b200: multivariate_normal with allow_singular=True is not implemented on device")
+            x, mean, cov = (A.asarray(v) if not isinstance(v, DeviceArray) else v for v in (x, mean, cov))
+            if cov.ndim == 0:
+                cov = A.reshape(cov, (1, 1))
+            elif cov.ndim == 1:
+                cov = A.diag(cov)
+            d = cov.shape[-1]
+            dev = x - mean
+            if d == 1 and dev.ndim == 0:
+                dev = A.reshape(dev, (1,))
+            single = dev.ndim == 1
+            if d == 1 and (dev.ndim == 0 or dev.shape[-1] != 1):
+                dev, single = dev[..., None], dev.ndim == 0
+            dev2 = A.reshape(dev, (-1, d))                                   # points x d
+            sol = onp.linalg.solve(cov, dev2.T)                              # d x points
+            maha = onp.sum(dev2.T * sol, axis=0)
+            _sgn, logdet = onp.linalg.slogdet(cov)
+            out = -0.5 * (d * onp.log(2.0 * onp.pi) + logdet + maha)
+            return A.reshape(out, dev.shape[:-1]) if not single else A.reshape(out, ())
+
+        def _mvn_entropy(mean, cov):
+            cov = A.asarray(cov) if not isinstance(cov, DeviceArray) else cov
+            _sgn, logdet = onp.linalg.slogdet(2.0 * onp.pi * onp.e * cov)
+            return 0.5 * logdet
+
+        _mvn = getattr(astats, "multivariate_normal", None)
+        if _mvn is not None:
+            _swap_raw(_mvn.logpdf, _density_raw(_mvn.logpdf.fun, _mvn_logpdf, False))
+            _swap_raw(_mvn.pdf, _density_raw(_mvn.pdf.fun, _mvn_logpdf, True))
+            _ref_entropy = _mvn.entropy.fun
+            _swap_raw(_mvn.entropy, lambda mean, cov, *a, **k: _mvn_entropy(mean, cov) if _dev(mean, cov)
+                      else _ref_entropy(mean, cov, *a, **k))
+
         _ref_betaln, _ref_beta = aspecial.betaln.fun, aspecial.beta.fun
 
         def _betaln_raw(a, b, *args, **kw):

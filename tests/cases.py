@@ -1570,3 +1570,51 @@ def grad_case_complex():
 
 
 GRAD_CASES["complex"] = grad_case_complex
+
+
+def grad_case_linalg_composed():
+    """np.linalg.solve / inv / det / slogdet / cholesky composed from device array operations (autograd_b200/linalg.py:
+    Gauss-Jordan with on-device partial pivoting, column Cholesky) and scipy.stats.multivariate_normal on top of them:
+    values against NumPy / SciPy, gradients against the reference rules (autograd/numpy/linalg.py:57-88,260-279,
+    autograd/scipy/stats/multivariate_normal.py)."""
+    import scipy.stats as sst
+    import autograd.scipy.stats.multivariate_normal as mvn
+
+    import autograd.numpy as np
+
+    r = rs(81)
+    for n in (1, 3, 6):
+        a = r.randn(n, n) + 0.5 * onp.eye(n)
+        bm, bv = r.randn(n, 2), r.randn(n)
+        check(lambda a, b: onp.linalg.solve(a, b), a, bm, tol=TOL_REDUCE, what=f"solve {n} matrix rhs")
+        check(lambda a, b: onp.linalg.solve(a, b), a, bv, tol=TOL_REDUCE, what=f"solve {n} vector rhs")
+        check(lambda a: (onp.linalg.inv(a), onp.linalg.det(a)), a, tol=TOL_REDUCE, what=f"inv/det {n}")
+        check(lambda a: tuple(onp.linalg.slogdet(a)), a, tol=TOL_REDUCE, what=f"slogdet {n}")
+        spd = a @ a.T + n * onp.eye(n)
+        check(lambda s: onp.linalg.cholesky(s), spd, tol=TOL_REDUCE, what=f"cholesky {n}")
+    perm = onp.array([[0.0, 2.0, 1.0], [1e-9, 1.0, 3.0], [4.0, 0.5, 0.25]])          # needs the row exchanges
+    check(lambda a: (onp.linalg.inv(a), onp.linalg.det(a), onp.linalg.solve(a, a[:, 0] + 1.0)), perm, tol=TOL_REDUCE, what="pivoting")
+    stack = r.randn(3, 4, 4) + onp.eye(4)
+    check(lambda a, b: (onp.linalg.inv(a), onp.linalg.det(a), onp.linalg.solve(a, b)), stack, r.randn(3, 4, 2), tol=TOL_REDUCE,
+          what="batched")
+    a = r.randn(4, 4) + onp.eye(4)
+    b = r.randn(4, 3)
+    check_grad(lambda a, b: np.sum(np.linalg.solve(a, b) ** 2), (a, b), TOL_REDUCE, "solve da", 0)
+    check_grad(lambda a, b: np.sum(np.linalg.solve(a, b) ** 2), (a, b), TOL_REDUCE, "solve db", 1)
+    check_grad(lambda a: np.sum(np.linalg.inv(a) * np.cos(a)) + np.linalg.det(a) + np.linalg.slogdet(a)[1], (a,), TOL_REDUCE, "inv/det/slogdet")
+    spd = a @ a.T + 4 * onp.eye(4)
+    check_grad(lambda s: np.sum(np.linalg.cholesky(s) ** 3), (spd,), TOL_REDUCE, "cholesky")
+
+    x, mean = r.randn(7, 4), r.randn(4)
+    with onp.errstate(all="ignore"):
+        want = sst.multivariate_normal.logpdf(x, mean, spd)
+    got = to_host(mvn.logpdf(to_dev(x), to_dev(mean), to_dev(spd)))
+    assert_close(got, want, TOL_REDUCE, "mvn.logpdf")
+    assert_close(to_host(mvn.logpdf(to_dev(x[0]), to_dev(mean), to_dev(spd))), onp.asarray(sst.multivariate_normal.logpdf(x[0], mean, spd)),
+                 TOL_REDUCE, "mvn.logpdf one point")
+    assert_close(to_host(mvn.entropy(to_dev(mean), to_dev(spd))), onp.asarray(sst.multivariate_normal.entropy(mean, spd)), TOL_REDUCE, "mvn.entropy")
+    for argnum in (0, 1, 2):
+        check_grad(lambda x, m, c: np.sum(mvn.logpdf(x, m, c)) + np.sum(mvn.pdf(x, m, c)), (x, mean, spd), TOL_REDUCE, f"mvn d{argnum}", argnum)
+
+
+GRAD_CASES["linalg_composed"] = grad_case_linalg_composed
