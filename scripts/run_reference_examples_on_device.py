@@ -214,6 +214,24 @@ def main():
         compare("gp", grad(log_marginal_likelihood), (rs.randn(num_params) * 0.1, X, y))
 
     @probe
+    def gaussian_process_predict():
+        import gaussian_process as m
+        num_params, predict, lml = m.make_gp_funs(m.rbf_covariance, num_cov_params=2)
+        X, y, xs = rs.randn(10, 1), rs.randn(10), rs.randn(5, 1)
+
+        def loss(params, X, y, xs):
+            mean, cov = predict(params, X, y, xs)
+            return np.sum(mean ** 2) + np.sum(np.diag(cov))
+        compare("gp predict", grad(loss), (rs.randn(num_params) * 0.1, X, y, xs))
+
+    @probe
+    def bayesian_optimization():
+        import bayesian_optimization as m
+        mean, std = rs.randn(8), rs.rand(8) + 0.5
+        compare("expected_new_max", grad(lambda mu, sd: np.sum(m.expected_new_max(mu, sd, 0.3))), (mean, std))
+        compare("probability_of_improvement", grad(lambda mu, sd: np.sum(m.probability_of_improvement(mu, sd, 0.3))), (mean, std))
+
+    @probe
     def define_gradient():
         import define_gradient as m            # a user-defined primitive with its own VJP (extension API on device values)
 

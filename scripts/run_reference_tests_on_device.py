@@ -9,8 +9,8 @@ registration are what these tests exercise); with ``--cuda`` the production back
     python scripts/run_reference_tests_on_device.py [--cuda] [--ref /root/reference] [pytest args / test files]
 
 Last run (round 1, fake device): 413 passed, 13 skipped, 2 failed (float16 storage; ``isinstance(x, np.ndarray)`` on a
-device array).  test_complex.py: all pass.  test_scipy.py: 74 passed, 15 failed (multivariate_normal / scipy.linalg /
-scipy.integrate, non-integer Bessel orders, complex erf).
+device array).  test_complex.py: all pass.  test_scipy.py: 79 passed, 10 failed (singular-covariance multivariate_normal,
+scipy.linalg / scipy.integrate, non-integer Bessel orders, complex erf).  test_linalg.py: 24 passed, 39 failed (eigh/eig/svd/pinv).
 """
 import argparse
 import glob
