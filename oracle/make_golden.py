@@ -134,6 +134,33 @@ def main():
     W, X, T = w.convnet_data(6, N)
     g = grad(loss)(W, X, T)
     onp.savez(os.path.join(OUT, "c5_convnet_small.npz"), n_weights=N, value=loss(W, X, T), grad=g)
+    # ---------------- rows a13 / a14 beyond the configs: weighted logsumexp and general N-d convolve (values + both VJPs)
+    from autograd.scipy.signal import convolve
+    from autograd.scipy.special import logsumexp
+
+    rs = onp.random.RandomState(123)
+    out = {}
+    x, b = rs.randn(5, 6) * 3, onp.exp(rs.randn(5, 6))
+    out["lse_x"], out["lse_b"] = x, b
+    for axis in (None, 0, 1):
+        tag = "all" if axis is None else str(axis)
+        out[f"lse_val_{tag}"] = logsumexp(x, axis=axis, b=b)
+        out[f"lse_grad_{tag}"] = grad(lambda x_: np.sum(logsumexp(x_, axis=axis, b=b) ** 2))(x)
+    onp.savez(os.path.join(OUT, "a13_logsumexp_weighted.npz"), **out)
+
+    out = {}
+    configs = {"1d": ((7,), (3,), None, None), "swap": ((3,), (6,), None, None), "axes": ((2, 5, 4, 3), (3, 4, 2), ([1, 2], [1, 0]), None),
+               "dot": ((2, 4, 2, 3, 2), (2, 5, 4, 3), ([1, 3], [2, 3]), ([0], [0])), "nchw": ((3, 2, 8, 7), (2, 4, 3, 3), ([2, 3], [2, 3]), ([1], [0]))}
+    for name, (a_shape, b_shape, axes, dot_axes) in configs.items():
+        A, B = rs.randn(*a_shape), rs.randn(*b_shape)
+        out[f"{name}_A"], out[f"{name}_B"] = A, B
+        for mode in ("valid", "full", "same"):
+            kw = dict(axes=axes, dot_axes=dot_axes, mode=mode)
+            out[f"{name}_{mode}_val"] = convolve(A, B, **kw)
+            loss = lambda A_, B_: np.sum(np.sin(convolve(A_, B_, **kw)))
+            out[f"{name}_{mode}_gA"] = grad(loss, 0)(A, B)
+            out[f"{name}_{mode}_gB"] = grad(loss, 1)(A, B)
+    onp.savez(os.path.join(OUT, "a14_convolve_general.npz"), **out)
     print("make_golden: wrote", sorted(os.listdir(OUT)))
     return 0
 

@@ -83,6 +83,46 @@ def _run_all(asarray, getter, exact):
     cases.assert_close(getter(grad(loss)(lift(W), lift(X), lift(T))), gold["grad"], tol_r, "C5 grad")
 
 
+A14_CONFIGS = {"1d": (None, None), "swap": (None, None), "axes": (([1, 2], [1, 0]), None),
+               "dot": (([1, 3], [2, 3]), ([0], [0])), "nchw": (([2, 3], [2, 3]), ([1], [0]))}
+
+
+def _run_a13_a14(lift, getter):
+    """Rows a13 / a14 beyond the five configs: weighted logsumexp and general N-d convolve against fixtures produced by
+    the reference itself (oracle/make_golden.py)."""
+    from autograd import grad
+    from autograd.scipy.signal import convolve
+    from autograd.scipy.special import logsumexp
+
+    import autograd.numpy as np
+
+    gold = _load("a13_logsumexp_weighted.npz")
+    x, b = gold["lse_x"], gold["lse_b"]
+    for axis in (None, 0, 1):
+        tag = "all" if axis is None else str(axis)
+        cases.assert_close(onp.asarray(getter(logsumexp(lift(x), axis=axis, b=lift(b)))), gold[f"lse_val_{tag}"], cases.TOL_REDUCE, f"a13 value {tag}")
+        g = grad(lambda x_: np.sum(logsumexp(x_, axis=axis, b=lift(b)) ** 2))(lift(x))
+        cases.assert_close(getter(g), gold[f"lse_grad_{tag}"], cases.TOL_REDUCE, f"a13 grad {tag}")
+    gold = _load("a14_convolve_general.npz")
+    for name, (axes, dot_axes) in A14_CONFIGS.items():
+        A, B = gold[f"{name}_A"], gold[f"{name}_B"]
+        for mode in ("valid", "full", "same"):
+            kw = dict(axes=axes, dot_axes=dot_axes, mode=mode)
+            cases.assert_close(getter(convolve(lift(A), lift(B), **kw)), gold[f"{name}_{mode}_val"], cases.TOL_REDUCE, f"a14 {name} {mode}")
+            loss = lambda A_, B_: np.sum(np.sin(convolve(A_, B_, **kw)))
+            cases.assert_close(getter(grad(loss, 0)(lift(A), lift(B))), gold[f"{name}_{mode}_gA"], cases.TOL_REDUCE, f"a14 {name} {mode} dA")
+            cases.assert_close(getter(grad(loss, 1)(lift(A), lift(B))), gold[f"{name}_{mode}_gB"], cases.TOL_REDUCE, f"a14 {name} {mode} dB")
+
+
+def test_host_logic_matches_golden_a13_a14(fake_dev):
+    _run_a13_a14(cases.to_dev, cases.to_host)
+
+
+@pytest.mark.gpu
+def test_device_matches_golden_a13_a14(cuda_dev):
+    _run_a13_a14(cases.to_dev, cases.to_host)
+
+
 def test_oracle_restated_workloads_match_reference_examples_bit_for_bit(fake_dev):
     import autograd_b200 as b200
 
