@@ -73,3 +73,53 @@ def untake_pairs(shape, rows, cols, g):
     out = np.zeros(shape)
     np.add.at(out, (rows, cols), g)
     return out
+
+
+def logsumexp_weighted_and_grad(x, b, axis=None):
+    """log(sum(b * exp(x))) over ``axis`` and the gradient of sum(result**2) wrt x, written out by hand.
+
+    forward : shift by the maximum (scipy/special/_logsumexp.py); backward: autograd/scipy/special.py:123-131 —
+    d lse / d x = b * exp(x - lse) broadcast back over the reduced axes; the square's VJP is 2 * lse."""
+    m = np.max(x, axis=axis, keepdims=True)
+    s = np.sum(b * np.exp(x - m), axis=axis, keepdims=True)
+    lse = np.log(s) + m
+    grad = 2.0 * lse * b * np.exp(x - lse)
+    return (lse.reshape(()) if axis is None else np.squeeze(lse, axis=axis)), grad
+
+
+def convolve_direct(A, B, axes=None, dot_axes=((), ()), mode="full"):
+    """autograd.scipy.signal.convolve (scipy/signal.py:10-76) as explicit sums: no strided views, no einsum.
+
+    out[ia..., ib..., p...] = sum_{d, k} A[ia, d, k] * B[ib, d, p - k]   (true convolution along the convolved axes,
+    contraction over the dot axes, untouched axes of A then of B first — the reference's output layout), restricted to
+    the window that ``mode`` keeps: 'full' every p with overlap, 'valid' the p where the smaller operand lies fully
+    inside the larger, 'same' the central part of 'full' with A's extent."""
+    A, B = np.asarray(A, dtype=float), np.asarray(B, dtype=float)
+    if axes is None:
+        axes = (list(range(A.ndim)), list(range(A.ndim)))
+    ca, cb = [list(a) for a in axes]
+    da, db = [list(a) for a in dot_axes]
+    ia = [i for i in range(A.ndim) if i not in ca and i not in da]
+    ib = [i for i in range(B.ndim) if i not in cb and i not in db]
+    At = np.transpose(A, ia + da + ca)
+    Bt = np.transpose(B, ib + db + cb)
+    na, nb = [A.shape[i] for i in ca], [B.shape[i] for i in cb]
+    full_shape = [x + y - 1 for x, y in zip(na, nb)]
+    out = np.zeros([A.shape[i] for i in ia] + [B.shape[i] for i in ib] + full_shape)
+    nia, nib, nd = len(ia), len(ib), len(da)
+    for ka in np.ndindex(*na):
+        a_slab = At[(Ellipsis,) + ka]                                   # [ia..., d...]
+        for kb in np.ndindex(*nb):
+            b_slab = Bt[(Ellipsis,) + kb]                               # [ib..., d...]
+            contrib = np.tensordot(a_slab, b_slab, axes=(list(range(nia, nia + nd)), list(range(nib, nib + nd))))
+            out[(Ellipsis,) + tuple(i + j for i, j in zip(ka, kb))] += contrib
+    if mode == "full":
+        return out
+    sl = [slice(None)] * (nia + nib)
+    for x, y in zip(na, nb):
+        if mode == "valid":
+            lo, n = min(x, y) - 1, abs(x - y) + 1
+        else:                                                            # 'same': A's extent, centred like the reference
+            lo, n = (y - 1) // 2, x
+        sl.append(slice(lo, lo + n))
+    return out[tuple(sl)]

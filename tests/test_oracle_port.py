@@ -65,3 +65,30 @@ def test_device_matches_port(cuda_dev):
     x = onp.linspace(-7.0, 7.0, 1 << 16)
     for k, d in enumerate(numpy_port.tanh_derivatives(x)):
         cases.assert_close(w.tanh_nth_derivative(k)(b200.asarray(x)).get(), d, 1e-11, f"device vs closed form, order {k}")
+
+
+def test_port_weighted_logsumexp_matches_golden():
+    import numpy_port
+
+    gold = onp.load(os.path.join(GOLD, "a13_logsumexp_weighted.npz"))
+    x, b = gold["lse_x"], gold["lse_b"]
+    for axis in (None, 0, 1):
+        tag = "all" if axis is None else str(axis)
+        val, grad = numpy_port.logsumexp_weighted_and_grad(x, b, axis)
+        cases.assert_close(onp.asarray(val), gold[f"lse_val_{tag}"], 1e-12, f"port weighted logsumexp {tag}")
+        cases.assert_close(grad, gold[f"lse_grad_{tag}"], 1e-11, f"port weighted logsumexp gradient {tag}")
+
+
+def test_port_direct_convolution_matches_golden():
+    """The explicit-sum convolution of the port reproduces the reference's strided-view einsum on every axis layout and
+    mode of the a14 fixture — two independent formulations of scipy/signal.py:10-76 agreeing pins both."""
+    import numpy_port
+
+    from test_golden import A14_CONFIGS
+
+    gold = onp.load(os.path.join(GOLD, "a14_convolve_general.npz"))
+    for name, (axes, dot_axes) in A14_CONFIGS.items():
+        A, B = gold[f"{name}_A"], gold[f"{name}_B"]
+        for mode in ("valid", "full", "same"):
+            got = numpy_port.convolve_direct(A, B, axes=axes, dot_axes=dot_axes or ((), ()), mode=mode)
+            cases.assert_close(got, gold[f"{name}_{mode}_val"], 1e-12, f"port convolve {name} {mode}")
