@@ -107,7 +107,7 @@ class DeviceArray:
         if m.shifts is not None:
             # a rolled view is made contiguous by the generated identity kernel
             return lazy.materialize(lazy.Node("positive", (lazy.leaf(m),), (m.dtype,), m.shape, m.dtype))
-        out = Mat.empty(m.shape, m.dtype)
+        out = Mat.empty(m.shape, m.dtype, inexact=m.buf.inexact)
         backend.get().copy_strided(out.ptr, out.dtype, out.strides, m.ptr, m.dtype, m.strides, m.shape)
         return out
 
@@ -358,7 +358,7 @@ class DeviceArray:
 
     def copy(self, order="C"):
         m = self._mat()
-        out = Mat.empty(m.shape, m.dtype)
+        out = Mat.empty(m.shape, m.dtype, inexact=m.buf.inexact)
         if m.shifts is not None:
             return DeviceArray(lazy.leaf(self._cmat()))
         backend.get().copy_strided(out.ptr, out.dtype, out.strides, m.ptr, m.dtype, m.strides, m.shape)
@@ -419,6 +419,7 @@ class DeviceArray:
         if src.shifts is not None:
             src = DeviceArray(lazy.leaf(src))._cmat()
         backend.get().copy_strided(view.ptr, view.dtype, view.strides, src.ptr, src.dtype, src.strides, view.shape)
+        view.buf.inexact = view.buf.inexact or src.buf.inexact
 
     def _assign_at(self, info, value):
         """x[index arrays] = value (e.g. ``unsort[permutation] = range(n)`` in unpermuter, numpy_vjps.py:803-806)."""
@@ -435,6 +436,7 @@ class DeviceArray:
         ptrs = [a._cmat() for a in idx_arrays]
         backend.get().scatter_assign(m.ptr, vm.ptr, self.dtype, [p.ptr for p in ptrs], list(self.shape[:n_lead]),
                                      prod(idx_shape), prod(inner_shape))
+        m.buf.inexact = m.buf.inexact or vm.buf.inexact
 
     def _own_buffer(self):
         """Make sure this handle is backed by real memory that may be written in place."""
@@ -447,7 +449,7 @@ class DeviceArray:
         if shared or m.shifts is not None or any(st == 0 and s > 1 for s, st in zip(m.shape, m.strides)):
             c = self._cmat() if m.shifts is not None else None
             if c is None:
-                c = Mat.empty(m.shape, m.dtype)
+                c = Mat.empty(m.shape, m.dtype, inexact=m.buf.inexact)
                 backend.get().copy_strided(c.ptr, c.dtype, c.strides, m.ptr, m.dtype, m.strides, m.shape)
             new = lazy.leaf(c)
             new.nhandles += 1
@@ -487,6 +489,7 @@ class DeviceArray:
             if sm.shifts is not None:
                 sm = src._cmat()
             be.add_strided(view.ptr, view.dtype, view.strides, sm.ptr, sm.strides, view.shape)
+            view.buf.inexact = view.buf.inexact or sm.buf.inexact
             return
         idx_arrays, idx_shape, n_lead = info
         if not m.is_contiguous:
@@ -504,6 +507,7 @@ class DeviceArray:
         ptrs = [a._cmat() for a in idx_arrays]
         be.scatter_add(m.ptr, vm.ptr, self.dtype, [p.ptr for p in ptrs], list(self.shape[:n_lead]), prod(idx_shape),
                        prod(inner_shape))
+        m.buf.inexact = True      # atomic accumulation order is not NumPy's sequential order
 
 
 # =================================================================== construction
@@ -1356,7 +1360,7 @@ def concatenate(arrays, axis=0, out=None, dtype=None, casting="same_kind"):
                     all(r() is a._node for r, a in zip(hit[2], arrays) if r is not None):
                 return DeviceArray(node)
             del _CONCAT_MEMO[key]
-    out_m = Mat.empty(shape, out_dtype)
+    out_m = Mat.empty(shape, out_dtype, inexact=any(a._node.mat is not None and a._node.mat.buf.inexact for a in arrays))
     be = backend.get()
     live = [a for a in arrays if a.size]
     if 3 <= len(live) <= 16 and all(a.dtype == out_dtype and a._node.mat is not None and a._node.mat.is_contiguous
@@ -1536,7 +1540,7 @@ def _cumulate(a, op, axis, dtype):
     if a.size == 0:
         return a
     src = a._cmat()
-    out = Mat.empty(a.shape, dt)
+    out = Mat.empty(a.shape, dt, inexact=dt.kind == "f")      # scan order differs from NumPy's sequential loop
     backend.get().cumulate(out.ptr, src.ptr, dt, op, prod(a.shape[:axis]), a.shape[axis], prod(a.shape[axis + 1:]))
     return DeviceArray(lazy.leaf(out))
 
@@ -1956,7 +1960,7 @@ def getitem(a: DeviceArray, idx):
         # every axis is indexed: a pure element lookup, kept symbolic and fused into its consumers
         table = a._node if a._node.mat is m else lazy.leaf(m)
         return DeviceArray(lazy.make_gather(table, [i._node for i in idx_arrays]))
-    out = Mat.empty(tuple(idx_shape) + tuple(inner_shape), a.dtype)
+    out = Mat.empty(tuple(idx_shape) + tuple(inner_shape), a.dtype, inexact=m.buf.inexact)
     mats = [i._cmat() for i in idx_arrays]
     backend.get().gather(out.ptr, m.ptr, a.dtype, [p.ptr for p in mats], list(a.shape[:n_lead]), prod(idx_shape),
                          prod(inner_shape))
@@ -2041,7 +2045,8 @@ def reduce_(a, op, axis=None, keepdims=False, dtype=None):
             outer = prod(cur_shape[: run[0]])
             red = prod(cur_shape[run[0]: run[-1] + 1])
             inner = prod(cur_shape[run[-1] + 1:])
-            out = Mat.empty((outer, inner), work_dtype)
+            out = Mat.empty((outer, inner), work_dtype,
+                            inexact=work_dtype.kind == "f" and (kern_op in ("sum", "prod") or cur.buf.inexact))
             be.reduce(out.ptr, cur.ptr, work_dtype, kern_op, outer, red, inner)
             cur = out
             for ax in run:
@@ -2183,7 +2188,7 @@ def logsumexp(a, axis=None, b=None, keepdims=False, return_sign=False):
         axes = tuple(range(len(keep), a.ndim))
     m = a._cmat()
     outer, red, inner = prod(shape[: axes[0]]), prod(shape[axes[0]: axes[-1] + 1]), prod(shape[axes[-1] + 1:])
-    out = Mat.empty((outer, inner), a.dtype)
+    out = Mat.empty((outer, inner), a.dtype, inexact=True)
     if red == 0:
         return full(final_shape, -np.inf, a.dtype)
     backend.get().logsumexp(out.ptr, m.ptr, a.dtype, outer, red, inner)
@@ -2218,7 +2223,7 @@ def _gemm2d(a: DeviceArray, b: DeviceArray, out_dtype=None) -> DeviceArray:
         raise ValueError(f"shapes {a.shape} and {b.shape} not aligned: {K} (dim 1) != {K2} (dim 0)")
     out_dtype = out_dtype or _float_result(a, b)
     am, bm = _as_gemm_operand(a), _as_gemm_operand(b)
-    out = Mat.empty((M, N), out_dtype)
+    out = Mat.empty((M, N), out_dtype, inexact=True)     # accumulation order differs from OpenBLAS'
     if M and N:
         backend.get().gemm(out.ptr, out_dtype, (N, 1, 0), am.ptr, am.dtype, (am.strides[0], am.strides[1], 0),
                            bm.ptr, bm.dtype, (bm.strides[0], bm.strides[1], 0), M, N, K, 1)
@@ -2291,7 +2296,7 @@ def matmul(a, b, out=None, **kw):
     ab = reshape(broadcast_to(a, batch_shape + (M, K)).copy() if a.shape[:-2] != batch_shape else a, (nb, M, K))
     bb = reshape(broadcast_to(b, batch_shape + (K, N)).copy() if b.shape[:-2] != batch_shape else b, (nb, K, N))
     am, bm = _as_gemm_operand(ab), _as_gemm_operand(bb)
-    out = Mat.empty((nb, M, N), out_dtype)
+    out = Mat.empty((nb, M, N), out_dtype, inexact=True)
     if nb and M and N:
         backend.get().gemm(out.ptr, out_dtype, (N, 1, M * N), am.ptr, am.dtype, (am.strides[1], am.strides[2], am.strides[0]),
                            bm.ptr, bm.dtype, (bm.strides[1], bm.strides[2], bm.strides[0]), M, N, K, nb)
@@ -2462,7 +2467,7 @@ def conv2d(x, w, mode="valid", flip=True):
         raise NotImplementedError(f"autograd_b200: convolve mode {mode!r} is not implemented on device")
     if Ho <= 0 or Wo <= 0:
         raise ValueError("One array must be larger than the other along all convolved dimensions")
-    out = Mat.empty((N, F, Ho, Wo), dt)
+    out = Mat.empty((N, F, Ho, Wo), dt, inexact=True)
     xm, wm = x._cmat(), w._cmat()  # keep the (possibly temporary) contiguous payloads alive across the launch
     backend.get().conv2d(out.ptr, xm.ptr, wm.ptr, dt, N, C, H, W, F, kh, kw, 0 if mode == "valid" else 1,
                          1 if flip else 0)
@@ -2482,7 +2487,7 @@ def conv2d_filter_grad(g, x, w_shape, mode="valid"):
     g, x, dt = _conv_operands(g, x)
     N, C, H, W = x.shape
     _, F, kh, kw = w_shape
-    out = Mat.empty((C, F, kh, kw), dt)
+    out = Mat.empty((C, F, kh, kw), dt, inexact=True)
     xm, gm = x._cmat(), g._cmat()
     backend.get().conv2d_wgrad(out.ptr, xm.ptr, gm.ptr, dt, N, C, H, W, F, kh, kw)
     return DeviceArray(lazy.leaf(out))

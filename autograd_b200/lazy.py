@@ -53,6 +53,9 @@ KEEP_COST = 96
 # Re-materialising nodes that keep being recomputed was measured on C4 (fluidsim): +1 % speed for +65 % retained
 # memory (the 200-step tape would no longer fit 180 GB), so it is off; the hook stays for experiments.
 REUSE_LIMIT = int(__import__("os").environ.get("B200AG_REUSE_LIMIT", str(1 << 30)))
+# B200AG_EXACT=1 keeps one IEEE rounding per recorded ufunc call in every generated kernel (no contraction anywhere);
+# by default only values that are still bit-reproducible against NumPy are computed that way (Buffer.inexact).
+RELAXED = __import__("os").environ.get("B200AG_EXACT", "0") in ("", "0")
 # Hard caps that force a flush while a graph is still being built.
 MAX_NODES = 1500
 MAX_LEAVES = 48
@@ -61,11 +64,17 @@ MAX_LEAVES = 48
 class Buffer:
     """Owner of one device allocation; freed back to the pool when unreferenced."""
 
-    __slots__ = ("ptr", "nbytes", "version", "__weakref__")
+    __slots__ = ("ptr", "nbytes", "version", "inexact", "__weakref__")
 
     def __init__(self, nbytes: int, upload: bool = False):
         self.nbytes = int(nbytes)
         self.version = 0          # bumped before every in-place write (DeviceArray._own_buffer): invalidates memoised copies
+        # True once the float payload can no longer be bit-identical to what NumPy computes from the same inputs: it is
+        # (or derives from) the result of a transcendental function, a float sum / contraction (reduction order), an
+        # atomic accumulation.  Generated kernels contract multiply-add pairs and share reciprocals freely on such
+        # values (they are held to north_star's 1e-12, not to bit-exactness) and keep one IEEE rounding per recorded
+        # ufunc call everywhere else (codegen.taint).
+        self.inexact = False
         be = backend.get()
         self.ptr = be.malloc_upload(self.nbytes) if upload else be.malloc(self.nbytes)
 
@@ -122,9 +131,11 @@ class Mat:
         return True
 
     @staticmethod
-    def empty(shape, dtype, upload=False):
+    def empty(shape, dtype, upload=False, inexact=False):
         shape = tuple(int(s) for s in shape)
-        return Mat(Buffer(prod(shape) * dtype.itemsize, upload), shape, c_strides(shape), 0, dtype)
+        buf = Buffer(prod(shape) * dtype.itemsize, upload)
+        buf.inexact = inexact
+        return Mat(buf, shape, c_strides(shape), 0, dtype)
 
 
 class Const:
@@ -305,10 +316,10 @@ class Program:
     """Structural description of one fused kernel; ``key`` identifies the generated code."""
 
     __slots__ = ("instrs", "leaves", "consts", "outputs", "ndim", "idx64", "vec", "key", "cost", "tables", "mode", "bx",
-                 "bdims", "share")
+                 "bdims", "share", "relax")
 
     def __init__(self, instrs, leaves, consts, outputs, ndim, idx64, vec, cost, tables=(), mode="flat", bx=256,
-                 bdims=None, share=None):
+                 bdims=None, share=None, relax=()):
         self.instrs = instrs      # tuple of (op, in_dtype chars, out dtype char, arg refs)
         self.leaves = leaves      # tuple of (dtype char, layout class 'C'|'S'|'G', has_shift)
         self.consts = consts      # tuple of C scalar kinds: 'd' | 'q' | '?'
@@ -326,7 +337,11 @@ class Program:
         # flat kernels: general-layout leaves with identical strides (the window slices of a pooled tensor) share one
         # element-offset computation; share[i] = index of the leaf whose offset leaf i reuses
         self.share = share
-        self.key = (instrs, leaves, consts, outputs, ndim, idx64, vec, tables, mode, bx, bdims, share)
+        # indices of the float add / subtract / divide instructions whose result is already inexact with respect to NumPy
+        # (downstream of a Buffer.inexact operand or of a transcendental function) and which the generated code may
+        # therefore contract into an FMA / compute with a shared reciprocal (codegen.relax_plan)
+        self.relax = relax
+        self.key = (instrs, leaves, consts, outputs, ndim, idx64, vec, tables, mode, bx, bdims, share, relax)
 
     def launch_config(self, sm_count):
         block = 256
@@ -445,7 +460,7 @@ def materialize(root: Node, store_root: bool = True) -> Mat:
                 nd_.uses += 1
 
     # ---- gather sources ("tables") are addressed by computed indices, not by the iteration index
-    table_index, table_descs, table_rt, elementwise_leaf = {}, [], [], set()
+    table_index, table_descs, table_rt, elementwise_leaf, table_taint = {}, [], [], set(), []
     for nd_ in order:
         for k, a in enumerate(nd_.args):
             if type(a) is Node and a.mat is not None:
@@ -454,11 +469,12 @@ def materialize(root: Node, store_root: bool = True) -> Mat:
                         table_index[a.nid] = len(table_descs)
                         table_descs.append((a.mat.dtype.char, len(a.mat.shape)))
                         table_rt.append((a.mat.ptr, a.mat.shape))
+                        table_taint.append(bool(a.mat.buf.inexact))
                 else:
                     elementwise_leaf.add(a.nid)
 
     # ---- leaves: classify layout relative to the iteration space
-    leaf_index, leaf_descs, leaf_ptrs, g_layouts, g_slots = {}, [], [], [], []
+    leaf_index, leaf_descs, leaf_ptrs, g_layouts, g_slots, leaf_taint = {}, [], [], [], [], []
     dedup = {}
     for ln in leaf_nodes:
         if ln.nid not in elementwise_leaf:
@@ -481,6 +497,7 @@ def materialize(root: Node, store_root: bool = True) -> Mat:
         leaf_index[ln.nid] = idx
         leaf_descs.append((m.dtype.char, cls, has_shift))
         leaf_ptrs.append([m.ptr, None, None])
+        leaf_taint.append(bool(m.buf.inexact) and m.dtype.kind == "f")
         if cls == "G":
             g_layouts.append((strides, shifts))
             g_slots.append(idx)
@@ -593,11 +610,17 @@ def materialize(root: Node, store_root: bool = True) -> Mat:
             rep[slot] = first.setdefault(tuple(st_), slot)
         if any(r != i for i, r in enumerate(rep)):
             share = tuple(rep)
-    program = Program(tuple(instrs), tuple(leaf_descs), tuple(const_kinds), outputs, ndim, idx64, vec, total_cost,
-                      tuple(table_descs), mode, bx, bdims, share)
+    from . import codegen
 
-    out_mats = [Mat.empty(root_shape, o.dtype) for o in outs]
+    instrs = tuple(instrs)
+    inexact = codegen.taint(instrs, leaf_taint, table_taint)
+    relax = codegen.relax_plan(instrs, inexact) if RELAXED else ()
+    program = Program(instrs, tuple(leaf_descs), tuple(const_kinds), outputs, ndim, idx64, vec, total_cost,
+                      tuple(table_descs), mode, bx, bdims, share, relax)
+    out_mats = [Mat.empty(root_shape, o.dtype, inexact=inexact[j] and o.dtype.kind == "f") for o, (j, _) in zip(outs, outputs)]
     backend.get().run_program(program, (leaf_ptrs, dims, table_rt), const_values, [m.ptr for m in out_mats], n)
+    if not store_root and root.op == "scatter":
+        root.args[0].mat.buf.inexact = True     # atomic accumulation order is not NumPy's sequential order
     for o, m in zip(outs, out_mats):
         o.mat = m
     if not store_root:

@@ -119,8 +119,6 @@ def test_host_logic_matches_golden_a13_a14(fake_dev):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="first GPU run (written after the round's GPU budget was spent; the same operations "
-                                        "pass on the GPU in cases.convolve_general / logsumexp_weighted) - remove after its XPASS")
 def test_device_matches_golden_a13_a14(cuda_dev):
     _run_a13_a14(cases.to_dev, cases.to_host)
 

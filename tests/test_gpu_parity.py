@@ -24,25 +24,12 @@ def test_binary_f64(name, cuda_dev):
     cases.case_binary(name)
 
 
-# Cases added after the round's GPU budget was spent: they only compose kernels that the cases above verify on the GPU
-# (a smoke run of the complex formulas on the B200 agreed with NumPy to 1.1e-15, scripts/gpu_complex_smoke.py), but the
-# full cases have so far run on the host emulation only.  Until they have passed once on a GPU they must not be able to
-# stop the suite (the driver runs it with -x): a pass shows up as XPASS, a failure as xfailed.  Remove a name from this set
-# once its XPASS has been seen.
-FIRST_GPU_RUN = {"complex_values", "complex", "linalg_composed"}
-
-
-def _params(names):
-    return [pytest.param(n, marks=pytest.mark.xfail(strict=False, reason="first GPU run of a composition-only case"))
-            if n in FIRST_GPU_RUN else n for n in sorted(names)]
-
-
-@pytest.mark.parametrize("name", _params(cases.OP_CASES))
+@pytest.mark.parametrize("name", sorted(cases.OP_CASES))
 def test_ops(name, cuda_dev):
     cases.OP_CASES[name]()
 
 
-@pytest.mark.parametrize("name", _params(cases.GRAD_CASES))
+@pytest.mark.parametrize("name", sorted(cases.GRAD_CASES))
 def test_grads(name, cuda_dev):
     cases.GRAD_CASES[name]()
 

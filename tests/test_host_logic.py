@@ -102,13 +102,59 @@ def test_c2_kernel_shares_reciprocals_and_prefetches(fake_dev):
     assert sum(1 for j, r in enumerate(rep) if r == j) < 0.6 * len(ops)          # > 40 % of the body is redundant
     shared = {d: c for d, c in den_uses.items() if c >= 2}
     assert 2 <= len(shared) <= 4 and sum(shared.values()) >= 18
-    src, name, _ = codegen.generate(prog)
-    body = src[src.index("__device__ __forceinline__ void body("):src.index('extern "C"')]
+    from autograd_b200 import lazy
+
+    def variant(relax):
+        q = lazy.Program(prog.instrs, prog.leaves, prog.consts, prog.outputs, prog.ndim, prog.idx64, prog.vec, prog.cost,
+                         prog.tables, prog.mode, prog.bx, prog.bdims, prog.share, relax)
+        src, _name, _ = codegen.generate(q)
+        return src, src[src.index("__device__ __forceinline__ void body("):src.index('extern "C"')]
+
+    # (a) the bit-exact form (B200AG_EXACT=1, and every value that is still bit-reproducible against NumPy)
+    src, body = variant(())
     assert body.count("b200_rcp(") == len(shared)
     assert body.count("b200_div(") == sum(shared.values())
+    assert "__fma_rn(" not in body.replace("b200_", "")
     assert "body_exact(" in body and "__noinline__ Outs body_exact" in src
     kern = src[src.index('extern "C"'):]
     assert "nx0 = *reinterpret_cast" in kern and "__launch_bounds__(256, 2)" in kern
+    # (b) what actually runs: everything downstream of exp() is inexact against NumPy anyway (CUDA libm vs glibc), so
+    # the recorded program carries a relax plan: multiply-add pairs become FMAs, every quotient is numerator x shared
+    # reciprocal, one range check per denominator, the exact twin still catches out-of-range denominators
+    inexact = codegen.taint(prog.instrs)
+    assert not inexact[0] and sum(inexact) > 0.95 * len(ops)            # 2*x is exact, exp(-2x) and all after it are not
+    assert prog.relax == codegen.relax_plan(prog.instrs, inexact) and len(prog.relax) > 60
+    src, body = variant(prog.relax)
+    assert body.count("__fma_rn(") >= 40 and "b200_div(" not in body
+    assert body.count("b200_rcp(") == body.count("b200_den_ok(") <= 6
+    assert "body_exact(" in body and "__noinline__ Outs body_exact" in src
+
+
+def test_exact_values_are_never_contracted(fake_dev):
+    """FMA contraction and reciprocal sharing are a property of each VALUE, not of the build: chains of + - * / on
+    data that is still bit-reproducible against NumPy (uploaded arrays, C4's whole forward pass) keep one IEEE
+    rounding per recorded ufunc call; the same chain downstream of a float sum (reduction order differs from NumPy's)
+    may be contracted."""
+    import autograd_b200 as b200
+    from autograd_b200 import codegen
+
+    r = onp.random.RandomState(0)
+    a, b, c = (b200.asarray(r.randn(4096)) for _ in range(3))
+    (a * b + c / a).get()
+    prog = max(fake_dev.programs.values(), key=lambda p: len(p.instrs))
+    assert prog.relax == ()
+    src, _n, _ = codegen.generate(prog)
+    assert "__fma_rn(" not in src[src.index("void body("):]
+    fake_dev.programs.clear()
+    s = onp.sum(a)                       # a float sum: inexact against NumPy's pairwise order
+    assert s._mat().buf.inexact
+    y = (a * s + c)
+    y.get()
+    prog = max(fake_dev.programs.values(), key=lambda p: len(p.instrs))
+    assert len(prog.relax) == 1
+    src, _n, _ = codegen.generate(prog)
+    assert "__fma_rn(" in src[src.index("void body("):]
+    assert y._mat().buf.inexact and not (a * b)._mat().buf.inexact
 
 
 def test_scatter_bodies_never_share_reciprocals(fake_dev):
