@@ -67,6 +67,8 @@ PROTOTYPES = {
                     c_i64, c_i64, c_i64, c_i64],
     "b200ag_gemm_f32_tc": [C.c_void_p, c_i64, C.c_void_p, c_i64, c_i64, C.c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64],
     "b200ag_gemm_f32_mode": [C.c_int, C.POINTER(C.c_int)],
+    "b200ag_index_flag": [c_void_pp],
+    "b200ag_index_error": [C.POINTER(C.c_int)],
     "b200ag_gather": [C.c_void_p, C.c_void_p, C.c_int, c_void_pp, C.c_int, c_i64_p, c_i64, c_i64],
     "b200ag_scatter_add": [C.c_void_p, C.c_void_p, C.c_int, c_void_pp, C.c_int, c_i64_p, c_i64, c_i64],
     "b200ag_scatter_assign": [C.c_void_p, C.c_void_p, C.c_int, c_void_pp, C.c_int, c_i64_p, c_i64, c_i64],

@@ -348,7 +348,11 @@ class DeviceArray:
     def astype(self, dtype, order="K", casting="unsafe", subok=True, copy=True):
         dtype = np.dtype(dtype)
         if dtype == self.dtype:
-            return self
+            if not copy:
+                return self
+            # NumPy returns an independent copy: share the payload, copy it when either handle is written in place
+            _MEMO_NODES.add(self._node)
+            return DeviceArray(self._node)
         if dtype not in lazy.SUPPORTED:
             backend.dtype_code(dtype)
         return DeviceArray(lazy.make_cast(self._node, dtype))
@@ -418,6 +422,11 @@ class DeviceArray:
         src = broadcast_to(value, view.shape)._mat()
         if src.shifts is not None:
             src = DeviceArray(lazy.leaf(src))._cmat()
+        elif src.buf is view.buf and prod(view.shape) > 0:
+            # `x[1:] = x[:-1]`: source and destination may overlap inside one buffer; NumPy copies through a temporary
+            tmp = Mat.empty(src.shape, src.dtype, inexact=src.buf.inexact)
+            backend.get().copy_strided(tmp.ptr, tmp.dtype, tmp.strides, src.ptr, src.dtype, src.strides, src.shape)
+            src = tmp
         backend.get().copy_strided(view.ptr, view.dtype, view.strides, src.ptr, src.dtype, src.strides, view.shape)
         view.buf.inexact = view.buf.inexact or src.buf.inexact
 
@@ -444,6 +453,7 @@ class DeviceArray:
         if node.mat is None:
             lazy.materialize(node)
         m = node.mat
+        lazy.flush_readers(m.buf)     # pending expressions that read this buffer must see the OLD contents
         m.buf.version += 1            # an in-place write follows: memoised copies of the old contents are stale
         shared = node.nhandles > 1 and node in _MEMO_NODES   # NumPy would have made independent copies: copy on write
         if shared or m.shifts is not None or any(st == 0 and s > 1 for s, st in zip(m.shape, m.strides)):
@@ -1844,11 +1854,20 @@ def _parse_index(shape, idx):
     if len(arrays) > len(shape):
         raise IndexError("too many indices for array")
     dev = []
-    for a in arrays:
+    for k, a in enumerate(arrays):
         if not isinstance(a, DeviceArray):
             a = np.asarray(a)
             if a.dtype == np.bool_:
                 raise NotImplementedError("autograd_b200: boolean mask indexing is not implemented on device")
+            if a.dtype.kind not in "iu":
+                raise IndexError("arrays used as indices must be of integer (or boolean) type")
+            if a.size:
+                # host index arrays are validated here like NumPy does; device index arrays are checked by the kernels
+                # themselves (out-of-range entries are skipped and reported at the next synchronisation)
+                lo, hi, n = int(a.min()), int(a.max()), shape[k]
+                if lo < -n or hi >= n:
+                    bad = hi if hi >= n else lo
+                    raise IndexError(f"index {bad} is out of bounds for axis {k} with size {n}")
             a = _upload(a.astype(np.int64))
         elif a.dtype == BOOL:
             raise NotImplementedError("autograd_b200: boolean mask indexing is not implemented on device")

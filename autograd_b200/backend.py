@@ -59,6 +59,9 @@ class CudaBackend:
         self._check(self._lib.b200ag_device_info(C.byref(sms), C.byref(major), C.byref(minor), C.byref(mem)))
         self.sm_count = sms.value
         self.total_mem = mem.value
+        flag = C.c_void_p()
+        self._check(self._lib.b200ag_index_flag(C.byref(flag)))
+        self._index_flag = flag.value
 
     # ------------------------------------------------------------ memory
     def malloc(self, nbytes: int) -> int:
@@ -81,6 +84,17 @@ class CudaBackend:
     def d2h(self, host: np.ndarray, ptr: int) -> None:
         assert host.flags.c_contiguous
         self._check(self._lib.b200ag_memcpy_d2h(host.ctypes.data, ptr, host.nbytes))
+        self._check_index_error()
+
+    def _check_index_error(self) -> None:
+        """Device index arrays are bounds-checked by the kernels that use them; what NumPy raises at the indexing
+        call surfaces here, at the first synchronisation after it."""
+        raised = C.c_int(0)
+        self._lib.b200ag_index_error(C.byref(raised))
+        if raised.value:
+            raise IndexError("autograd_b200: an index array on the device held an index that is out of bounds for the "
+                             "indexed axis (detected by a gather / np.add.at / item-assignment kernel since the last "
+                             "synchronisation; the offending accesses were skipped)")
 
     def d2d(self, dst: int, src: int, nbytes: int) -> None:
         self._check(self._lib.b200ag_memcpy_d2d(dst, src, nbytes))
@@ -107,6 +121,7 @@ class CudaBackend:
     # ------------------------------------------------------------ runtime
     def synchronize(self) -> None:
         self._check(self._lib.b200ag_synchronize())
+        self._check_index_error()
 
     def launch_count(self) -> int:
         n = C.c_uint64()
@@ -236,7 +251,8 @@ class CudaBackend:
         handle, _image, packer, (block, _elems_per_block, _max_grid) = rec
         if n == 0:
             return
-        params = packer(n, leaf_ptrs, const_values, out_ptrs, program)
+        params = packer(n, tuple(leaf_ptrs) + (self._index_flag,) if program.tables else leaf_ptrs, const_values, out_ptrs,
+                        program)
         grid = program.grid(n, leaf_ptrs[1], self.sm_count)
         if self.profile is None:
             self._check(self._lib.b200ag_kernel_launch(handle, grid, block, 0, params, len(params)))

@@ -14,6 +14,7 @@ cudaStream_t stream();
 int sm_count();
 void count_launch(uint64_t n = 1);
 bool ensure_init();
+int* index_flag();   // device address of the "index out of bounds" flag (mapped host memory), NULL on failure
 bool f32_tc_eligible(int64_t M, int64_t N, int64_t K, int64_t c_cs, int64_t batch);   // gemm_tc.cu
 
 #define B200AG_CHECK_INIT()                      \

@@ -33,6 +33,31 @@ bool ensure_init() {
   return b200ag_init(0) == 0;
 }
 
+// "index out of bounds" flag: one int in mapped pinned host memory.  Gather / scatter kernels (static and generated)
+// set it instead of touching memory outside the array; the host reads it after a synchronisation without any copy.
+static volatile int* g_index_flag_host = nullptr;
+static int* g_index_flag_dev = nullptr;
+int* index_flag() {
+  if (g_index_flag_dev) return g_index_flag_dev;
+  if (!ensure_init()) return nullptr;
+  int* h = nullptr;
+  if (cudaHostAlloc((void**)&h, sizeof(int), cudaHostAllocMapped) != cudaSuccess) {
+    set_error("index flag: cudaHostAlloc failed");
+    cudaGetLastError();
+    return nullptr;
+  }
+  *h = 0;
+  int* dptr = nullptr;
+  if (cudaHostGetDevicePointer((void**)&dptr, h, 0) != cudaSuccess) {
+    set_error("index flag: cudaHostGetDevicePointer failed");
+    cudaGetLastError();
+    return nullptr;
+  }
+  g_index_flag_host = h;
+  g_index_flag_dev = dptr;
+  return dptr;
+}
+
 // ---------------------------------------------------------------- allocator
 // Size-binned caching allocator.  All work runs on one stream, so a block
 // handed back by free() can be reused by the next malloc() at once: any kernel
@@ -92,6 +117,7 @@ int b200ag_init(int device) {
   B200AG_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
   B200AG_CUDA(cudaStreamCreateWithFlags(&g_side_stream, cudaStreamNonBlocking));
   g_device = device;
+  if (!index_flag()) return 1;   // allocated up front: never inside a stream capture
   return 0;
 }
 
@@ -131,6 +157,21 @@ int b200ag_synchronize(void) {
   B200AG_CHECK_INIT();
   if (g_capturing) B200AG_FAIL("synchronize() while a CUDA graph is being captured");
   B200AG_CUDA(cudaStreamSynchronize(g_stream));
+  return 0;
+}
+
+int b200ag_index_flag(void** dev_ptr) {
+  B200AG_CHECK_INIT();
+  *dev_ptr = (void*)index_flag();
+  return *dev_ptr ? 0 : 1;
+}
+
+int b200ag_index_error(int* raised) {
+  *raised = 0;
+  if (g_index_flag_host && *g_index_flag_host) {
+    *raised = 1;
+    *g_index_flag_host = 0;
+  }
   return 0;
 }
 

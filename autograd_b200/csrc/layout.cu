@@ -152,14 +152,21 @@ struct IndexDesc {
   int nidx;
   const int64_t* idx[B200AG_MAX_DIMS];
   int64_t dims[B200AG_MAX_DIMS];
+  int* err;   // library-wide "index out of bounds" flag (mapped host memory, read at the next synchronisation)
 };
 
+// Row addressed by the i-th index tuple, or -1 when an entry is outside [-dim, dim): NumPy raises IndexError there;
+// the kernels skip the access (never touch memory outside the array) and raise the flag the host reads back.
 __device__ __forceinline__ int64_t linear_row(const IndexDesc& d, int64_t i) {
   int64_t row = 0;
 #pragma unroll 1
   for (int k = 0; k < d.nidx; ++k) {
     int64_t v = d.idx[k][i];
     if (v < 0) v += d.dims[k];  // NumPy negative-index wrap
+    if ((uint64_t)v >= (uint64_t)d.dims[k]) {
+      *d.err = 1;
+      return -1;
+    }
     row = row * d.dims[k] + v;
   }
   return row;
@@ -171,12 +178,15 @@ __global__ void __launch_bounds__(256) gather_kernel(T* __restrict__ dst, const 
   int64_t n = n_index * inner;
   int64_t step = (int64_t)gridDim.x * blockDim.x;
   if (inner == 1) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step)
-      dst[i] = src[linear_row(d, i)];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+      const int64_t row = linear_row(d, i);
+      dst[i] = row < 0 ? T(0) : src[row];
+    }
   } else {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
       int64_t r = i / inner, c = i - r * inner;
-      dst[i] = src[linear_row(d, r) * inner + c];
+      const int64_t row = linear_row(d, r);
+      dst[i] = row < 0 ? T(0) : src[row * inner + c];
     }
   }
 }
@@ -196,12 +206,15 @@ __global__ void __launch_bounds__(256) scatter_add_kernel(T* __restrict__ dst, c
   int64_t n = n_index * inner;
   int64_t step = (int64_t)gridDim.x * blockDim.x;
   if (inner == 1) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step)
-      atomic_add_t(dst + linear_row(d, i), src[i]);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+      const int64_t row = linear_row(d, i);
+      if (row >= 0) atomic_add_t(dst + row, src[i]);
+    }
   } else {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
       int64_t r = i / inner, c = i - r * inner;
-      atomic_add_t(dst + linear_row(d, r) * inner + c, src[i]);
+      const int64_t row = linear_row(d, r);
+      if (row >= 0) atomic_add_t(dst + row * inner + c, src[i]);
     }
   }
 }
@@ -230,15 +243,27 @@ __global__ void __launch_bounds__(256) concat_kernel(T* __restrict__ dst, Concat
 }
 
 // x[idx] = values (integer-array item assignment, e.g. unpermuter in numpy_vjps.py:803-806).  With duplicate indices
-// NumPy keeps the last value; here the winner among duplicates is unspecified.
+// NumPy's sequential loop leaves the LAST value in place; two passes reproduce that deterministically: pass 1 records,
+// per destination row, the largest position in the index list that addresses it (atomicMax), pass 2 lets exactly that
+// position write.
+__global__ void __launch_bounds__(256) scatter_winner_kernel(long long* __restrict__ winner, IndexDesc d, int64_t n_index) {
+  int64_t step = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_index; i += step) {
+    const int64_t row = linear_row(d, i);
+    if (row >= 0) atomicMax(winner + row, (long long)i);
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) scatter_assign_kernel(T* __restrict__ dst, const T* __restrict__ src,
-                                                              IndexDesc d, int64_t n_index, int64_t inner) {
+                                                              const long long* __restrict__ winner, IndexDesc d,
+                                                              int64_t n_index, int64_t inner) {
   int64_t n = n_index * inner;
   int64_t step = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
     int64_t r = i / inner, c = i - r * inner;
-    dst[linear_row(d, r) * inner + c] = src[i];
+    const int64_t row = linear_row(d, r);
+    if (row >= 0 && winner[row] == (long long)r) dst[row * inner + c] = src[i];
   }
 }
 
@@ -302,6 +327,8 @@ static int fill_index_desc(IndexDesc& d, const int64_t* const* idx, int nidx, co
     d.idx[k] = idx[k];
     d.dims[k] = dims[k];
   }
+  d.err = index_flag();
+  if (!d.err) return 1;
   return 0;
 }
 
@@ -349,13 +376,22 @@ int b200ag_scatter_assign(void* dst, const void* src, int dtype, const int64_t* 
   if (fill_index_desc(d, idx, nidx, dst_dims)) return 1;
   int64_t n = n_index * inner;
   if (n == 0) return 0;
+  int64_t rows = 1;
+  for (int k = 0; k < nidx; ++k) rows *= dst_dims[k];
+  void* winner = nullptr;
+  if (b200ag_malloc((size_t)rows * sizeof(long long), &winner)) return 1;
+  if (b200ag_memset(winner, 0xFF, (size_t)rows * sizeof(long long))) return 1;   // every row: no writer (-1)
+  scatter_winner_kernel<<<grid_for(n_index, 256, 16), 256, 0, stream()>>>((long long*)winner, d, n_index);
+  B200AG_LAUNCH_CHECK();
   unsigned grid = grid_for(n, 256, 16);
+  const long long* w = (const long long*)winner;
   switch (dtype_size(dtype)) {
-    case 8: scatter_assign_kernel<int64_t><<<grid, 256, 0, stream()>>>((int64_t*)dst, (const int64_t*)src, d, n_index, inner); break;
-    case 4: scatter_assign_kernel<int32_t><<<grid, 256, 0, stream()>>>((int32_t*)dst, (const int32_t*)src, d, n_index, inner); break;
-    case 1: scatter_assign_kernel<uint8_t><<<grid, 256, 0, stream()>>>((uint8_t*)dst, (const uint8_t*)src, d, n_index, inner); break;
-    default: B200AG_FAIL("scatter_assign: unsupported dtype");
+    case 8: scatter_assign_kernel<int64_t><<<grid, 256, 0, stream()>>>((int64_t*)dst, (const int64_t*)src, w, d, n_index, inner); break;
+    case 4: scatter_assign_kernel<int32_t><<<grid, 256, 0, stream()>>>((int32_t*)dst, (const int32_t*)src, w, d, n_index, inner); break;
+    case 1: scatter_assign_kernel<uint8_t><<<grid, 256, 0, stream()>>>((uint8_t*)dst, (const uint8_t*)src, w, d, n_index, inner); break;
+    default: b200ag_free(winner); B200AG_FAIL("scatter_assign: unsupported dtype");
   }
+  b200ag_free(winner);   // stream-ordered allocator: the block is reused only by work enqueued after these kernels
   B200AG_LAUNCH_CHECK();
   return 0;
 }

@@ -92,8 +92,9 @@ def allreduce_sum_(x: DeviceArray) -> DeviceArray:
     import torch
 
     x._own_buffer()
+    x._mat().buf.inexact = True        # a float sum over ranks
     be = backend.get()
-    if _peer["ready"] and x.dtype == lazy.F64 and x.nbytes <= _peer["slot_bytes"]:
+    if _peer["ready"] and x.dtype == lazy.F64 and (x.size + 1) * 8 <= _peer["slot_bytes"]:
         m = x._mat()
         if m.is_contiguous:
             be.comm_allreduce_sum_f64(m.ptr, m.ptr, x.size)

@@ -62,11 +62,14 @@ def _out_leaves(tree, acc):
 
 
 class _Recording:
-    __slots__ = ("graph", "static_inputs", "outputs", "nodes", "seen", "__weakref__")
+    __slots__ = ("graph", "static_inputs", "outputs", "nodes", "seen", "out_bufs", "__weakref__")
 
     def __init__(self, graph, static_inputs, outputs, nodes):
         self.graph, self.static_inputs, self.outputs, self.nodes = graph, static_inputs, outputs, nodes
         self.seen = [None] * len(static_inputs)   # per input: what was copied in last (buffer identity + version)
+        acc = []
+        _out_leaves(outputs, acc)
+        self.out_bufs = [a._node.mat.buf for a in acc if a._node.mat is not None]   # rewritten by every replay
 
     def __del__(self):
         try:
@@ -83,19 +86,29 @@ class CapturedFunction:
         self.fn = fn
         self.copy_inputs = copy_inputs   # False: bake the caller's own input buffers into the graph (pipelines)
         self._recordings = {}
+        self.max_recordings = 16
 
     def __call__(self, *args):
         be = backend.get()
         leaves, spec = [], []
         _flatten(args, leaves, spec)
         key = tuple(spec)
-        rec = self._recordings.get(key)
+        rec = self._recordings.pop(key, None)
         if rec is None:
             rec = self._record(be, args, leaves)
-            self._recordings[key] = rec
+            # least-recently-used bound: Python scalars are constants of a recording and part of its key, so a call
+            # site that varies one (a step counter) would otherwise keep every graph and its arena alive for ever
+            while len(self._recordings) >= self.max_recordings:
+                self._recordings.pop(next(iter(self._recordings)))
         else:
             for i, (dst, src) in enumerate(zip(rec.static_inputs, leaves)):
                 self._refresh(be, dst, src, rec.seen, i)
+        self._recordings[key] = rec      # most recently used last
+        # The replay rewrites the recording's output buffers in place: expressions still pending on the previous
+        # results are computed first, and memoised copies (array._CONCAT_MEMO keys on buffer versions) become stale.
+        for buf in rec.out_bufs:
+            lazy.flush_readers(buf)
+            buf.version += 1
         be.graph_launch(rec.graph)
         return rec.outputs
 
@@ -110,9 +123,13 @@ class CapturedFunction:
                 tag = seen[i]
                 if tag is not None and tag[0]() is sm.buf and tag[1] == sm.buf.version and tag[2] == sm.offset:
                     return
+                lazy.flush_readers(dm.buf)
+                dm.buf.version += 1
                 be.d2d(dm.ptr, sm.ptr, src.nbytes)
                 seen[i] = (weakref.ref(sm.buf), sm.buf.version, sm.offset)
         else:
+            lazy.flush_readers(dm.buf)
+            dm.buf.version += 1
             be.h2d(dm.ptr, np.asarray(src, dtype=dm.dtype, order="C"))
 
     def _record(self, be, args, leaves):

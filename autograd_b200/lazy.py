@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import itertools
 import math
+import weakref
 
 import numpy as np
 
@@ -64,7 +65,7 @@ MAX_LEAVES = 48
 class Buffer:
     """Owner of one device allocation; freed back to the pool when unreferenced."""
 
-    __slots__ = ("ptr", "nbytes", "version", "inexact", "__weakref__")
+    __slots__ = ("ptr", "nbytes", "version", "inexact", "readers", "__weakref__")
 
     def __init__(self, nbytes: int, upload: bool = False):
         self.nbytes = int(nbytes)
@@ -75,6 +76,9 @@ class Buffer:
         # values (they are held to north_star's 1e-12, not to bit-exactness) and keep one IEEE rounding per recorded
         # ufunc call everywhere else (codegen.taint).
         self.inexact = False
+        # pending (not yet computed) expression nodes that read this buffer directly; an in-place write materialises them
+        # first so that `y = x * 2; x[0] = 100` leaves y computed from the old x, as NumPy's eager evaluation does
+        self.readers = None
         be = backend.get()
         self.ptr = be.malloc_upload(self.nbytes) if upload else be.malloc(self.nbytes)
 
@@ -85,6 +89,17 @@ class Buffer:
                 backend.get().free(ptr)
             except Exception:
                 pass
+
+
+def flush_readers(buf) -> None:
+    """Compute every pending expression that reads ``buf`` (called before an in-place write to it)."""
+    readers = buf.readers
+    if not readers:
+        return
+    buf.readers = None
+    for node in list(readers):
+        if node.mat is None and node.args:
+            materialize(node)
 
 
 def c_strides(shape):
@@ -176,6 +191,10 @@ class Node:
                         leafset = leafset | a.leafset if leafset else a.leafset
                     else:
                         leafset = leafset | a.leafset
+                        buf = a.mat.buf
+                        if buf.readers is None:
+                            buf.readers = weakref.WeakSet()
+                        buf.readers.add(self)
             self.lo = lo
             self.cost = cost if cost < 1 << 30 else 1 << 30
             self.leafset = leafset

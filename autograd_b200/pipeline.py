@@ -55,6 +55,7 @@ def map_elementwise(fn, x_host: np.ndarray, out: np.ndarray | None = None, chunk
             m = hi - lo
             if i >= 2:
                 be.stream_wait_event(up, ev_free[s])            # slot's previous contents have been consumed
+            in_bufs[s].buf.version += 1                         # rewritten in place: memoised copies are stale
             be.h2d_on(in_bufs[s].ptr, x_flat[lo:hi], up)
             be.event_record_on(ev_in[s], up)
             be.stream_wait_event(None, ev_in[s])

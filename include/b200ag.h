@@ -160,6 +160,13 @@ int b200ag_gemm_f32_mode(int mode, int* previous);
  * np.add.at(A, idx, g) with duplicate indices accumulated (numpy_vjps.py:941-950).
  * Negative indices wrap like NumPy.  inner = product of the trailing,
  * un-indexed dimensions (contiguous). */
+/* Index entries outside [-dim, dim) (NumPy: IndexError, raised by the index machinery
+ * under numpy_boxes.py:16-18 / np.add.at, numpy_vjps.py:947) are never dereferenced:
+ * gather yields 0 for them, scatter skips them, and a library-wide flag in mapped host
+ * memory is raised.  b200ag_index_error reports and clears it (call after a
+ * synchronisation); b200ag_index_flag gives generated kernels the flag's device address. */
+int b200ag_index_flag(void** device_ptr);
+int b200ag_index_error(int* raised);
 int b200ag_gather(void* dst, const void* src, int dtype,
                   const int64_t* const* idx, int nidx, const int64_t* src_dims,
                   int64_t n_index, int64_t inner);
@@ -168,8 +175,9 @@ int b200ag_scatter_add(void* dst, const void* src, int dtype,
                        int64_t n_index, int64_t inner);
 /* x[idx] = values for integer index arrays (item assignment on a raw array, e.g.
  * `unsort[permutation] = range(n)` in unpermuter, numpy_vjps.py:803-806).  Same
- * index convention as b200ag_scatter_add; the winner among duplicate indices is
- * unspecified (NumPy: the last one). */
+ * index convention as b200ag_scatter_add; among duplicate indices the LAST one in
+ * the index list wins, as in NumPy's sequential assignment (two passes: atomicMax
+ * of the writer position per row, then only that writer stores). */
 int b200ag_scatter_assign(void* dst, const void* src, int dtype,
                           const int64_t* const* idx, int nidx, const int64_t* dst_dims,
                           int64_t n_index, int64_t inner);

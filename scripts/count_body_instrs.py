@@ -44,7 +44,7 @@ def per_point_counts(src: str, workdir: str = "/tmp/count_body"):
     p, n = C.c_void_p(), C.c_size_t()
     rc = _lib.lib.b200ag_rtc_compile(full.encode(), b"one.cu", C.byref(p), C.byref(n))
     if rc:
-        raise RuntimeError(_lib.lib.b200ag_last_error().decode())
+        raise RuntimeError("\n".join(l for l in _lib.lib.b200ag_last_error().decode().splitlines() if "error" in l))
     path = os.path.join(workdir, "one.cubin")
     with open(path, "wb") as f:
         f.write(C.string_at(p.value, n.value))

@@ -1618,3 +1618,68 @@ def grad_case_linalg_composed():
 
 
 GRAD_CASES["linalg_composed"] = grad_case_linalg_composed
+
+
+def case_inplace_write_semantics():
+    """NumPy evaluates eagerly, so a later in-place write never changes an earlier result; the device records ufunc
+    calls lazily and must give the same values: pending readers of a buffer are computed before it is written, a copy
+    made by astype() is independent, and overlapping source / destination slices go through a temporary."""
+    import pytest
+
+    def script(xp, asarr):
+        out = []
+        x = asarr(onp.arange(8.0))
+        y = x * 2.0                      # pending when x is written
+        z = xp.exp(x)
+        x[0] = 100.0
+        x[1:3] = 1.0
+        out += [y, z, x * 1.0]
+        t = asarr(onp.arange(12.0).reshape(3, 4))
+        g = t[asarr(onp.array([2, 0, 1])), asarr(onp.array([1, 3, 0]))]   # lazy gather holds its table
+        onp.add.at(t, (slice(None), slice(0, 2)), 10.0)
+        out += [g * 1.0]
+        a = asarr(onp.arange(10.0))
+        c = a.astype(onp.float64)        # NumPy: a copy
+        c[0] = 9.0
+        out += [a * 1.0, c * 1.0]
+        s = asarr(onp.arange(10.0))
+        s[1:] = s[:-1]                   # overlapping, same buffer
+        out += [s * 1.0]
+        s2 = asarr(onp.arange(10.0))
+        s2[:-1] = s2[1:]
+        out += [s2 * 1.0]
+        return out
+
+    want = script(onp, lambda h: h.copy())
+    got = script(onp, lambda h: b200.asarray(h))
+    for i, (g, w) in enumerate(zip(got, want)):
+        assert_close(to_host(g), w, 0, f"in-place semantics #{i}")
+    with pytest.raises(IndexError):
+        b200.asarray(onp.arange(6.0).reshape(2, 3))[[7], [0]]
+    with pytest.raises(IndexError):
+        onp.add.at(b200.asarray(onp.zeros(4)), onp.array([0, -5]), 1.0)
+    with pytest.raises(IndexError):
+        b200.asarray(onp.zeros(4))[onp.array([1, 4])] = 1.0
+
+
+def case_item_assignment_duplicates_last_write_wins():
+    """x[idx] = v with duplicate indices: NumPy's sequential assignment leaves the LAST value (bit-exact index work)."""
+    r = rs(11)
+    idx = r.randint(0, 50, 4000)
+    vals = r.randn(4000)
+    want = onp.zeros(50)
+    want[idx] = vals
+    x = b200.asarray(onp.zeros(50))
+    x[b200.asarray(idx)] = b200.asarray(vals)
+    assert_close(x.get(), want, 0, "duplicate item assignment")
+    rows = r.randint(0, 7, 300)
+    v2 = r.randn(300, 5)
+    want2 = onp.full((7, 5), -1.0)
+    want2[rows] = v2
+    x2 = b200.asarray(onp.full((7, 5), -1.0))
+    x2[b200.asarray(rows)] = b200.asarray(v2)
+    assert_close(x2.get(), want2, 0, "duplicate row assignment")
+
+
+OP_CASES["inplace_write_semantics"] = case_inplace_write_semantics
+OP_CASES["item_assignment_duplicates_last_write_wins"] = case_item_assignment_duplicates_last_write_wins
