@@ -65,6 +65,7 @@ PROTOTYPES = {
                     C.c_void_p, C.c_int, c_i64, c_i64, c_i64,
                     C.c_void_p, C.c_int, c_i64, c_i64, c_i64,
                     c_i64, c_i64, c_i64, c_i64],
+    "b200ag_gemm_grouped": [C.c_void_p, C.c_int],
     "b200ag_gemm_f32_tc": [C.c_void_p, c_i64, C.c_void_p, c_i64, c_i64, C.c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64],
     "b200ag_gemm_f32_mode": [C.c_int, C.POINTER(C.c_int)],
     "b200ag_index_flag": [c_void_pp],
@@ -93,6 +94,15 @@ PROTOTYPES = {
     "b200ag_graph_num_nodes": [C.c_void_p, c_size_p],
 }
 _RESTYPE = {"b200ag_last_error": C.c_char_p}
+
+
+class GemmProblem(C.Structure):
+    """b200ag_gemm_problem (include/b200ag.h)."""
+
+    _fields_ = [("C", C.c_void_p), ("A", C.c_void_p), ("B", C.c_void_p),
+                ("c_dtype", C.c_int), ("a_dtype", C.c_int), ("b_dtype", C.c_int), ("reserved", C.c_int),
+                ("c_rs", c_i64), ("c_cs", c_i64), ("a_rs", c_i64), ("a_cs", c_i64), ("b_rs", c_i64), ("b_cs", c_i64),
+                ("M", c_i64), ("N", c_i64), ("K", c_i64)]
 
 
 def _load():

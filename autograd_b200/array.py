@@ -113,7 +113,8 @@ class DeviceArray:
 
     def materialize(self):
         """Force evaluation of pending lazy work behind this array (no host sync)."""
-        self._mat()
+        if self._mat().buf.pending:
+            lazy.flush_gemms()
         return self
 
     def get(self, out=None) -> np.ndarray:
@@ -2244,8 +2245,7 @@ def _gemm2d(a: DeviceArray, b: DeviceArray, out_dtype=None) -> DeviceArray:
     am, bm = _as_gemm_operand(a), _as_gemm_operand(b)
     out = Mat.empty((M, N), out_dtype, inexact=True)     # accumulation order differs from OpenBLAS'
     if M and N:
-        backend.get().gemm(out.ptr, out_dtype, (N, 1, 0), am.ptr, am.dtype, (am.strides[0], am.strides[1], 0),
-                           bm.ptr, bm.dtype, (bm.strides[0], bm.strides[1], 0), M, N, K, 1)
+        lazy.defer_gemm(out, am, bm, M, N, K)             # launched, grouped with its neighbours, when first needed
     return DeviceArray(lazy.leaf(out))
 
 

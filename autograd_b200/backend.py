@@ -120,6 +120,9 @@ class CudaBackend:
 
     # ------------------------------------------------------------ runtime
     def synchronize(self) -> None:
+        from . import lazy
+
+        lazy.flush_gemms()       # queued contractions are work the caller expects to be done after a synchronisation
         self._check(self._lib.b200ag_synchronize())
         self._check_index_error()
 
@@ -201,10 +204,16 @@ class CudaBackend:
 
     # ------------------------------------------------------------ CUDA graphs
     def graph_begin(self) -> None:
+        from . import lazy
+
+        lazy.flush_gemms()       # work queued before the capture must not be recorded into it
         self._check(self._lib.b200ag_graph_begin())
         self.capturing = True
 
     def graph_end(self) -> int:
+        from . import lazy
+
+        lazy.flush_gemms()       # everything recorded so far belongs to this graph
         p = C.c_void_p()
         self.capturing = False
         self._check(self._lib.b200ag_graph_end(C.byref(p)))
@@ -294,6 +303,22 @@ class CudaBackend:
         self._check(self._lib.b200ag_gemm(
             c, dtype_code(c_dt), *c_str, a, dtype_code(a_dt), *a_str, b, dtype_code(b_dt), *b_str, M, N, K, batch))
 
+    def gemm_grouped(self, problems) -> None:
+        """Independent products in one launch per operand class; ``problems`` = sequence of
+        (c, c_dt, (c_rs, c_cs), a, a_dt, (a_rs, a_cs), b, b_dt, (b_rs, b_cs), M, N, K)."""
+        from ._lib import GemmProblem
+
+        n = len(problems)
+        arr = (GemmProblem * n)()
+        for q, (c, c_dt, c_str, a, a_dt, a_str, b, b_dt, b_str, M, N, K) in zip(arr, problems):
+            q.C, q.A, q.B = c, a, b
+            q.c_dtype, q.a_dtype, q.b_dtype = dtype_code(c_dt), dtype_code(a_dt), dtype_code(b_dt)
+            q.c_rs, q.c_cs = c_str
+            q.a_rs, q.a_cs = a_str
+            q.b_rs, q.b_cs = b_str
+            q.M, q.N, q.K = M, N, K
+        self._check(self._lib.b200ag_gemm_grouped(arr, n))
+
     def gemm_f32_tc(self, c, c_rs, a, a_str, b, b_str, M, N, K) -> None:
         """float32 C = A @ B on the tcgen05 tensor cores (3xTF32); *_str = (row_stride, col_stride) in elements."""
         self._check(self._lib.b200ag_gemm_f32_tc(c, c_rs, a, a_str[0], a_str[1], b, b_str[0], b_str[1], M, N, K))
@@ -359,4 +384,11 @@ def get():
 def set_backend(b) -> None:
     """Install a backend object (used by the CPU test-suite to exercise host logic without a GPU)."""
     global _current
+    if _current is not None and _current is not b:
+        from . import lazy
+
+        try:
+            lazy.flush_gemms()           # queued work belongs to the backend that is being replaced
+        except Exception:
+            del lazy._gemm_queue[:]
     _current = b

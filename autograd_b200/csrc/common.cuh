@@ -15,6 +15,7 @@ int sm_count();
 void count_launch(uint64_t n = 1);
 bool ensure_init();
 int* index_flag();   // device address of the "index out of bounds" flag (mapped host memory), NULL on failure
+int gemm_init();        // gemm.cu: allocates the K-split arrival counters
 bool f32_tc_eligible(int64_t M, int64_t N, int64_t K, int64_t c_cs, int64_t batch);   // gemm_tc.cu
 
 #define B200AG_CHECK_INIT()                      \

@@ -118,6 +118,7 @@ int b200ag_init(int device) {
   B200AG_CUDA(cudaStreamCreateWithFlags(&g_side_stream, cudaStreamNonBlocking));
   g_device = device;
   if (!index_flag()) return 1;   // allocated up front: never inside a stream capture
+  if (gemm_init()) return 1;
   return 0;
 }
 

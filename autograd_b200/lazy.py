@@ -65,7 +65,7 @@ MAX_LEAVES = 48
 class Buffer:
     """Owner of one device allocation; freed back to the pool when unreferenced."""
 
-    __slots__ = ("ptr", "nbytes", "version", "inexact", "readers", "__weakref__")
+    __slots__ = ("ptr", "nbytes", "version", "inexact", "readers", "pending", "__weakref__")
 
     def __init__(self, nbytes: int, upload: bool = False):
         self.nbytes = int(nbytes)
@@ -79,6 +79,7 @@ class Buffer:
         # pending (not yet computed) expression nodes that read this buffer directly; an in-place write materialises them
         # first so that `y = x * 2; x[0] = 100` leaves y computed from the old x, as NumPy's eager evaluation does
         self.readers = None
+        self.pending = False      # True while a deferred contraction (defer_gemm) still has to write this buffer
         be = backend.get()
         self.ptr = be.malloc_upload(self.nbytes) if upload else be.malloc(self.nbytes)
 
@@ -91,8 +92,50 @@ class Buffer:
                 pass
 
 
+# ---------------------------------------------------------------- deferred contractions
+# np.dot on device operands does not launch its GEMM at once: the product is queued and launched when something needs
+# its result (Mat.ptr), when the queue is full, before an in-place write, a synchronisation or the end of a graph
+# capture.  Products queued together go to the GPU as ONE grouped launch (b200ag_gemm_grouped): the four gate products of
+# an LSTM cell (examples/lstm.py:38-49) and the G.B^T / A^T.G adjoints of a tape step (numpy_vjps.py:615-638) are each too
+# small to fill 148 SMs on their own.  Operands are materialised when the product is queued and held until it runs.
+GEMM_QUEUE_MAX = 16
+DEFER_GEMMS = __import__("os").environ.get("B200AG_DEFER_GEMM", "1") != "0"
+_gemm_queue = []
+
+
+def defer_gemm(out: "Mat", a: "Mat", b: "Mat", M: int, N: int, K: int) -> None:
+    """Queue out[M,N] = a[M,K] @ b[K,N] (2-D strided operands, float32/float64)."""
+    rec = (out, a, b, M, N, K, a.ptr, b.ptr)      # taking the operand addresses flushes what THEY still wait for
+    if not DEFER_GEMMS:
+        backend.get().gemm_grouped([_gemm_problem(rec)])
+        return
+    out.buf.pending = True
+    _gemm_queue.append(rec)
+    if len(_gemm_queue) >= GEMM_QUEUE_MAX:
+        flush_gemms()
+
+
+def _gemm_problem(rec):
+    out, a, b, M, N, K, a_ptr, b_ptr = rec
+    return (out.buf.ptr + out.offset * out.dtype.itemsize, out.dtype, (out.strides[0], out.strides[1]),
+            a_ptr, a.dtype, (a.strides[0], a.strides[1]), b_ptr, b.dtype, (b.strides[0], b.strides[1]), M, N, K)
+
+
+def flush_gemms() -> None:
+    """Launch every queued product (one grouped launch per operand class)."""
+    if not _gemm_queue:
+        return
+    queue = _gemm_queue[:]
+    del _gemm_queue[:]
+    for rec in queue:
+        rec[0].buf.pending = False
+    backend.get().gemm_grouped([_gemm_problem(rec) for rec in queue])
+
+
 def flush_readers(buf) -> None:
     """Compute every pending expression that reads ``buf`` (called before an in-place write to it)."""
+    if _gemm_queue:
+        flush_gemms()          # a queued product may read the buffer that is about to change
     readers = buf.readers
     if not readers:
         return
@@ -132,6 +175,10 @@ class Mat:
 
     @property
     def ptr(self) -> int:
+        """Device address of the first element.  Every kernel launch takes its operand addresses from here, so this
+        is also where a deferred contraction that still has to produce the payload is launched."""
+        if self.buf.pending:
+            flush_gemms()
         return self.buf.ptr + self.offset * self.dtype.itemsize
 
     @property

@@ -143,6 +143,20 @@ int b200ag_gemm(void* C, int c_dtype, int64_t c_rs, int64_t c_cs, int64_t c_bs,
                 const void* B, int b_dtype, int64_t b_rs, int64_t b_cs, int64_t b_bs,
                 int64_t M, int64_t N, int64_t K, int64_t batch);
 
+/* A group of independent products in ONE launch (per operand type / layout class):
+ * the four gate products of an LSTM cell that share their left operand
+ * (examples/lstm.py:38-49), the G·Bᵀ / Aᵀ·G adjoints of one tape step
+ * (numpy_vjps.py:615-638), the layer gradients of an MLP.  Each problem is what
+ * b200ag_gemm computes for batch = 1; together they fill the SMs without split-K.
+ * Results are deterministic (K-split partials are added in split order). */
+typedef struct {
+  void* C; const void* A; const void* B;
+  int c_dtype, a_dtype, b_dtype, reserved;
+  int64_t c_rs, c_cs, a_rs, a_cs, b_rs, b_cs;
+  int64_t M, N, K;
+} b200ag_gemm_problem;
+int b200ag_gemm_grouped(const b200ag_gemm_problem* problems, int count);
+
 /* float32 x float32 -> float32 products on the tcgen05 tensor cores (accumulator in
  * TMEM, operands staged by TMA): each operand is split into two TF32 terms and
  * Ahi*Bhi + Ahi*Blo + Alo*Bhi is accumulated in FP32 ("3xTF32"), which keeps the

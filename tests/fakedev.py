@@ -71,6 +71,7 @@ class FakeBackend:
         self._launches = 0
         self._compiled = set()
         self.programs = {}   # key -> Program (for inspection by tests)
+        self.gemm_groups = []  # problems per grouped-GEMM launch (for inspection by tests)
         self.compile_generated = compile_generated and os.path.exists(
             os.path.join(os.path.dirname(__file__), "..", "autograd_b200", "libb200ag.so"))
         self.in_use = 0
@@ -162,7 +163,9 @@ class FakeBackend:
 
     # ------------------------------------------------------------ runtime
     def synchronize(self):
-        pass
+        from autograd_b200 import lazy
+
+        lazy.flush_gemms()
 
     def launch_count(self):
         return self._launches
@@ -406,6 +409,14 @@ class FakeBackend:
         cel, cidx = self._strided(c, c_dt, (batch, M, N), (c_str[2], c_str[0], c_str[1]))
         r = np.matmul(ael[aidx].astype(np.float64), bel[bidx].astype(np.float64))
         cel[cidx] = r.astype(np.dtype(c_dt))
+
+    def gemm_grouped(self, problems):
+        self._launches += 1
+        self.gemm_groups.append(len(problems))
+        for (c, c_dt, c_str, a, a_dt, a_str, b, b_dt, b_str, M, N, K) in problems:
+            self.gemm(c, c_dt, (c_str[0], c_str[1], 0), a, a_dt, (a_str[0], a_str[1], 0), b, b_dt, (b_str[0], b_str[1], 0),
+                      M, N, K, 1)
+            self._launches -= 1
 
     def _rows(self, idx_ptrs, dims, n_index):
         row = np.zeros(n_index, dtype=np.int64)

@@ -137,3 +137,65 @@ def test_host_logic_matches_golden(fake_dev):
 @pytest.mark.gpu
 def test_device_matches_golden(cuda_dev):
     _run_all(True, cases.to_host, exact=False)
+
+
+def _check_summary(got_flat, gold, prefix, tol, what):
+    """Compare a full-size result with the reference's summary of it: strided sample, sum, sum of squares."""
+    got_flat = onp.asarray(got_flat, dtype=onp.float64).ravel()
+    assert got_flat.size == int(gold[prefix + "n"]), f"{what}: size"
+    stride = int(gold[prefix + "stride"])
+    cases.assert_close(got_flat[::stride], gold[prefix + "sample"], tol, f"{what} sample")
+    assert abs(got_flat.sum() - float(gold[prefix + "sum"])) <= tol * float(gold[prefix + "abssum"]), f"{what}: sum"
+    assert abs((got_flat * got_flat).sum() - float(gold[prefix + "sumsq"])) <= 2 * tol * float(gold[prefix + "sumsq"]), f"{what}: sumsq"
+
+
+def _run_c4_256(lift, getter):
+    """C4 at 256 x 256, 20 steps against the reference's own run of examples/fluidsim/fluidsim.py (oracle/make_golden.py):
+    gradient at the 1e-10 contract, forward smoke field bit for bit."""
+    from autograd import value_and_grad
+
+    from examples import workloads as w
+
+    gold = _load("c4_fluid_256x20_summary.npz")
+    rows = cols = 256
+    p, s0, tg = w.fluid_data(rows, cols)
+    val, g = value_and_grad(w.fluid_objective)(lift(p), lift(s0), lift(tg), rows, cols, 20)
+    _check_summary(getter(g), gold, "", cases.TOL_REDUCE, "C4 256x256x20 gradient")
+    assert abs(float(getter(val)) - float(gold["value"])) <= cases.TOL_REDUCE * abs(float(gold["value"]))
+    dp = lift(p)
+    smoke = onp.asarray(getter(w.fluid_simulate(dp[: rows * cols].reshape(rows, cols), dp[rows * cols:].reshape(rows, cols),
+                                                lift(s0), 20))).ravel()
+    assert onp.array_equal(smoke[:: int(gold["smoke_stride"])], gold["smoke_sample"]), "C4 forward not bit-identical"
+    assert smoke.sum() == float(gold["smoke_sum"]) and (smoke * smoke).sum() == float(gold["smoke_sumsq"])
+
+
+def test_host_logic_matches_golden_c4_256(fake_dev):
+    _run_c4_256(cases.to_dev, cases.to_host)
+
+
+@pytest.mark.gpu
+def test_device_matches_full_size_golden(cuda_dev):
+    """BASELINE-size (or host-feasible) runs of the reference's example code, summarised by oracle/make_golden.py:
+    C3 LSTM at T=256 / B=1024 / H=512 (float32 gradients), C5 convnet at batch 2048, C4 fluid at 256 x 256 x 20."""
+    from autograd import value_and_grad
+
+    from examples import workloads as w
+
+    _run_c4_256(cases.to_dev, cases.to_host)
+
+    gold = _load("c5_convnet_2048_summary.npz")
+    n, _pred, loss = w.convnet_make()
+    W, X, T = w.convnet_data(2048, n)
+    val, g = value_and_grad(loss)(cases.to_dev(W), cases.to_dev(X), cases.to_dev(T))
+    _check_summary(g.get(), gold, "", cases.TOL_REDUCE, "C5 batch-2048 gradient")
+    assert abs(float(val) - float(gold["value"])) <= cases.TOL_REDUCE * abs(float(gold["value"]))
+    del val, g, W, X, T
+
+    gold = _load("c3_lstm_full_summary.npz")
+    params, X, Y = w.lstm_data()
+    dX = cases.to_dev(X)
+    val, g = value_and_grad(w.lstm_objective)(cases.to_dev(params), dX, dX)
+    for k, v in g.items():
+        assert v.dtype == onp.float32, k
+        _check_summary(v.get(), gold, k.replace(" ", "_") + "__", cases.TOL_F32, f"C3 full-size d{k}")
+    assert abs(float(val) - float(gold["value"])) <= cases.TOL_REDUCE * abs(float(gold["value"]))

@@ -215,3 +215,46 @@ def test_roll_push_down_is_exact_and_fuses_sweeps(fake_dev, monkeypatch):
         return onp.roll(e, (2, -3), axis=(0, 1)) + onp.roll(onp.roll(e, 1, 0), -1, 1) * onp.roll(g + b, 5, axis=1) + onp.roll(e, 4)
 
     cases.check(f, a, b, idx, tol=0, what="roll push-down semantics")
+
+
+def test_lstm_gate_products_are_launched_as_groups(fake_dev):
+    """np.dot on device operands is queued, not launched: the four gate products of an LSTM cell that share
+    hstack(input, hiddens, 1) (examples/lstm.py:38-49) reach the GPU as ONE grouped launch, and so do the G.B^T / A^T.G
+    adjoints of a backward time step (numpy_vjps.py:615-638)."""
+    from autograd import grad
+
+    from examples import workloads as w
+
+    params, X, _ = w.lstm_data(seq_len=3, batch=8, hidden=16, chars=12)
+    want = grad(w.lstm_objective)(params, X, X)
+    del fake_dev.gemm_groups[:]
+    got = grad(w.lstm_objective)(cases.to_dev(params), cases.to_dev(X), cases.to_dev(X))
+    for g, r in zip(cases.leaves(cases.to_host(got)), cases.leaves(want)):
+        cases.assert_close(g, r, cases.TOL_REDUCE, "lstm grad")
+    groups = list(fake_dev.gemm_groups)
+    assert groups.count(4) >= 3, groups                  # forward: the four gates of every time step
+    assert max(groups) >= 8, groups                      # backward: both adjoints of the four gates together
+    assert sum(groups) / len(groups) > 2.5, groups
+
+
+def test_deferred_products_see_the_operands_they_were_given(fake_dev):
+    """A queued product is launched before anything overwrites its operands or reads its result."""
+    import autograd_b200 as b200
+
+    r = onp.random.RandomState(5)
+    A, B = r.randn(6, 5), r.randn(5, 7)
+    a, b = b200.asarray(A), b200.asarray(B)
+    c = onp.dot(a, b)                     # queued
+    a[0, 0] = 1e6                         # in-place write to an operand: the product must run first
+    d = onp.dot(a, b)
+    cases.assert_close(c.get(), A @ B, cases.TOL_REDUCE, "product queued before the write")
+    A2 = A.copy()
+    A2[0, 0] = 1e6
+    cases.assert_close(d.get(), A2 @ B, cases.TOL_REDUCE, "product queued after the write")
+    e = onp.dot(onp.dot(a, b), b.T)       # chained: the inner result is needed when the outer is queued
+    cases.assert_close(e.get(), A2 @ B @ B.T, cases.TOL_REDUCE, "chained products")
+    f = onp.dot(a, b)
+    fake_dev.synchronize()                # a synchronisation leaves nothing queued
+    from autograd_b200 import lazy
+
+    assert not lazy._gemm_queue and not f._mat().buf.pending
