@@ -15,6 +15,7 @@ without the built library raises.
 from . import array, backend, lazy
 from . import linalg  # noqa: F401  (registers np.linalg.solve/inv/det/slogdet/cholesky for device arrays)
 from .array import DeviceArray, asarray, to_device
+from .checkpoint import checkpoint
 from .complex_array import ComplexDeviceArray
 from .graph import capture
 from .install import host_arrays, install, is_installed
@@ -29,5 +30,5 @@ def to_host(x):
     return x.get() if isinstance(x, (DeviceArray, ComplexDeviceArray)) else x
 
 
-__all__ = ["ComplexDeviceArray", "map_elementwise", "capture", "host_arrays", "DeviceArray", "asarray", "to_device", "to_host", "install", "is_installed", "synchronize", "array",
+__all__ = ["ComplexDeviceArray", "map_elementwise", "capture", "checkpoint", "host_arrays", "DeviceArray", "asarray", "to_device", "to_host", "install", "is_installed", "synchronize", "array",
            "backend", "lazy"]

@@ -59,6 +59,7 @@ PROTOTYPES = {
     "b200ag_copy_strided": [C.c_void_p, C.c_int, c_i64_p, C.c_void_p, C.c_int, c_i64_p, c_i64_p, C.c_int],
     "b200ag_add_strided": [C.c_void_p, C.c_int, c_i64_p, C.c_void_p, c_i64_p, c_i64_p, C.c_int],
     "b200ag_concat": [C.c_void_p, C.c_int, c_void_pp, c_i64_p, C.c_int, c_i64],
+    "b200ag_concat_mixed": [C.c_void_p, C.c_int, c_void_pp, C.POINTER(C.c_int), C.POINTER(C.c_double), c_i64_p, C.c_int, c_i64],
     "b200ag_reduce": [C.c_void_p, C.c_void_p, C.c_int, C.c_int, c_i64, c_i64, c_i64],
     "b200ag_argreduce": [C.c_void_p, C.c_void_p, C.c_int, C.c_int, c_i64, c_i64, c_i64],
     "b200ag_gemm": [C.c_void_p, C.c_int, c_i64, c_i64, c_i64,
@@ -66,6 +67,7 @@ PROTOTYPES = {
                     C.c_void_p, C.c_int, c_i64, c_i64, c_i64,
                     c_i64, c_i64, c_i64, c_i64],
     "b200ag_gemm_grouped": [C.c_void_p, C.c_int],
+    "b200ag_gemm_tune": [C.c_int, C.c_int],
     "b200ag_gemm_f32_tc": [C.c_void_p, c_i64, C.c_void_p, c_i64, c_i64, C.c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64],
     "b200ag_gemm_f32_mode": [C.c_int, C.POINTER(C.c_int)],
     "b200ag_index_flag": [c_void_pp],

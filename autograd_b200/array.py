@@ -1381,6 +1381,17 @@ def concatenate(arrays, axis=0, out=None, dtype=None, casting="same_kind"):
         rest = prod(shape[axis + 1:])
         be.concat(out_m.ptr, out_dtype, [a._node.mat.ptr for a in live], [a.shape[axis] * rest for a in live], outer)
         live = []
+    if live and 2 <= len(live) <= 16 and out_dtype in (F64, F32) and all(
+            (a._node.mat is not None and a._node.mat.is_contiguous and a._node.mat.shifts is None and a.dtype in (F64, F32))
+            or (a._node.mat is None and a._node.op == "full" and isinstance(a._node.args[0], lazy.Const)) for a in live):
+        # float pieces of mixed dtype and symbolic constants (hstack((input float32, hiddens float64, ones)) of an LSTM
+        # cell): still a single launch, the promotion to float64 and the constant fill happen inside it
+        outer = prod(shape[:axis])
+        rest = prod(shape[axis + 1:])
+        pieces = [(a._node.mat.ptr, a.dtype) if a._node.mat is not None else (None, float(a._node.args[0].value))
+                  for a in live]
+        be.concat_mixed(out_m.ptr, out_dtype, pieces, [a.shape[axis] * rest for a in live], outer)
+        live = []
     pos = 0
     for a in (arrays if live else ()):
         if a.size == 0:

@@ -289,6 +289,14 @@ class CudaBackend:
         arr = (C.c_void_p * len(src_ptrs))(*src_ptrs)
         self._check(self._lib.b200ag_concat(dst, dtype_code(dt), arr, _i64_array(inner), len(src_ptrs), outer))
 
+    def concat_mixed(self, dst, dt, pieces, inner, outer: int) -> None:
+        """hstack of float pieces of mixed dtype / constants: pieces = [(ptr, dtype) | (None, fill value)] (<= 16)."""
+        n = len(pieces)
+        ptrs = (C.c_void_p * n)(*[p if p is not None else None for p, _ in pieces])
+        dts = (C.c_int * n)(*[dtype_code(d) if p is not None else 0 for p, d in pieces])
+        fills = (C.c_double * n)(*[0.0 if p is not None else float(d) for p, d in pieces])
+        self._check(self._lib.b200ag_concat_mixed(dst, dtype_code(dt), ptrs, dts, fills, _i64_array(inner), n, outer))
+
     def reduce(self, dst, src, dt, op: str, outer: int, red: int, inner: int) -> None:
         self._check(self._lib.b200ag_reduce(dst, src, dtype_code(dt), REDUCE_CODE[op], outer, red, inner))
 
@@ -318,6 +326,10 @@ class CudaBackend:
             q.b_rs, q.b_cs = b_str
             q.M, q.N, q.K = M, N, K
         self._check(self._lib.b200ag_gemm_grouped(arr, n))
+
+    def gemm_tune(self, tile: int = 0, splits: int = 0) -> None:
+        """Measurement hook: force tile (1 = 64x64, 2 = 128x128) and K split of the following GEMM launches; 0 = automatic."""
+        self._check(self._lib.b200ag_gemm_tune(tile, splits))
 
     def gemm_f32_tc(self, c, c_rs, a, a_str, b, b_str, M, N, K) -> None:
         """float32 C = A @ B on the tcgen05 tensor cores (3xTF32); *_str = (row_stride, col_stride) in elements."""

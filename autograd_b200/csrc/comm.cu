@@ -19,9 +19,11 @@ struct PeerComm {
   unsigned char* peers[16] = {nullptr};
   uint32_t* flags_of[16] = {nullptr};  // flags array inside each peer's block
   size_t flags_off = 0;
+  unsigned char* mc = nullptr;         // multicast (NVLS) mapping of the same block on all ranks, when attached
+  bool external = false;               // block allocated by the caller (b200ag_comm_attach): never freed here
 };
 static PeerComm g_comm;
-static int g_comm_mode = 0;   // 0 = choose by rank count and size, 1 = one-shot pull, 2 = two-shot, 3 = push (b200ag_comm_mode)
+static int g_comm_mode = 0;   // 0 = choose by rank count and size, 1 = one-shot pull, 2 = two-shot, 3 = push, 4 = NVLS multimem (b200ag_comm_mode)
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -209,6 +211,93 @@ __global__ void __launch_bounds__(256) peer_allreduce2_kernel(AllreduceArgs a, d
   }
 }
 
+// NVLS variant (b200ag_comm_attach with a multicast mapping): the reduction happens INSIDE the NVSwitch.  Rank r owns
+// chunk r: one `multimem.ld_reduce.add.f64` per element makes the switch fetch that element from every rank's published
+// slot and return the sum (one NVLink round trip instead of world-1 peer loads), and one `multimem.st` writes the sum
+// into the result area of EVERY rank.  Each element is reduced exactly once, by one rank, so all ranks hold the same
+// bits.  Same flag protocol as the two-shot kernel: A = "my input is published", B = "my chunk is broadcast".
+__device__ __forceinline__ double multimem_ld_reduce_add(const double* mc) {
+  double v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f64 %0, [%1];" : "=d"(v) : "l"(mc) : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st(double* mc, double v) {
+  asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(mc), "d"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(256) nvls_allreduce_kernel(AllreduceArgs a, const double* mc_slots, double* mc_result,
+                                                             const double* my_result) {
+  __shared__ int ok;
+  __shared__ unsigned last;
+  const uint32_t epoch = *a.epoch;
+  const int slot = epoch & 1;
+  uint32_t* flagsB_mine = a.my_flags + 256;
+  if (threadIdx.x == 0) {
+    if (blockIdx.x == 0) {
+      __threadfence_system();
+      for (int p = 0; p < a.world; ++p) st_release_sys(a.peer_flags[p] + slot * a.world + a.rank, epoch);
+    }
+    int good = 1;
+    for (int p = 0; p < a.world && good; ++p) {
+      const uint32_t* f = a.my_flags + slot * a.world + p;
+      long long spins = 0;
+      while (ld_acquire_sys(f) != epoch) {
+        if (++spins > 20000000LL) { good = 0; *a.status = 1; break; }
+        __nanosleep(64);
+      }
+    }
+    ok = good;
+  }
+  __syncthreads();
+  const int64_t off = (int64_t)slot * a.slot_elems;
+  const int64_t chunk = (a.n + a.world - 1) / a.world;
+  const int64_t c_lo = (int64_t)a.rank * chunk, c_hi = min(c_lo + chunk, a.n);
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ok) {
+    for (int64_t i = c_lo + tid; i < c_hi; i += step) multimem_st(mc_result + i, multimem_ld_reduce_add(mc_slots + off + i));
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    unsigned done = atomicAdd(a.epoch + 2, 1u);
+    last = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    a.epoch[2] = 0;
+    __threadfence_system();
+    for (int p = 0; p < a.world; ++p) st_release_sys(a.peer_flags[p] + 256 + slot * a.world + a.rank, epoch);
+  }
+  if (threadIdx.x == 0) {
+    int good = ok;
+    for (int p = 0; p < a.world && good; ++p) {
+      const uint32_t* f = flagsB_mine + slot * a.world + p;
+      long long spins = 0;
+      while (ld_acquire_sys(f) != epoch) {
+        if (++spins > 20000000LL) { good = 0; *a.status = 1; break; }
+        __nanosleep(64);
+      }
+    }
+    ok = good;
+  }
+  __syncthreads();
+  if (ok) {
+    for (int64_t i = tid; i < a.n; i += step) a.out[i] = __ldcv(my_result + i);     // local HBM: every chunk was broadcast here
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned done = atomicAdd(a.epoch + 3, 1u);
+    last = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    a.epoch[3] = 0;
+    a.epoch[0] = epoch + 1;
+  }
+}
+
 // Push variant: instead of every rank pulling all peers' vectors (round-trip loads over NVLink), every rank WRITES its
 // vector into an inbox slot of every peer (posted stores pipeline much better than loads), raises the peers' flags once
 // all of its CTAs have finished, and the sum then runs over local HBM only.
@@ -340,6 +429,36 @@ int b200ag_comm_create(int rank, int world, size_t slot_bytes, void* ipc_handle_
   return 0;
 }
 
+// Size of one rank's comm block for b200ag_comm_attach.
+int b200ag_comm_block_bytes(int world, size_t slot_bytes, size_t* total) {
+  slot_bytes = (slot_bytes + 255) & ~size_t(255);
+  *total = (3 + 2 * (size_t)world) * slot_bytes + 4096;
+  return 0;
+}
+
+// Use comm blocks the CALLER allocated symmetrically on every rank (zero-filled, b200ag_comm_block_bytes each) and mapped
+// into this process: peer_bases[p] = rank p's block as addressable from here, multicast_base = the NVLS multicast
+// mapping of the same blocks (NULL when the platform has none).  torch.distributed's symmetric memory provides both.
+int b200ag_comm_attach(int rank, int world, size_t slot_bytes, void* const* peer_bases, void* multicast_base) {
+  B200AG_CHECK_INIT();
+  if (world < 1 || world > 16 || rank < 0 || rank >= world) B200AG_FAIL("comm_attach: bad rank/world (max 16 ranks)");
+  if (g_comm.local) B200AG_FAIL("comm_attach: a communicator already exists");
+  slot_bytes = (slot_bytes + 255) & ~size_t(255);
+  g_comm.rank = rank; g_comm.world = world; g_comm.slot_bytes = slot_bytes;
+  g_comm.flags_off = (3 + 2 * (size_t)world) * slot_bytes;
+  g_comm.external = true;
+  g_comm.mc = (unsigned char*)multicast_base;
+  for (int p = 0; p < world; ++p) {
+    if (!peer_bases[p]) { g_comm = PeerComm(); B200AG_FAIL("comm_attach: missing peer mapping"); }
+    g_comm.peers[p] = (unsigned char*)peer_bases[p];
+    g_comm.flags_of[p] = (uint32_t*)(g_comm.peers[p] + g_comm.flags_off);
+  }
+  g_comm.local = g_comm.peers[rank];
+  uint32_t one = 1;   // epoch starts at 1 so that zeroed flags never match
+  B200AG_CUDA(cudaMemcpy(g_comm.local + g_comm.flags_off + 2048, &one, 4, cudaMemcpyHostToDevice));
+  return 0;
+}
+
 // Map every rank's comm block (handles = world x 64 bytes, in rank order).
 int b200ag_comm_connect(const void* handles) {
   B200AG_CHECK_INIT();
@@ -408,6 +527,18 @@ int b200ag_comm_allreduce_sum_f64(void* out, const void* src, int64_t n) {
   if (((uintptr_t)out & 15) != 0) B200AG_FAIL("comm_allreduce: output must be 16-byte aligned");
   // measured at 1.42 MB: one-shot 21 / 43 us at 2 / 8 ranks, two-shot 31 / 66 us (two flag rounds + a grid-wide arrival):
   // the two-shot form only pays once the (world-1)x larger one-shot traffic dominates, i.e. for multi-megabyte vectors
+  const bool nvls = g_comm.mc && (g_comm_mode == 4 || (g_comm_mode == 0 && g_comm.world >= 4));
+  if (nvls) {
+    int64_t per_rank = (n + g_comm.world - 1) / g_comm.world;
+    unsigned grid = (unsigned)((per_rank + 255) / 256);
+    unsigned cap = (unsigned)sm_count();          // grid-wide arrival rounds: every CTA must be resident
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    nvls_allreduce_kernel<<<grid, 256, 0, stream()>>>(a, (const double*)g_comm.mc, (double*)(g_comm.mc + 2 * g_comm.slot_bytes),
+                                                      (const double*)(g_comm.local + 2 * g_comm.slot_bytes));
+    B200AG_LAUNCH_CHECK();
+    return 0;
+  }
   const bool two_shot = g_comm_mode == 2 || (g_comm_mode == 0 && g_comm.world >= 4 && n >= (1 << 19));
   if (two_shot) {
     // every CTA takes part in a grid-wide arrival round, so all of them must be resident at once
@@ -443,9 +574,11 @@ int b200ag_comm_status(int* timed_out) {
 int b200ag_comm_destroy(void) {
   if (!g_comm.local) return 0;
   cudaStreamSynchronize(stream());
-  for (int p = 0; p < g_comm.world; ++p)
-    if (p != g_comm.rank && g_comm.peers[p]) cudaIpcCloseMemHandle(g_comm.peers[p]);
-  cudaFree(g_comm.local);
+  if (!g_comm.external) {
+    for (int p = 0; p < g_comm.world; ++p)
+      if (p != g_comm.rank && g_comm.peers[p]) cudaIpcCloseMemHandle(g_comm.peers[p]);
+    cudaFree(g_comm.local);
+  }
   g_comm = PeerComm();
   return 0;
 }
@@ -454,7 +587,7 @@ int b200ag_comm_destroy(void) {
 // 2 = two-shot (reduce-scatter + all-gather over peer memory).
 int b200ag_comm_mode(int mode, int* previous) {
   if (previous) *previous = g_comm_mode;
-  if (mode >= 0 && mode <= 3) g_comm_mode = mode;
+  if (mode >= 0 && mode <= 4) g_comm_mode = mode;
   return 0;
 }
 

@@ -267,6 +267,37 @@ __global__ void __launch_bounds__(256) scatter_assign_kernel(T* __restrict__ dst
   }
 }
 
+// np.hstack of float pieces of MIXED dtype and of symbolic constants in ONE launch: the cell input of an LSTM step is
+// hstack(input float32, hiddens float64, ones) (examples/rnn.py:21 via examples/lstm.py:33-36), which NumPy promotes to
+// float64.  Piece k is [outer, inner[k]] of float32 / float64, or a constant fill when its source is NULL.
+struct ConcatMixedDesc {
+  const void* src[16];
+  double fill[16];
+  int src_f32[16];
+  int64_t inner[16];
+  int64_t start[17];
+  int npieces;
+  int64_t outer, total_inner;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) concat_mixed_kernel(T* __restrict__ dst, ConcatMixedDesc d) {
+  const int64_t n = d.outer * d.total_inner;
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += step) {
+    const int64_t row = idx / d.total_inner, col = idx - row * d.total_inner;
+    int k = 0;
+#pragma unroll 1
+    while (k + 1 < d.npieces && col >= d.start[k + 1]) ++k;
+    const int64_t off = row * d.inner[k] + (col - d.start[k]);
+    double v;
+    if (!d.src[k]) v = d.fill[k];
+    else if (d.src_f32[k]) v = (double)reinterpret_cast<const float*>(d.src[k])[off];
+    else v = reinterpret_cast<const double*>(d.src[k])[off];
+    dst[idx] = (T)v;
+  }
+}
+
 }  // namespace b200ag
 
 using namespace b200ag;
@@ -420,6 +451,36 @@ int b200ag_concat(void* dst, int dtype, const void* const* srcs, const int64_t* 
     case 1: concat_kernel<uint8_t><<<grid, 256, 0, stream()>>>((uint8_t*)dst, d); break;
     default: B200AG_FAIL("concat: unsupported dtype");
   }
+  B200AG_LAUNCH_CHECK();
+  return 0;
+}
+
+int b200ag_concat_mixed(void* dst, int dtype, const void* const* srcs, const int* src_dtypes, const double* fills,
+                        const int64_t* inner, int npieces, int64_t outer) {
+  B200AG_CHECK_INIT();
+  if (npieces < 1 || npieces > 16) B200AG_FAIL("concat_mixed: between 1 and 16 pieces per call");
+  if (dtype != B200AG_F64 && dtype != B200AG_F32) B200AG_FAIL("concat_mixed: output dtype must be float64 or float32");
+  ConcatMixedDesc d;
+  d.npieces = npieces;
+  d.outer = outer;
+  int64_t pos = 0;
+  for (int k = 0; k < npieces; ++k) {
+    if (srcs[k] && src_dtypes[k] != B200AG_F64 && src_dtypes[k] != B200AG_F32)
+      B200AG_FAIL("concat_mixed: pieces must be float64 or float32");
+    d.src[k] = srcs[k];
+    d.src_f32[k] = src_dtypes[k] == B200AG_F32;
+    d.fill[k] = fills[k];
+    d.inner[k] = inner[k];
+    d.start[k] = pos;
+    pos += inner[k];
+  }
+  d.start[npieces] = pos;
+  d.total_inner = pos;
+  int64_t n = outer * pos;
+  if (n == 0) return 0;
+  unsigned grid = grid_for(n, 256, 8);
+  if (dtype == B200AG_F64) concat_mixed_kernel<double><<<grid, 256, 0, stream()>>>((double*)dst, d);
+  else concat_mixed_kernel<float><<<grid, 256, 0, stream()>>>((float*)dst, d);
   B200AG_LAUNCH_CHECK();
   return 0;
 }

@@ -105,6 +105,72 @@ def _dist_setup(n_gpus):
     return rank, local, world, dist
 
 
+def _bind_to_gpu_numa(gpu_index: int):
+    """Run this rank (and so its pinned staging buffers, first-touched by it) on the CPU cores of the GPU's own NUMA
+    node, so host<->device copies do not cross the socket interconnect.  Returns what was done, for the JSON line."""
+    info = {"numa_node": None, "cpus": None}
+    try:
+        bus = subprocess.run(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=10).stdout.strip().lower()
+        if bus.startswith("00000000:"):
+            bus = bus[4:]                                   # sysfs uses a 4-digit PCI domain
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        info["numa_node"] = node
+        if node < 0:
+            return info
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info["cpus"] = f"{min(cpus)}-{max(cpus)} ({len(cpus)})"
+    except Exception as exc:
+        info["error"] = f"{type(exc).__name__}: {exc}"
+    return info
+
+
+def _copy_ceiling_ms(be, x_host, y_host, dist, reps=3, chunk_bytes=64 << 20):
+    """What the box allows: plain pinned cudaMemcpyAsync of the step's input (H2D) and output (D2H) on two streams at
+    once, one call per 64 MiB chunk, nothing computed.  Max over ranks; e2e cannot be faster than this."""
+    from autograd_b200.lazy import Mat
+
+    n = x_host.size
+    din, dout = Mat.empty((n,), x_host.dtype), Mat.empty((n,), y_host.dtype)
+    up, down = be.stream_create(), be.stream_create()
+    e0, e1, eu, ed = (be.event_create() for _ in range(4))
+    step = max(1, chunk_bytes // x_host.itemsize)
+
+    def once():
+        for lo in range(0, n, step):
+            hi = min(n, lo + step)
+            be.h2d_on(din.ptr + lo * x_host.itemsize, x_host[lo:hi], up)
+            be.d2h_on(y_host[lo:hi], dout.ptr + lo * y_host.itemsize, down)
+        be.event_record_on(eu, up)
+        be.event_record_on(ed, down)
+        be.stream_wait_event(None, eu)
+        be.stream_wait_event(None, ed)
+
+    keep = y_host[:16].copy()
+    once()
+    be.synchronize()
+    _barrier(dist)
+    be.event_record(e0)
+    for _ in range(reps):
+        once()
+    be.event_record(e1)
+    be.synchronize()
+    ms = be.event_elapsed_ms(e0, e1) / reps
+    be.stream_destroy(up)
+    be.stream_destroy(down)
+    del keep
+    return _max_over_ranks(ms, dist)
+
+
 def _barrier(dist):
     if dist is not None:
         dist.barrier()
@@ -121,55 +187,83 @@ def _max_over_ranks(value, dist):
 
 
 # ----------------------------------------------------------------------------- reference arm / cpu baseline
-def time_reference_cpu(sample_points: int, full_points: int, steps: int, warmup: int):
-    """Reference autograd on NumPy (its own CPU path, unmodified, from baseline/_ref) on a bounded sample.
-    NumPy's elementwise loops are single-threaded, so the path can use 1 core."""
-    from examples import workloads as w
+REF_SAMPLE_POINTS = 1 << 22   # points per timed reference step: 74 live vectors x 32 MiB, far outside any cache
 
+
+def time_reference_cpu(sample_points: int, full_points: int, steps: int, warmup: int, procs: int | None = None):
+    """Reference autograd on NumPy (its own CPU path, unmodified, from baseline/_ref) on a bounded sample of the
+    workload: every step evaluates egrad^4(tanh) on `sample_points` points with ALL host cores (one worker process per
+    core, each on its own chunk - NumPy's elementwise loops are single-threaded).  Returns whole-workload evals/s
+    (the measured points/s divided by the points of one full evaluation), seconds per sample step, cores, description."""
+    from benchmarks.cpu_reference import HostPool
+
+    pool = HostPool(procs)
     try:
-        import autograd_b200 as b200
-
-        ctx = b200.host_arrays()
-    except Exception:
-        import contextlib
-
-        ctx = contextlib.nullcontext()
-    x = onp.linspace(-7.0, 7.0, sample_points)
-    f = w.tanh_nth_derivative(ORDER)
-    with ctx:
-        for _ in range(warmup):
-            f(x)
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            f(x)
-        dt = (time.perf_counter() - t0) / steps
-    scale = full_points / sample_points
-    value = 1.0 / (dt * scale)
-    sample = (f"reference autograd 1.9.1 on NumPy {onp.__version__}, egrad^{ORDER}(tanh) on {sample_points} of "
-              f"{full_points} points per step ({dt:.3f} s), scaled linearly (elementwise workload) to the full size")
-    return value, dt, sample
+        for _ in range(max(warmup, 1)):
+            pool.step(sample_points)
+        times = [pool.step(sample_points) for _ in range(max(steps, 1))]
+    finally:
+        pool.close()
+    dt = sum(times) / len(times)
+    value = (sample_points / dt) / full_points
+    sample = (f"reference autograd 1.9.1 on NumPy {onp.__version__}: egrad^{ORDER}(tanh) on {sample_points} of "
+              f"{full_points} points per step, {pool.procs} worker processes (one per host core, "
+              f"{sample_points // pool.procs} points each), {dt:.3f} s per step measured; value = measured points/s "
+              f"divided by the points of one full evaluation (elementwise workload: linear in points)")
+    return value, dt, pool.procs, sample
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    full = args.n * args.gpus
-    sample_points = min(args.n, 1 << 20)
-    value, dt, sample = time_reference_cpu(sample_points, full, max(args.steps, 1), max(args.warmup, 1))
-    # `value` is whole-job evals/s on the N-GPU job's total points; per-job evaluations = gpus
-    value *= args.gpus
+    full = args.n                      # points of ONE evaluation (per GPU in the device arm)
+    sample_points = min(full, REF_SAMPLE_POINTS)
+    value, dt, cores, sample = time_reference_cpu(sample_points, full, max(args.steps, 1), max(args.warmup, 1))
+    # the N-GPU job evaluates N chunks of `full` points per step; the host's points/s does not change with N, so in
+    # evaluations of one chunk per second the whole-job figure is the same number
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt * (args.n / sample_points) * 1e3, "higher_is_better": True,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": _config(args.n, args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "reference", "sample": sample},
+        "step_definition": f"one timed step = {sample_points} points (a bounded sample); one full evaluation = {full} points "
+                           f"= {full / sample_points:g} such steps = {dt * full / sample_points:.1f} s at the measured rate",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     _emit(line)
     return 0
+
+
+def _ncu_capture(kernel_name):
+    """DRAM traffic and FP64-pipe activity of `kernel_name` from the committed `ncu --set full` captures under profiles/
+    (raw-page CSV exports, newest round first).  None when no capture of THIS kernel exists: a stale figure is worse
+    than none."""
+    import csv
+    import glob
+
+    unit_scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_c2_fused_ncu_raw*.csv")), reverse=True):
+        try:
+            with open(path) as f:
+                rows = list(csv.reader(f))
+            hdr, units = rows[0], rows[1]
+            col = {h: i for i, h in enumerate(hdr)}
+            for r in rows[2:]:
+                if r[col["Kernel Name"]] != kernel_name:
+                    continue
+                def val(name):
+                    return float(r[col[name]].replace(",", "")) * unit_scale.get(units[col[name]], 1.0)
+                return {"traffic": val("dram__bytes_read.sum") + val("dram__bytes_write.sum"),
+                        "fp64_pipe_active_pct": float(r[col["sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed"]]),
+                        "ncu_kernel_ms": float(r[col["gpu__time_duration.sum"]]) *
+                        {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(units[col["gpu__time_duration.sum"]], 1.0),
+                        "source": os.path.relpath(path, ROOT)}
+        except Exception:
+            continue
+    return None
 
 
 def _config(n, gpus):
@@ -184,6 +278,8 @@ def _config(n, gpus):
 def run_b200(args):
     rank, local, world, dist = _dist_setup(args.gpus)
     os.environ.setdefault("B200AG_DEVICE", str(local))
+    full_affinity = os.sched_getaffinity(0)
+    numa = _bind_to_gpu_numa(local)       # before any pinned allocation
     import autograd_b200 as b200
 
     b200.install()
@@ -271,18 +367,41 @@ def run_b200(args):
     peak, peak_src = _peaks()
     achieved = ALGO_BYTES_PER_POINT * n / (kern_ms * 1e-3) / 1e9
     prog = durs[0][0] if durs else None
-    # DRAM traffic per launch from the committed ncu capture of this very command (profiles/r01_c2_fused_ncu_raw.csv:
-    # dram__bytes_read.sum 2.1476 GB + dram__bytes_write.sum 2.1058 GB at 2^28 points), scaled to --n
-    traffic = (2.147620e9 + 2.105774e9) * n / float(1 << 28)
+    # DRAM traffic per launch and FP64-pipe activity: read from the committed `ncu --set full` capture of THIS kernel
+    # (matched by its generated name, which is a hash of the program) - never typed in
+    kname, fp64_per_point = None, None
+    if prog is not None:
+        from autograd_b200 import codegen
+
+        src_, kname, _ = codegen.generate(prog)
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "scripts"))
+            from count_body_instrs import per_point_counts
+
+            cnt, _sass = per_point_counts(src_)
+            fp64_per_point = int(sum(cnt[k] for k in ("DFMA", "DMUL", "DADD", "DSETP")))
+        except Exception as exc:      # cuobjdump / NVRTC unavailable: leave the count out
+            print("bench: per-point instruction count unavailable:", exc, file=sys.stderr)
+    cap = _ncu_capture(kname) if kname else None
+    sm_clock_hz = 1.965e9
+    # FP64 issue roofline: FP64-pipe instructions per point x points / (SMs x 64 lanes per clock x clock)
+    fp64_floor_ms = (fp64_per_point * n / (be.sm_count * 64 * sm_clock_hz) * 1e3) if fp64_per_point else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "traffic_source": "ncu --set full, profiles/r01_c2_fused_ncu_raw.csv",
-                "fp64_pipe_active_pct_ncu": 77.0,
-                "peak_source": peak_src, "kernel": "fused elementwise (generated, NVRTC sm_100a)",
+                "traffic": (cap["traffic"] * n / float(1 << 28)) if cap else None,
+                "traffic_source": (f"ncu --set full, {cap['source']} (kernel {kname}, 2^28 points, scaled to --n)" if cap else
+                                   f"no committed capture of kernel {kname} under profiles/"),
+                "fp64_pipe_active_pct_ncu": cap["fp64_pipe_active_pct"] if cap else None,
+                "fp64_instructions_per_point": fp64_per_point,
+                "fp64_issue_floor_ms": fp64_floor_ms,
+                "fp64_issue_frac": (fp64_floor_ms / kern_ms) if fp64_floor_ms else None,
+                "peak_source": peak_src, "kernel": f"fused elementwise {kname} (generated, NVRTC sm_100a)",
                 "kernel_ms": kern_ms, "kernel_ops_fused": len(prog.instrs) if prog else None,
                 "kernel_share_of_step": kern_ms / ms_per_step,
-                "note": "algorithmic bytes = 16 B/point (read x, write y); the body is 348 recorded ufunc calls = 242 FP64 "
-                        "instructions per point after value numbering and reciprocal sharing, so the kernel sits on the "
-                        "FP64 pipe (77 % active in ncu), not on HBM"}
+                "note": "algorithmic bytes = 16 B/point (read x, write y).  The body is 348 recorded ufunc calls; everything "
+                        "downstream of exp() is inexact against NumPy anyway, so multiply-add pairs are contracted and "
+                        "quotients share one refined reciprocal (bit-exact rounding is kept only on values that can still "
+                        "be bit-identical to NumPy's).  The kernel is bound by FP64 issue, not by HBM: fp64_issue_frac is "
+                        "the fraction of the FP64-pipe roofline (static SASS count of the body, 64 lanes/clk/SM at 1.965 GHz)"}
 
     # ---- end to end through the public API with HOST buffers: H2D + grad + D2H inside the timed region
     for _ in range(2):
@@ -317,11 +436,22 @@ def run_b200(args):
         pipe_ms = None
         pipe_err = f"{type(exc).__name__}: {exc}"
     best_ms = min(e2e_ms, pipe_ms) if pipe_ms else e2e_ms
+    # the box's own ceiling for this much host<->device traffic on `world` GPUs at once (nothing computed)
+    try:
+        ceiling_ms = _copy_ceiling_ms(be, x_host, y_host, dist)
+    except Exception as exc:
+        ceiling_ms = None
+        print("bench: copy ceiling probe failed:", exc, file=sys.stderr)
     e2e = {"value": world / (best_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(x_host.nbytes),
            "d2h_bytes_per_step": int(y_host.nbytes), "ms_per_step": best_ms,
            "api": "autograd_b200.map_elementwise(f, x_host, out=y_host)" if pipe_ms and pipe_ms <= e2e_ms else
                   "f(autograd_b200.asarray(x_host)).get(out=y_host)",
-           "monolithic_ms_per_step": e2e_ms, "chunk_pipelined_ms_per_step": pipe_ms}
+           "monolithic_ms_per_step": e2e_ms, "chunk_pipelined_ms_per_step": pipe_ms,
+           "copy_ceiling_ms": ceiling_ms,
+           "copy_ceiling_note": "plain pinned cudaMemcpyAsync H2D + D2H of the same bytes on two streams, all ranks at once, "
+                                "max over ranks, no compute",
+           "frac_of_copy_ceiling": (ceiling_ms / best_ms) if ceiling_ms else None,
+           "host_binding": numa}
 
     # parity spot check on the bench inputs themselves: 2^16 points strided across the whole resident vector,
     # error relative to the max-norm of the reference result (the derivative crosses zero)
@@ -353,10 +483,11 @@ def run_b200(args):
         return 0
 
     # ---- reference CPU path timed beside it on this box's host cores (bounded sample)
-    sample_points = min(n, 1 << 20)
-    cpu_value, cpu_dt, sample = time_reference_cpu(sample_points, n, 2, 1)
-    cpu = {"value": cpu_value, "unit": UNIT, "cores": 1, "kind": "reference", "sample": sample,
-           "host_cpu_count": os.cpu_count()}
+    sample_points = min(n, REF_SAMPLE_POINTS)
+    os.sched_setaffinity(0, full_affinity)      # the CPU baseline may use every host core again
+    cpu_value, cpu_dt, cores, sample = time_reference_cpu(sample_points, n, 3, 1)
+    cpu = {"value": cpu_value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample,
+           "seconds_per_sample_step": cpu_dt, "host_cpu_count": os.cpu_count()}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

@@ -358,3 +358,143 @@ def convnet_data(batch, num_weights, seed=0):
     X = rs.rand(batch, 1, 28, 28)
     T = onp.eye(10)[rs.randint(0, 10, batch)]
     return W, X, T
+
+
+# ===================================================================== SURVEY §8(f) row 4: extra workloads
+# examples/rnn.py:27-60, examples/bayesian_neural_net.py:11-52, examples/black_box_svi.py:11-36,56-61 restated the same way
+# (the example modules import matplotlib at the top); pinned to the real example code by tests/golden/f4_*.npz.
+def rnn_init_params(input_size, state_size, output_size, param_scale=0.01, rs=None):
+    rs = rs if rs is not None else onp.random.RandomState(0)
+    return {"init hiddens": rs.randn(1, state_size) * param_scale,
+            "change": rs.randn(input_size + state_size + 1, state_size) * param_scale,
+            "predict": rs.randn(state_size + 1, output_size) * param_scale}
+
+
+def rnn_predict(params, inputs):
+    logsumexp = _logsumexp()
+
+    def update_rnn(input, hiddens):
+        return np.tanh(_concat_and_multiply(params["change"], input, hiddens))
+
+    def hiddens_to_output_probs(hiddens):
+        output = _concat_and_multiply(params["predict"], hiddens)
+        return output - logsumexp(output, axis=1, keepdims=True)
+
+    num_sequences = inputs.shape[1]
+    hiddens = np.repeat(params["init hiddens"], num_sequences, axis=0)
+    output = [hiddens_to_output_probs(hiddens)]
+    for input in inputs:
+        hiddens = update_rnn(input, hiddens)
+        output.append(hiddens_to_output_probs(hiddens))
+    return output
+
+
+def rnn_log_likelihood(params, inputs, targets):
+    logprobs = rnn_predict(params, inputs)
+    loglik = 0.0
+    num_time_steps, num_examples, _ = inputs.shape
+    for t in range(num_time_steps):
+        loglik += np.sum(logprobs[t] * targets[t])
+    return loglik / (num_time_steps * num_examples)
+
+
+def rnn_objective(params, inputs, targets):
+    return -rnn_log_likelihood(params, inputs, targets)
+
+
+def rnn_data(seq_len=6, batch=8, hidden=16, chars=12, seed=0):
+    rs = onp.random.RandomState(seed)
+    params = rnn_init_params(chars, hidden, chars, param_scale=0.01, rs=rs)
+    inputs = onp.eye(chars)[rs.randint(0, chars, (seq_len, batch))]
+    return params, inputs, inputs
+
+
+def bnn_make_nn_funs(layer_sizes, L2_reg, noise_variance, nonlinearity=np.tanh):
+    """MLP vectorised over training examples AND weight samples (bayesian_neural_net.py:11-42)."""
+    shapes = list(itertools.pairwise(layer_sizes))
+    num_weights = sum((m + 1) * n for m, n in shapes)
+
+    def unpack_layers(weights):
+        num_weight_sets = len(weights)
+        for m, n in shapes:
+            yield (weights[:, : m * n].reshape((num_weight_sets, m, n)),
+                   weights[:, m * n: m * n + n].reshape((num_weight_sets, 1, n)))
+            weights = weights[:, (m + 1) * n:]
+
+    def predictions(weights, inputs):
+        inputs = np.expand_dims(inputs, 0)
+        for W, b in unpack_layers(weights):
+            outputs = np.einsum("mnd,mdo->mno", inputs, W) + b
+            inputs = nonlinearity(outputs)
+        return outputs
+
+    def logprob(weights, inputs, targets):
+        log_prior = -L2_reg * np.sum(weights**2, axis=1)
+        preds = predictions(weights, inputs)
+        log_lik = -np.sum((preds - targets) ** 2, axis=1)[:, 0] / noise_variance
+        return log_prior + log_lik
+
+    return num_weights, predictions, logprob
+
+
+def bnn_toy_dataset(n_data=40, noise_std=0.1):
+    """bayesian_neural_net.py:45-52."""
+    D = 1
+    rs = onp.random.RandomState(0)
+    inputs = onp.concatenate([onp.linspace(0, 2, num=n_data // 2), onp.linspace(6, 8, num=n_data // 2)])
+    targets = onp.cos(inputs) + rs.randn(n_data) * noise_std
+    inputs = (inputs - 4.0) / 4.0
+    return inputs.reshape((len(inputs), D)), targets.reshape((len(targets), D))
+
+
+def svi_objective(logprob, D, num_samples, seed=0):
+    """Stochastic variational lower bound of a diagonal Gaussian (black_box_svi.py:11-36).  The standard-normal draws
+    come from a host RandomState exactly as in the example; they meet the device parameters in ``* np.exp(log_std)``."""
+    rs = onp.random.RandomState(seed)
+
+    def gaussian_entropy(log_std):
+        return 0.5 * D * (1.0 + np.log(2 * np.pi)) + np.sum(log_std)
+
+    def variational_objective(params, t):
+        mean, log_std = params[:D], params[D:]
+        samples = rs.randn(num_samples, D) * np.exp(log_std) + mean
+        lower_bound = gaussian_entropy(log_std) + np.mean(logprob(samples, t))
+        return -lower_bound
+
+    return variational_objective
+
+
+def svi_funnel_log_density(x, t):
+    """The example's target density (black_box_svi.py:56-61)."""
+    import autograd.scipy.stats.norm as norm
+
+    mu, log_sigma = x[:, 0], x[:, 1]
+    sigma_density = norm.logpdf(log_sigma, 0, 1.35)
+    mu_density = norm.logpdf(mu, 0, np.exp(log_sigma))
+    return sigma_density + mu_density
+
+
+def fluid_step(vx, vy, smoke):
+    """One time step of fluid_simulate (fluidsim.py:73-80) as a function of the whole state."""
+    vx_updated = fluid_advect(vx, vx, vy)
+    vy_updated = fluid_advect(vy, vx, vy)
+    vx, vy = fluid_project(vx_updated, vy_updated)
+    return vx, vy, fluid_advect(smoke, vx, vy)
+
+
+def fluid_objective_checkpointed(params, init_smoke, target, rows, cols, steps, checkpoint=None):
+    """fluid_objective with every time step wrapped in a checkpoint — ``autograd.checkpoint``
+    (differential_operators.py:230-242) by default, or the wrapper passed in: the memory lever SURVEY §0-6 names for
+    tapes that do not fit."""
+    from autograd.builtins import tuple as ag_tuple
+
+    if checkpoint is None:
+        from autograd.differential_operators import checkpoint
+
+    step = checkpoint(lambda state: ag_tuple(fluid_step(state[0], state[1], state[2])))
+    vx = np.reshape(params[: (rows * cols)], (rows, cols))
+    vy = np.reshape(params[(rows * cols):], (rows, cols))
+    state = ag_tuple((vx, vy, init_smoke))
+    for _ in range(steps):
+        state = step(state)
+    return np.mean((target - state[2]) ** 2)

@@ -118,6 +118,12 @@ int b200ag_add_strided(void* dst, int dtype, const int64_t* dst_strides,
  * misc.flatten, numpy_wrapper.py:57-59, misc/flatten.py:11-27). */
 int b200ag_concat(void* dst, int dtype, const void* const* srcs, const int64_t* inner,
                   int npieces, int64_t outer);
+/* The same for float pieces of mixed dtype and symbolic constants: piece k is float32 or float64
+ * (src_dtypes[k]), or the constant fills[k] when srcs[k] is NULL; dst is float64 or float32.
+ * hstack((input float32, hiddens float64, ones)) of an LSTM / RNN cell (examples/rnn.py:21,
+ * examples/lstm.py:33-36: NumPy promotes the row to float64) in one launch. */
+int b200ag_concat_mixed(void* dst, int dtype, const void* const* srcs, const int* src_dtypes,
+                        const double* fills, const int64_t* inner, int npieces, int64_t outer);
 
 /* ---------------------------------------------------------------- reductions
  * np.sum / np.max / np.min / np.prod over one contiguous group of axes of a
@@ -156,6 +162,9 @@ typedef struct {
   int64_t M, N, K;
 } b200ag_gemm_problem;
 int b200ag_gemm_grouped(const b200ag_gemm_problem* problems, int count);
+/* Measurement hook: force the K split (0 = automatic) of the following launches; scripts/gemm_sweep.py uses it to
+ * calibrate the automatic choice.  `tile` is accepted for ABI stability and ignored (one tile shape, 64x64). */
+int b200ag_gemm_tune(int tile, int splits);
 
 /* float32 x float32 -> float32 products on the tcgen05 tensor cores (accumulator in
  * TMEM, operands staged by TMA): each operand is split into two TF32 terms and

@@ -182,6 +182,47 @@ def main():
         onp.savez(os.path.join(OUT, "c4_fluid_256x20_summary.npz"), value=val, smoke_sum=sm["sum"], smoke_sumsq=sm["sumsq"],
                   smoke_sample=sm["sample"], smoke_stride=53, **summary(g, 97))
 
+    # ---------------- rnn.py, bayesian_neural_net.py, black_box_svi.py (their own model code)
+    import rnn as rnn_example
+    import bayesian_neural_net as bnn_example
+    import black_box_svi as svi_example
+
+    params, X, Y = w.rnn_data()
+    ref = rnn_example.create_rnn_params(12, 16, 12, param_scale=0.01, rs=onp.random.RandomState(0))
+    assert all(onp.array_equal(ref[k], params[k]) for k in ref)
+    val, g = value_and_grad(lambda p: -rnn_example.rnn_log_likelihood(p, X, Y))(params)
+    val2, g2 = value_and_grad(w.rnn_objective)(params, X, Y)
+    assert val == val2 and all(onp.array_equal(g[k], g2[k]) for k in g)
+    out = {"rnn_value": val, **{"rnn_" + k.replace(" ", "_"): v for k, v in g.items()}}
+
+    rbf = lambda x: np.exp(-(x**2))
+    nw_, _pred, logprob = bnn_example.make_nn_funs(layer_sizes=[1, 20, 20, 1], L2_reg=0.1, noise_variance=0.01, nonlinearity=rbf)
+    inputs, targets = bnn_example.build_toy_dataset()
+    objective_, gradient_, _unpack = svi_example.black_box_variational_inference(
+        lambda weights, t: logprob(weights, inputs, targets), nw_, num_samples=20)
+    rs_ = onp.random.RandomState(0)
+    init = onp.concatenate([rs_.randn(nw_), -5 * onp.ones(nw_)])
+    gb = gradient_(init, 0)                                     # first call of a fresh objective: first draw of its stream
+    nw2, _p2, logprob2 = w.bnn_make_nn_funs([1, 20, 20, 1], 0.1, 0.01, nonlinearity=rbf)
+    in2, tg2 = w.bnn_toy_dataset()
+    assert nw2 == nw_ and onp.array_equal(in2, inputs) and onp.array_equal(tg2, targets)
+    gb2 = grad(w.svi_objective(lambda weights, t: logprob2(weights, in2, tg2), nw2, 20))(init, 0)
+    assert onp.array_equal(gb, gb2)
+    out["bnn_init"], out["bnn_grad"] = init, gb
+
+    def log_density(x, t):                                       # black_box_svi.py:56-61 (inside its __main__ block)
+        from autograd.scipy.stats import norm
+        mu, log_sigma = x[:, 0], x[:, 1]
+        return norm.logpdf(log_sigma, 0, 1.35) + norm.logpdf(mu, 0, np.exp(log_sigma))
+
+    objective_, gradient_, _unpack = svi_example.black_box_variational_inference(log_density, 2, num_samples=2000)
+    init = onp.concatenate([-1 * onp.ones(2), -5 * onp.ones(2)])
+    gs = gradient_(init, 0)
+    gs2 = grad(w.svi_objective(w.svi_funnel_log_density, 2, 2000))(init, 0)
+    assert onp.array_equal(gs, gs2)
+    out["svi_init"], out["svi_grad"] = init, gs
+    onp.savez(os.path.join(OUT, "f4_extra_workloads.npz"), **out)
+
     # ---------------- rows a13 / a14 beyond the configs: weighted logsumexp and general N-d convolve (values + both VJPs)
     from autograd.scipy.signal import convolve
     from autograd.scipy.special import logsumexp

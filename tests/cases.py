@@ -1683,3 +1683,69 @@ def case_item_assignment_duplicates_last_write_wins():
 
 OP_CASES["inplace_write_semantics"] = case_inplace_write_semantics
 OP_CASES["item_assignment_duplicates_last_write_wins"] = case_item_assignment_duplicates_last_write_wins
+
+
+def grad_case_extra_workloads():
+    """the model code of examples/rnn.py, bayesian_neural_net.py (through black_box_svi.py's
+    variational objective, einsum over weight samples) and black_box_svi.py's own funnel density (scipy.stats.norm),
+    device gradients against the reference on NumPy.  The stochastic objectives draw from a host RandomState: a fresh
+    objective per evaluation gives both sides the same draws."""
+    import autograd.numpy as np
+    from autograd import grad
+
+    from examples import workloads as w
+
+    params, X, Y = w.rnn_data()
+    check_grad(w.rnn_objective, (params, X, Y), TOL_REDUCE, "rnn.py gradient")
+
+    rbf = lambda x: np.exp(-(x**2))
+    nw, _pred, logprob = w.bnn_make_nn_funs([1, 20, 20, 1], 0.1, 0.01, nonlinearity=rbf)
+    inputs, targets = w.bnn_toy_dataset()
+    init = onp.concatenate([rs(0).randn(nw), -5 * onp.ones(nw)])
+    make = lambda lift: w.svi_objective(lambda weights, t: logprob(weights, lift(inputs), lift(targets)), nw, 20)
+    want = _ref(grad(make(lambda a: a)), init, 0)
+    got = grad(make(b200.asarray))(b200.asarray(init), 0).get()
+    assert_close(got, want, TOL_REDUCE, "bayesian_neural_net.py gradient")
+
+    init = onp.concatenate([-1 * onp.ones(2), -5 * onp.ones(2)])
+    want = _ref(grad(w.svi_objective(w.svi_funnel_log_density, 2, 2000)), init, 0)
+    got = grad(w.svi_objective(w.svi_funnel_log_density, 2, 2000))(b200.asarray(init), 0).get()
+    assert_close(got, want, TOL_REDUCE, "black_box_svi.py gradient")
+
+
+def grad_case_checkpoint():
+    """Gradient checkpointing around every fluid time step.  The reference's ``autograd.checkpoint``
+    (differential_operators.py:230-242) runs unchanged on device values and gives the reference's gradient; its v1.9.1
+    staging (core.py:60-65 calls the rule's maker when the node is recorded) re-traces during the FORWARD pass, so it
+    retains as much as the plain tape - on NumPy and here alike.  ``autograd_b200.checkpoint`` defers the re-trace to the
+    backward pass as the docstring promises: same gradient, and the retained memory drops to the state between steps."""
+    from autograd import value_and_grad
+
+    from examples import workloads as w
+
+    be = b200.backend.get()
+    rows = cols = 64
+    steps = 30          # the plain tape grows by ~11 arrays per step, the checkpointed one by the 3 state arrays + 3 results
+    p, s0, tg = w.fluid_data(rows, cols)
+    vw, gw = _ref(value_and_grad(w.fluid_objective), p, s0, tg, rows, cols, steps)
+    args = (b200.asarray(p), b200.asarray(s0), b200.asarray(tg), rows, cols, steps)
+
+    def run(fn, *extra):
+        be.synchronize()
+        be.mem_stats()                                # reading the statistics resets the peak to the current use
+        v, g = value_and_grad(fn)(*args, *extra)
+        gh, vh = g.get(), float(v)
+        return vh, gh, be.mem_stats()["peak_in_use"]
+
+    v1, g1, plain_peak = run(w.fluid_objective)
+    v2, g2, ref_ckpt_peak = run(w.fluid_objective_checkpointed)
+    v3, g3, ckpt_peak = run(w.fluid_objective_checkpointed, b200.checkpoint)
+    for v, g, what in ((v1, g1, "plain tape"), (v2, g2, "autograd.checkpoint"), (v3, g3, "autograd_b200.checkpoint")):
+        assert_close(g, gw, TOL_REDUCE, f"fluid gradient, {what}")
+        assert abs(v - float(vw)) <= TOL_REDUCE * abs(float(vw)), what
+    assert ckpt_peak < 0.7 * plain_peak, f"checkpoint kept {ckpt_peak} bytes, plain tape {plain_peak}"
+    assert ref_ckpt_peak > 0.8 * plain_peak            # documents the reference's behaviour; not a requirement on us
+
+
+GRAD_CASES["extra_workloads"] = grad_case_extra_workloads
+GRAD_CASES["checkpoint"] = grad_case_checkpoint

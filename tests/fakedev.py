@@ -375,6 +375,20 @@ class FakeBackend:
             d[:, pos: pos + k] = sel[s0: s0 + outer * k].reshape(outer, k)
             pos += k
 
+    def concat_mixed(self, dst, dt, pieces, inner, outer):
+        self._launches += 1
+        total = int(sum(inner))
+        del_, d0 = self._elems(dst, dt)
+        d = del_[d0: d0 + outer * total].reshape(outer, total)
+        pos = 0
+        for (ptr, info), k in zip(pieces, inner):
+            if ptr is None:
+                d[:, pos: pos + k] = info
+            else:
+                sel, s0 = self._elems(ptr, info)
+                d[:, pos: pos + k] = sel[s0: s0 + outer * k].reshape(outer, k)
+            pos += k
+
     def _view3(self, ptr, dt, outer, red, inner):
         el, e0 = self._elems(ptr, dt)
         return el[e0: e0 + outer * red * inner].reshape(outer, red, inner)

@@ -199,3 +199,43 @@ def test_device_matches_full_size_golden(cuda_dev):
         assert v.dtype == onp.float32, k
         _check_summary(v.get(), gold, k.replace(" ", "_") + "__", cases.TOL_F32, f"C3 full-size d{k}")
     assert abs(float(val) - float(gold["value"])) <= cases.TOL_REDUCE * abs(float(gold["value"]))
+
+
+def _run_f4(lift, getter, exact):
+    """examples/rnn.py, bayesian_neural_net.py and black_box_svi.py against fixtures produced by the example files
+    themselves (oracle/make_golden.py)."""
+    import autograd.numpy as np
+    from autograd import grad, value_and_grad
+
+    from examples import workloads as w
+
+    gold = _load("f4_extra_workloads.npz")
+    tol = 0 if exact else cases.TOL_REDUCE
+    params, X, Y = w.rnn_data()
+    val, g = value_and_grad(w.rnn_objective)(lift(params), lift(X), lift(Y))
+    assert abs(float(getter(val)) - float(gold["rnn_value"])) <= max(tol, 0) * abs(float(gold["rnn_value"]))
+    for k, v in getter(g).items():
+        cases.assert_close(v, gold["rnn_" + k.replace(" ", "_")], tol, f"rnn.py d{k}")
+    rbf = lambda x: np.exp(-(x**2))
+    nw, _pred, logprob = w.bnn_make_nn_funs([1, 20, 20, 1], 0.1, 0.01, nonlinearity=rbf)
+    inputs, targets = w.bnn_toy_dataset()
+    obj = w.svi_objective(lambda weights, t: logprob(weights, lift(inputs), lift(targets)), nw, 20)
+    cases.assert_close(getter(grad(obj)(lift(gold["bnn_init"]), 0)), gold["bnn_grad"], tol, "bayesian_neural_net.py gradient")
+    obj = w.svi_objective(w.svi_funnel_log_density, 2, 2000)
+    cases.assert_close(getter(grad(obj)(lift(gold["svi_init"]), 0)), gold["svi_grad"], tol, "black_box_svi.py gradient")
+
+
+def test_oracle_restated_extra_workloads_match_reference_examples_bit_for_bit(fake_dev):
+    import autograd_b200 as b200
+
+    with b200.host_arrays(), onp.errstate(all="ignore"):
+        _run_f4(lambda t: t, lambda t: t, exact=True)
+
+
+def test_host_logic_matches_golden_f4(fake_dev):
+    _run_f4(cases.to_dev, cases.to_host, exact=False)
+
+
+@pytest.mark.gpu
+def test_device_matches_golden_f4(cuda_dev):
+    _run_f4(cases.to_dev, cases.to_host, exact=False)
