@@ -85,6 +85,8 @@ PROTOTYPES = {
     "b200ag_conv_mode": [C.c_int, C.POINTER(C.c_int)],
     "b200ag_comm_create": [C.c_int, C.c_int, C.c_size_t, C.c_void_p],
     "b200ag_comm_connect": [C.c_void_p],
+    "b200ag_comm_block_bytes": [C.c_int, C.c_size_t, c_size_p],
+    "b200ag_comm_attach": [C.c_int, C.c_int, C.c_size_t, c_void_pp, C.c_void_p],
     "b200ag_comm_allreduce_sum_f64": [C.c_void_p, C.c_void_p, c_i64],
     "b200ag_comm_mode": [C.c_int, C.POINTER(C.c_int)],
     "b200ag_comm_status": [C.POINTER(C.c_int)],

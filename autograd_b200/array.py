@@ -879,6 +879,9 @@ def reshape(a, shape=None, order="C", *, newshape=None, copy=None):
         unit = _reshape_unit_axes_lazy(node, shape)
         if unit is not None:
             return DeviceArray(unit)
+        general = _reshape_strided_lazy(node, shape)
+        if general is not None:
+            return DeviceArray(general)
     m = a._mat()
     new_strides = _reshape_strides(m, shape)
     if new_strides is None:
@@ -929,6 +932,59 @@ def _reshape_lazy(node, shape, root_shape, memo):
         res = Node(node.op, args, node.in_dtypes, new_shape, node.dtype)
     memo[node.nid] = res
     return res
+
+
+def _reshape_strided_lazy(node, new_shape):
+    """C-order reshape of a pending elementwise expression whose operands are NOT all contiguous arrays of its own
+    shape — a broadcast bias, a strided view — pushed down to the leaves: every operand, seen as a strided (zero-stride
+    where it broadcasts) view of the root's shape, is reshaped without a copy (``_reshape_strides``).  This keeps
+    ``conv(x, w) + b`` pending through the ``reshape(N, C, H/2, 2, W/2, 2)`` of a max-pool (examples/convnet.py:108-117),
+    so the bias add fuses into the pooling kernel instead of costing a pass of its own.  None when some operand cannot
+    be reshaped in place (then the caller materialises first, as before)."""
+    root_shape = node.shape
+    if _pending_size(node, 48) > 48:
+        return None
+    nd = len(root_shape)
+    memo = {}
+
+    def go(n_):
+        hit = memo.get(n_.nid, memo)
+        if hit is not memo:
+            return hit
+        res = None
+        if prod(n_.shape) == 1 and n_.mat is None and n_.op == "full":
+            res = Node("full", n_.args, n_.in_dtypes, (), n_.dtype)
+        elif n_.mat is not None:
+            m = n_.mat
+            if m.shifts is None:
+                if prod(m.shape) == 1:
+                    res = lazy.leaf(Mat(m.buf, (), (), m.offset, m.dtype))
+                else:
+                    off = nd - len(m.shape)
+                    if off >= 0 and all(s == 1 or s == root_shape[off + i] for i, s in enumerate(m.shape)):
+                        bstr = (0,) * off + tuple(0 if s == 1 else st for s, st in zip(m.shape, m.strides))
+                        view = Mat(m.buf, root_shape, bstr, m.offset, m.dtype)
+                        st_new = _reshape_strides(view, new_shape) if not view.is_contiguous else lazy.c_strides(new_shape)
+                        if st_new is not None:
+                            res = lazy.leaf(Mat(m.buf, tuple(new_shape), st_new, m.offset, m.dtype))
+        elif n_.op == "full":
+            res = Node("full", n_.args, n_.in_dtypes, tuple(new_shape), n_.dtype) if n_.shape == root_shape else None
+        elif n_.op in ("scatter", "gather"):
+            res = None
+        elif n_.shape == root_shape or prod(n_.shape) == 1:
+            args = []
+            for a in n_.args:
+                if type(a) is Node:
+                    a = go(a)
+                    if a is None:
+                        break
+                args.append(a)
+            if len(args) == len(n_.args):
+                res = Node(n_.op, tuple(args), n_.in_dtypes, tuple(new_shape) if n_.shape == root_shape else (), n_.dtype)
+        memo[n_.nid] = res
+        return res
+
+    return go(node)
 
 
 _SELECTABLE_SPECIAL = ("where", "cast", "full")

@@ -91,7 +91,11 @@ class CudaBackend:
         call surfaces here, at the first synchronisation after it."""
         raised = C.c_int(0)
         self._lib.b200ag_index_error(C.byref(raised))
-        if raised.value:
+        if raised.value & 2:
+            raise RuntimeError("autograd_b200: a peer-memory allreduce gave up waiting for another rank (bounded spin timed "
+                               "out); the gradient on this rank is not the sum over ranks and replicas may have diverged - "
+                               "abort the job")
+        if raised.value & 1:
             raise IndexError("autograd_b200: an index array on the device held an index that is out of bounds for the "
                              "indexed axis (detected by a gather / np.add.at / item-assignment kernel since the last "
                              "synchronisation; the offending accesses were skipped)")
@@ -190,6 +194,15 @@ class CudaBackend:
     def comm_connect(self, handles: bytes) -> None:
         buf = C.create_string_buffer(handles, len(handles))
         self._check(self._lib.b200ag_comm_connect(buf))
+
+    def comm_block_bytes(self, world: int, slot_bytes: int) -> int:
+        n = C.c_size_t()
+        self._check(self._lib.b200ag_comm_block_bytes(world, slot_bytes, C.byref(n)))
+        return n.value
+
+    def comm_attach(self, rank: int, world: int, slot_bytes: int, peer_ptrs, multicast_ptr: int) -> None:
+        arr = (C.c_void_p * len(peer_ptrs))(*peer_ptrs)
+        self._check(self._lib.b200ag_comm_attach(rank, world, slot_bytes, arr, multicast_ptr or None))
 
     def comm_allreduce_sum_f64(self, out: int, src: int, n: int) -> None:
         self._check(self._lib.b200ag_comm_allreduce_sum_f64(out, src, n))
@@ -367,7 +380,7 @@ class CudaBackend:
         self._check(self._lib.b200ag_conv2d(out, a, b, dtype_code(dt), N, Cc, H, W, F, kh, kw, mode, flip))
 
     def comm_mode(self, mode: int) -> int:
-        """Peer allreduce algorithm: 0 automatic, 1 one-shot, 2 two-shot; returns the previous setting."""
+        """Peer allreduce algorithm: 0 automatic, 1 one-shot pull, 2 two-shot, 3 push, 4 NVLS multimem; returns the previous setting."""
         prev = C.c_int(0)
         self._check(self._lib.b200ag_comm_mode(mode, C.byref(prev)))
         return prev.value

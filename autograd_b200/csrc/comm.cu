@@ -491,7 +491,7 @@ int b200ag_comm_allreduce_sum_f64(void* out, const void* src, int64_t n) {
     for (int p = 0; p < g_comm.world; ++p) { q.peer_base[p] = g_comm.peers[p]; q.peer_flags[p] = g_comm.flags_of[p]; }
     q.my_flags = g_comm.flags_of[g_comm.rank];
     q.epoch = (uint32_t*)(g_comm.local + g_comm.flags_off + 2048);
-    q.status = q.epoch + 1;
+    q.status = (uint32_t*)(index_flag() + 1);    // mapped host memory: the host sees a timeout at its next synchronisation
     q.src = (const double*)src; q.out = (double*)out;
     q.n = n; q.slot_elems = (int64_t)(g_comm.slot_bytes / 8);
     q.inbox_off = 3 * (int64_t)g_comm.slot_bytes;
@@ -515,7 +515,7 @@ int b200ag_comm_allreduce_sum_f64(void* out, const void* src, int64_t n) {
   }
   a.my_flags = g_comm.flags_of[g_comm.rank];
   a.epoch = (uint32_t*)(g_comm.local + g_comm.flags_off + 2048);
-  a.status = a.epoch + 1;
+  a.status = (uint32_t*)(index_flag() + 1);      // mapped host memory: the host sees a timeout at its next synchronisation
   a.n = n;
   a.slot_elems = (int64_t)(g_comm.slot_bytes / 8);
   a.rank = g_comm.rank;
@@ -563,11 +563,9 @@ int b200ag_comm_allreduce_sum_f64(void* out, const void* src, int64_t n) {
 
 int b200ag_comm_status(int* timed_out) {
   B200AG_CHECK_INIT();
-  *timed_out = 0;
-  if (!g_comm.local) return 0;
-  uint32_t v = 0;
-  B200AG_CUDA(cudaMemcpy(&v, g_comm.local + g_comm.flags_off + 2048 + 4, 4, cudaMemcpyDeviceToHost));
-  *timed_out = (int)v;
+  int flags = 0;
+  b200ag_index_error(&flags);
+  *timed_out = (flags & 2) ? 1 : 0;
   return 0;
 }
 

@@ -41,12 +41,12 @@ int* index_flag() {
   if (g_index_flag_dev) return g_index_flag_dev;
   if (!ensure_init()) return nullptr;
   int* h = nullptr;
-  if (cudaHostAlloc((void**)&h, sizeof(int), cudaHostAllocMapped) != cudaSuccess) {
+  if (cudaHostAlloc((void**)&h, 2 * sizeof(int), cudaHostAllocMapped) != cudaSuccess) {
     set_error("index flag: cudaHostAlloc failed");
     cudaGetLastError();
     return nullptr;
   }
-  *h = 0;
+  h[0] = h[1] = 0;     // [0] index out of bounds, [1] peer collective timed out (comm.cu)
   int* dptr = nullptr;
   if (cudaHostGetDevicePointer((void**)&dptr, h, 0) != cudaSuccess) {
     set_error("index flag: cudaHostGetDevicePointer failed");
@@ -169,9 +169,12 @@ int b200ag_index_flag(void** dev_ptr) {
 
 int b200ag_index_error(int* raised) {
   *raised = 0;
-  if (g_index_flag_host && *g_index_flag_host) {
+  if (g_index_flag_host && g_index_flag_host[0]) {
     *raised = 1;
-    *g_index_flag_host = 0;
+    g_index_flag_host[0] = 0;
+  }
+  if (g_index_flag_host && g_index_flag_host[1]) {   // reported in bit 1, left set: a timed-out collective is fatal
+    *raised |= 2;
   }
   return 0;
 }

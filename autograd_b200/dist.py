@@ -63,22 +63,65 @@ def _as_torch(x: DeviceArray):
     return torch.from_numpy(el[e0: e0 + x.size]).reshape(m.shape)
 
 
-_peer = {"ready": False, "slot_bytes": 0}
+_peer = {"ready": False, "slot_bytes": 0, "transport": None, "nvls": False, "keep": None}
 
 
-def enable_peer_allreduce(max_bytes: int = 4 << 20) -> bool:
-    """Set up the one-kernel NVLink allreduce (csrc/comm.cu) for float64 vectors up to ``max_bytes``: every rank
-    allocates its comm block and the CUDA-IPC handles are exchanged through torch.distributed."""
+def _attach_symmetric(be, world: int, r: int, max_bytes: int) -> bool:
+    """Comm blocks from torch.distributed's symmetric memory: peer mappings AND, where the platform has NVLS, a
+    multicast mapping of the same blocks - the plumbing (handle exchange, cuMulticast* calls) is torch's, the kernels
+    that use the addresses are ours (csrc/comm.cu).  False when this torch build / platform cannot provide it."""
+    import torch
+
+    try:
+        import torch.distributed._symmetric_memory as symm
+
+        nbytes = be.comm_block_bytes(world, max_bytes)
+        dev = torch.device("cuda", be.device)
+        block = symm.empty(nbytes, dtype=torch.uint8, device=dev)
+        block.zero_()
+        torch.cuda.synchronize(dev)
+        hdl = symm.rendezvous(block, _pg.group.WORLD)
+        peers = [int(p) for p in hdl.buffer_ptrs]
+        mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+        if len(peers) != world or not all(peers):
+            return False
+        _pg.barrier()                                # every rank zeroed its block before anybody raises a flag in it
+        be.comm_attach(r, world, max_bytes, peers, mc)
+        _peer["keep"] = (block, hdl)                 # the mappings live as long as these objects
+        _peer["transport"], _peer["nvls"] = "torch symmetric memory", bool(mc)
+        return True
+    except Exception as exc:                         # older torch, no fabric / pidfd support in the container, ...
+        _peer["transport_error"] = f"{type(exc).__name__}: {exc}"
+        return False
+
+
+def enable_peer_allreduce(max_bytes: int = 4 << 20, symmetric: bool = True) -> bool:
+    """Set up the one-kernel NVLink allreduce (csrc/comm.cu) for float64 vectors up to ``max_bytes``.  The comm blocks
+    come from torch's symmetric memory when available (which also gives the NVLS multicast mapping used by the
+    in-switch reduction); otherwise every rank cudaMallocs its block and the CUDA-IPC handles are exchanged through
+    torch.distributed."""
     if _pg is None or _pg.get_world_size() == 1 or backend.get().name != "cuda":
         return False
     if _peer["ready"]:
         return True
     be = backend.get()
     world, r = _pg.get_world_size(), _pg.get_rank()
-    handle = be.comm_create(r, world, max_bytes)
-    gathered = [None] * world
-    _pg.all_gather_object(gathered, handle)
-    be.comm_connect(b"".join(gathered))
+    ok = symmetric and os.environ.get("B200AG_COMM_SYMMETRIC", "1") != "0" and _attach_symmetric(be, world, r, max_bytes)
+    # all ranks must take the same path
+    import torch
+
+    flag = torch.tensor([1 if ok else 0], device=torch.device("cuda", be.device))
+    _pg.all_reduce(flag, op=_pg.ReduceOp.MIN)
+    if ok and int(flag.item()) == 0:
+        be.comm_destroy()
+        _peer["keep"] = None
+        ok = False
+    if not ok:
+        handle = be.comm_create(r, world, max_bytes)
+        gathered = [None] * world
+        _pg.all_gather_object(gathered, handle)
+        be.comm_connect(b"".join(gathered))
+        _peer["transport"], _peer["nvls"] = "CUDA IPC", False
     _pg.barrier()
     _peer["ready"], _peer["slot_bytes"] = True, max_bytes
     return True

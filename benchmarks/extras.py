@@ -324,14 +324,24 @@ def c1_dp(be, world=1, rank=0):
             flat = bdist.flatten_tree(g(p, x, t, 1.0 / world)).materialize()
             return bdist.allreduce_sum_(flat)
 
+        steps = {}
+        be.comm_mode(1 if bdist._peer["nvls"] else 0)
         whole = b200.capture(fused)
-        step_peer = lambda: whole(dp, dX, dT)
-        variants["one graph incl. peer-memory allreduce kernel"] = _dp_time(be, step_peer, 50, world)
+        steps["one graph incl. peer-memory allreduce kernel"] = lambda: whole(dp, dX, dT)
+        variants["one graph incl. peer-memory allreduce kernel"] = _dp_time(be, steps["one graph incl. peer-memory allreduce kernel"], 50, world)
+        if bdist._peer["nvls"]:
+            # variant C: the same single graph, the sum taken inside the NVSwitch (multimem.ld_reduce / multimem.st)
+            be.comm_mode(4)
+            whole_nvls = b200.capture(fused)
+            name = "one graph incl. NVLS in-switch allreduce kernel"
+            steps[name] = lambda: whole_nvls(dp, dX, dT)
+            variants[name] = _dp_time(be, steps[name], 50, world)
+        be.comm_mode(0)
         best = min(variants, key=lambda k: variants[k][0])
         if best.startswith("graph + nccl"):
             bdist._peer["ready"] = False
         else:
-            step = step_peer
+            step = steps[best]
         ms, launches = variants[best]
     else:
         best = "ncclAllReduce after the replayed graph" if world > 1 else "none (1 GPU)"
@@ -339,7 +349,8 @@ def c1_dp(be, world=1, rank=0):
     res = {"workload": f"C1 MLP grad, 256 rows per GPU x {world} GPUs, 1.42 MB f64 gradient allreduce per step",
            "collective": best, "scaling": "weak", "ms_per_step": ms, "grad_evals_per_sec": world * 1e3 / ms,
            "rows_per_sec": world * 256 * 1e3 / ms, "launches_per_step": launches,
-           "variants_ms_per_step": {k: v[0] for k, v in variants.items()}}
+           "variants_ms_per_step": {k: v[0] for k, v in variants.items()},
+           "comm_blocks": bdist._peer.get("transport"), "nvls_multicast": bool(bdist._peer.get("nvls"))}
     # parity: the summed gradient equals the reference gradient of the concatenated batch
     flat = step().get()
     if rank == 0:
@@ -378,7 +389,22 @@ def c5_dp(be, world=1, rank=0, N=65536):
         return flat
 
     ms, launches = _dp_time(be, step, 5, world)
-    return {"workload": f"C5 convnet grad, {N} images split over {world} GPUs ({per} each), 355 KB f64 gradient "
+    # parity of the sharded path at a size the host can check: 64 images per rank through the same step function,
+    # against the reference gradient of the concatenated batch (the example's logsumexp shifts by the shard's max
+    # instead of the global one, convnet.py:40-42: rounding-level differences only)
+    _, Xs, Ts = w.convnet_data(64, n, seed=100 + rank)
+    got = fused(dW, b200.asarray(Xs), b200.asarray(Ts))
+    if world > 1 and not peer:
+        bdist.allreduce_sum_(got)
+    got = got.get()
+    err = None
+    if rank == 0:
+        parts = [w.convnet_data(64, n, seed=100 + r)[1:] for r in range(world)]
+        with b200.host_arrays():
+            want = g(W, onp.concatenate([p_[0] for p_ in parts]), onp.concatenate([p_[1] for p_ in parts]), 1.0)
+        err = float(onp.max(onp.abs(got - want)) / onp.max(onp.abs(want)))
+    return {"max_rel_err_vs_reference_at_64_images_per_rank": err,
+            "workload": f"C5 convnet grad, {N} images split over {world} GPUs ({per} each), 355 KB f64 gradient "
                         f"allreduce per step", "collective": "one-kernel NVLink peer-memory allreduce inside the replayed "
                         "CUDA graph" if peer else ("ncclAllReduce" if world > 1 else "none (1 GPU)"),
             "scaling": "strong", "ms_per_step": ms,

@@ -189,7 +189,7 @@ int b200ag_gemm_f32_mode(int mode, int* previous);
  * memory is raised.  b200ag_index_error reports and clears it (call after a
  * synchronisation); b200ag_index_flag gives generated kernels the flag's device address. */
 int b200ag_index_flag(void** device_ptr);
-int b200ag_index_error(int* raised);
+int b200ag_index_error(int* raised);   /* bit 0: index out of bounds (cleared by the call); bit 1: collective timed out */
 int b200ag_gather(void* dst, const void* src, int dtype,
                   const int64_t* const* idx, int nidx, const int64_t* src_dims,
                   int64_t n_index, int64_t inner);
@@ -251,11 +251,20 @@ int b200ag_conv_mode(int direct, int* previous);
  * in rank order.  handles = world x 64-byte cudaIpcMemHandle_t, exchanged by the caller (torch.distributed). */
 int b200ag_comm_create(int rank, int world, size_t slot_bytes, void* ipc_handle_out);
 int b200ag_comm_connect(const void* handles);
+/* The same communicator over comm blocks the caller allocated symmetrically on every rank (zero-filled,
+ * b200ag_comm_block_bytes each) and mapped into this process — peer_bases[p] = rank p's block as addressable from
+ * here, multicast_base = the NVLS multicast mapping of those blocks, or NULL (torch.distributed's symmetric memory
+ * hands out both).  With a multicast mapping the sum is taken INSIDE the NVSwitch: rank r reduces chunk r with one
+ * multimem.ld_reduce.add.f64 per element and broadcasts it with one multimem.st (mode 4). */
+int b200ag_comm_block_bytes(int world, size_t slot_bytes, size_t* total);
+int b200ag_comm_attach(int rank, int world, size_t slot_bytes, void* const* peer_bases, void* multicast_base);
 int b200ag_comm_allreduce_sum_f64(void* out, const void* src, int64_t n);
+/* 1 when a collective gave up waiting for a peer (bounded spin): the flag lives in mapped host memory, is also
+ * reported by b200ag_index_error (bit 1) after any synchronisation, and is never cleared — replicas may have diverged. */
 int b200ag_comm_status(int* timed_out);
-/* 0 = choose automatically (one-shot; two-shot reduce-scatter + all-gather from 4 ranks and
- * 4 MB up), 1 = one-shot (pull), 2 = two-shot, 3 = one-shot push (every rank writes its vector into
- * the peers' inboxes, the sum reads local memory only). */
+/* 0 = choose automatically (NVLS from 4 ranks up when a multicast mapping is attached, else one-shot; two-shot
+ * reduce-scatter + all-gather from 4 ranks and 4 MB up), 1 = one-shot (pull), 2 = two-shot, 3 = one-shot push (every
+ * rank writes its vector into the peers' inboxes, the sum reads local memory only), 4 = NVLS multimem. */
 int b200ag_comm_mode(int mode, int* previous);
 int b200ag_comm_destroy(void);
 

@@ -26,7 +26,14 @@ for v in all_vecs:                                            # rank order, like
 
 # 1. eager calls, many epochs (exercises both slots and the epoch counter), one-shot and two-shot interleaved,
 #    plus an odd length and a short vector through both algorithms
-for mode in (1, 2, 3):
+import torch
+
+NVLS = bool(dist._peer["nvls"])
+if rank == 0:
+    print(f"comm blocks: {dist._peer['transport']}, NVLS multicast mapping: {NVLS}"
+          + (f" (symmetric memory unavailable: {dist._peer.get('transport_error')})" if dist._peer.get("transport_error") else ""),
+          flush=True)
+for mode in (1, 2, 3) + ((4,) if NVLS else ()):
     be.comm_mode(mode)
     for n_el in (178109, 7, 2):
         xs = b200.asarray(all_vecs[rank][:n_el].copy())
@@ -34,7 +41,16 @@ for mode in (1, 2, 3):
         exp = onp.zeros(n_el)
         for v in all_vecs:
             exp = exp + v[:n_el]
-        assert onp.array_equal(xs.get(), exp), f"rank {rank} mode {mode} n {n_el}"
+        got = xs.get()
+        if mode == 4:
+            # the NVSwitch adds in its own order: equal to rounding, and the SAME bits on every rank
+            assert onp.allclose(got, exp, rtol=1e-14, atol=1e-14), f"rank {rank} NVLS n {n_el}: {onp.abs(got - exp).max()}"
+            t = torch.as_tensor(xs, device="cuda")
+            gathered = [torch.empty_like(t) for _ in range(world)]
+            dist._pg.all_gather(gathered, t)
+            assert all(torch.equal(g, gathered[0]) for g in gathered), f"NVLS result differs between ranks (n {n_el})"
+        else:
+            assert onp.array_equal(got, exp), f"rank {rank} mode {mode} n {n_el}"
 be.comm_mode(0)
 for it in range(20):
     be.comm_mode(1 + (it % 3))
@@ -53,7 +69,6 @@ assert be.comm_status() == 0
 be.comm_mode(0)
 
 # 2. bit-identical across ranks
-import torch
 t = torch.as_tensor(x, device="cuda")
 gathered = [torch.empty_like(t) for _ in range(world)]
 dist._pg.all_gather(gathered, t)
@@ -97,6 +112,15 @@ be.comm_mode(2)
 t_two = timeit(lambda: dist.allreduce_sum_(y))
 be.comm_mode(3)
 t_push = timeit(lambda: dist.allreduce_sum_(y))
+t_nvls = None
+if NVLS:
+    be.comm_mode(4)
+    t_nvls = timeit(lambda: dist.allreduce_sum_(y))
+    # NVLS inside a replayed graph
+    fast4 = b200.capture(step)
+    for it in range(4):
+        out = fast4(xin).get()
+        assert onp.allclose(out, want * 2.0 + world, rtol=1e-14, atol=1e-12), f"NVLS graph replay {it}"
 be.comm_mode(0)
 t_peer = timeit(lambda: dist.allreduce_sum_(y))
 dist._peer["ready"] = False
@@ -104,6 +128,6 @@ t_nccl = timeit(lambda: dist.allreduce_sum_(y))
 dist._peer["ready"] = True
 if rank == 0:
     print(f"peer-memory allreduce 1.42 MB x{world}: one-shot pull {t_one:.1f} us, two-shot {t_two:.1f} us, push {t_push:.1f} us, automatic {t_peer:.1f} us/call; "
-          f"NCCL via torch: {t_nccl:.1f} us/call", flush=True)
+          f"NVLS multimem {'%.1f us' % t_nvls if t_nvls is not None else 'n/a'}; NCCL via torch: {t_nccl:.1f} us/call", flush=True)
 print(f"rank {rank}/{world} peer allreduce ok", flush=True)
 dist._pg.barrier()
