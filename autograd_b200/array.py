@@ -1327,44 +1327,6 @@ def flipud(a): return flip(a, 0)
 def fliplr(a): return flip(a, 1)
 
 
-# Experiment knob (default 0 = off, not yet measured on the GPU): np.roll of a PENDING expression of at most this many
-# nodes is pushed down to the expression's leaves instead of materialising it first, so consecutive stencil sweeps
-# (the Jacobi loop of examples/fluidsim/fluidsim.py:21-30) share one kernel.  DESIGN.md section 9 has the estimate.
-_ROLL_PUSH_NODES = int(__import__("os").environ.get("B200AG_ROLL_PUSH", "0"))
-
-
-def _roll_lazy(node, ndim, shifts, memo):
-    """``np.roll`` by ``shifts`` (one entry per axis of the ``ndim``-dimensional root) pushed down to the leaves of a
-    pending elementwise expression: roll(f(a, b)) = f(roll(a), roll(b)).  Broadcast (size-1) axes ignore their shift;
-    a gather rolls its index expressions, not its table.  Returns None when impossible (scatter)."""
-    hit = memo.get(node.nid, memo)
-    if hit is not memo:
-        return hit
-    shape = node.shape
-    off = ndim - len(shape)
-    eff = tuple((shifts[off + i] % n) if n > 1 else 0 for i, n in enumerate(shape))
-    if not any(eff) or node.op == "full":
-        res = node
-    elif node.mat is not None:
-        m = node.mat
-        old = m.shifts if m.shifts is not None else (0,) * len(shape)
-        new = tuple((o + e) % n if n > 1 else 0 for o, e, n in zip(old, eff, shape))
-        res = lazy.leaf(Mat(m.buf, m.shape, m.strides, m.offset, m.dtype, new if any(new) else None))
-    elif node.op == "scatter":
-        res = None
-    else:
-        args = []
-        for k, a in enumerate(node.args):
-            if type(a) is Node and not (node.op == "gather" and k == 0):
-                a = _roll_lazy(a, len(shape), eff, memo)
-                if a is None:
-                    break
-            args.append(a)
-        res = Node(node.op, tuple(args), node.in_dtypes, shape, node.dtype) if len(args) == len(node.args) else None
-    memo[node.nid] = res
-    return res
-
-
 def roll(a, shift, axis=None):
     """np.roll as an index transform: the result is a circularly shifted VIEW that fused kernels read
     in place (the VJP is the opposite shift, numpy_vjps.py:193)."""
@@ -1375,15 +1337,10 @@ def roll(a, shift, axis=None):
     shifts_in = (shift,) * len(axes) if isinstance(shift, numbers.Integral) else tuple(shift)
     if len(shifts_in) != len(axes):
         raise ValueError("shift and axis must have the same length")
-    if _ROLL_PUSH_NODES and a._node.mat is None and a.ndim and a.size:
-        if a._node.op == "full" or _pending_size(a._node, _ROLL_PUSH_NODES) <= _ROLL_PUSH_NODES:
-            vec = [0] * a.ndim
-            for s_, ax in zip(shifts_in, axes):
-                ax = _normalize_axis(ax, a.ndim)
-                vec[ax] = (vec[ax] + int(s_)) % a.shape[ax]
-            pushed = _roll_lazy(a._node, a.ndim, vec, {})
-            if pushed is not None:
-                return DeviceArray(pushed)
+    # (Pushing the shift down through a PENDING expression, so that two Jacobi sweeps share one kernel, was implemented
+    # and measured on the B200 in round 2: C4 at 20 steps 30.2 ms without, 30.6 / 36.0 / 35.6 / 38.7 ms with pending
+    # expressions of up to 8 / 12 / 24 / 40 nodes pushed - the fused kernels re-derive the inner sweep at five
+    # positions per output and become issue-bound.  Removed; a rolled operand is always a materialised view.)
     m = a._mat()
     shifts = list(m.shifts) if m.shifts is not None else [0] * a.ndim
     for s, ax in zip(shifts_in, axes):
@@ -2020,7 +1977,10 @@ def _basic_view(m: Mat, ops) -> Mat:
             shape.append(n)
             strides.append(m.strides[dim] * step)
             offset += start * m.strides[dim]
-    return Mat(m.buf, tuple(shape), tuple(strides), offset, m.dtype)
+    view = Mat(m.buf, tuple(shape), tuple(strides), offset, m.dtype, track=False)
+    if m.buf.pending:
+        lazy.note_view(m, view)        # a window on the result of a queued product: remember which part is wanted
+    return view
 
 
 def getitem(a: DeviceArray, idx):
@@ -2312,7 +2272,7 @@ def _gemm2d(a: DeviceArray, b: DeviceArray, out_dtype=None) -> DeviceArray:
     am, bm = _as_gemm_operand(a), _as_gemm_operand(b)
     out = Mat.empty((M, N), out_dtype, inexact=True)     # accumulation order differs from OpenBLAS'
     if M and N:
-        lazy.defer_gemm(out, am, bm, M, N, K)             # launched, grouped with its neighbours, when first needed
+        return DeviceArray(lazy.defer_gemm(out, am, bm, M, N, K))   # launched, grouped with its neighbours, when first needed
     return DeviceArray(lazy.leaf(out))
 
 

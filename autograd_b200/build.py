@@ -26,6 +26,10 @@ NVCC_FLAGS = [
 ]
 
 
+# extra compiler flags for experiments (e.g. B200AG_NVCC_EXTRA="-DB200AG_GEMM_STAGES=2"); part of the build stamp
+NVCC_FLAGS += os.environ.get("B200AG_NVCC_EXTRA", "").split()
+
+
 def _nvcc() -> str:
     cand = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "bin", "nvcc")
     return cand if os.path.exists(cand) else "nvcc"

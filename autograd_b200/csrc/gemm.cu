@@ -7,8 +7,8 @@
 // the accumulator is rounded once to the output dtype on store.
 //
 // Tiling: CTA tile 64×64×16, operand slabs staged in shared memory in their own dtype
-// ([row][k] with a 4-element pad: conflict-free fragment loads) through a 3-stage
-// cp.async ring, so two k-slabs are in flight while the current one is multiplied.
+// ([row][k] with a 4-element pad: conflict-free fragment loads) through a cp.async
+// ring (the next k-slab is in flight while the current one is multiplied).
 //
 // Launch shape: ONE grid covers a GROUP of up to 16 independent products (the four
 // gate products of an LSTM cell, examples/lstm.py:38-49, or the eight G·Bᵀ / Aᵀ·G
@@ -77,7 +77,12 @@ struct Tile {
   __device__ static int at(int row, int k) { return KMAJOR ? row * PITCH + k : k * PITCH + row; }
 };
 
-constexpr int NSTAGE = 3;   // k-slabs in flight per CTA (cp.async ring)
+#ifndef B200AG_GEMM_STAGES
+#define B200AG_GEMM_STAGES 2
+#endif
+// k-slabs per CTA in the cp.async ring.  Measured on the B200 (scripts/gpu_r2_stage_ab.sh): 2 stages (40 KB of shared
+// memory, more CTAs per SM) beat 3 stages (61 KB) on the LSTM config (104.6 vs 107.4 ms) and tie on C1 / C5.
+constexpr int NSTAGE = B200AG_GEMM_STAGES;
 
 template <typename TA, typename TB, int BM, int BN, bool AK, bool BKM>
 __host__ __device__ constexpr size_t stage_bytes() {
@@ -99,9 +104,9 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // One BM x BN output tile over k in [k_lo, k_hi): the accumulators stay in registers.  The operand slabs travel
-// global -> shared through a ring of NSTAGE cp.async stages: while slab kt is multiplied, slabs kt+1 and kt+2 are in
-// flight, so a CTA that is alone on its SM (small products, the tail of a wave) no longer pays one global-memory round
-// trip per 16 columns of K, and nothing is staged through registers.
+// global -> shared through a ring of NSTAGE cp.async stages: while slab kt is multiplied the following slab(s) are in
+// flight, and nothing is staged through registers (30 registers per thread less than a register-staged prefetch, so
+// more CTAs fit an SM).
 template <typename TA, typename TB, int BM, int BN, int WM, int WN, bool A_KMAJOR, bool B_KMAJOR>
 __device__ __forceinline__ void gemm_tile(const GemmArgs& g, int64_t m0, int64_t n0, int64_t bz, int64_t k_lo,
                                           int64_t k_hi, double (&acc)[WM / 8][WN / 8][2], unsigned char* smem) {
@@ -315,37 +320,43 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32) gemm_grouped_kerne
   cluster.sync();   // nobody leaves while its shared memory may still be read
 }
 
-// Second pass of a deep split: one CTA per output tile adds the S partial tiles in split order (every load of a thread
-// is independent of the others: one round trip) and rounds once to the output dtype.
+// Second pass of a deep split: CTA (tile, w) adds slot w of the tile's S partial tiles in split order - one output
+// element per thread, its S loads independent of each other - and rounds once to the output dtype.  TM*TN*2 CTAs per
+// tile: the pass is spread over the machine instead of serialised on a handful of CTAs.
 template <int BM, int BN, int WM, int WN>
 __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32) gemm_splitk_reduce_kernel(const __grid_constant__ GroupArgs ga) {
   constexpr int NT = (BM / WM) * (BN / WN) * 32;
   constexpr int TM = WM / 8, TN = WN / 8;
+  constexpr int SLOTS = TM * TN * 2;
   const int S = ga.splits;
+  const int tile_global = (int)blockIdx.x / SLOTS, w = (int)blockIdx.x - tile_global * SLOTS;
   int p = 0;
 #pragma unroll 1
-  while (p + 1 < ga.count && (int)blockIdx.x * S >= ga.g[p + 1].cta_start) ++p;
+  while (p + 1 < ga.count && tile_global * S >= ga.g[p + 1].cta_start) ++p;
   const GemmArgs& g = ga.g[p];
-  const int t = (int)blockIdx.x - g.cta_start / S;
+  const int t = tile_global - g.cta_start / S;
   const int tm = t / g.tiles_n, tn = t - tm * g.tiles_n;
-  const int64_t m0 = (int64_t)tm * BM, n0 = (int64_t)tn * BN;
-  const double* base = ga.ws + ((int64_t)g.cta_start + (int64_t)t * S) * (BM * BN) + threadIdx.x;
-  double acc[TM][TN][2];
+  const double* part = ga.ws + ((int64_t)g.cta_start + (int64_t)t * S) * (BM * BN) + (int64_t)w * NT + threadIdx.x;
+  double sum = 0.0;
+  int sidx = 0;
+  for (; sidx + 8 <= S; sidx += 8) {
+    double v[8];
 #pragma unroll
-  for (int i = 0; i < TM; ++i)
+    for (int u = 0; u < 8; ++u) v[u] = __ldcg(part + (int64_t)(sidx + u) * (BM * BN));
 #pragma unroll
-    for (int j = 0; j < TN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-  for (int sidx = 0; sidx < S; ++sidx) {
-    const double* part = base + (int64_t)sidx * (BM * BN);
-#pragma unroll
-    for (int i = 0; i < TM; ++i)
-#pragma unroll
-      for (int j = 0; j < TN; ++j) {
-        acc[i][j][0] += __ldcg(part + ((i * TN + j) * 2 + 0) * NT);
-        acc[i][j][1] += __ldcg(part + ((i * TN + j) * 2 + 1) * NT);
-      }
+    for (int u = 0; u < 8; ++u) sum += v[u];
   }
-  store_tile<BM, BN, WM, WN>(g, m0, n0, 0, acc);
+  for (; sidx < S; ++sidx) sum += __ldcg(part + (int64_t)sidx * (BM * BN));
+  const int tt = w & 1, j = (w >> 1) % TN, i = (w >> 1) / TN;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wm = warp / (BN / WN), wn = warp % (BN / WN);
+  const int64_t row = (int64_t)tm * BM + wm * WM + i * 8 + (lane >> 2);
+  const int64_t col = (int64_t)tn * BN + wn * WN + j * 8 + (lane & 3) * 2 + tt;
+  if (row < g.M && col < g.N) {
+    const int64_t off = row * g.c_rs + col * g.c_cs;
+    if (g.c_is_f32) ((float*)g.C)[off] = (float)sum;
+    else ((double*)g.C)[off] = sum;
+  }
 }
 
 int gemm_init() { return 0; }
@@ -451,7 +462,7 @@ static int launch_group_tiles(GroupArgs& ga) {
     if (b200ag_malloc((size_t)cta * BM * BN * sizeof(double), &ws)) return 1;
     ga.ws = (double*)ws;
     kern<<<(unsigned)cta, NT, smem, stream()>>>(ga);
-    gemm_splitk_reduce_kernel<BM, BN, WM, WN><<<(unsigned)(cta / best), NT, 0, stream()>>>(ga);
+    gemm_splitk_reduce_kernel<BM, BN, WM, WN><<<(unsigned)(cta / best) * (WM / 8) * (WN / 8) * 2, NT, 0, stream()>>>(ga);
     b200ag_free(ws);   // stream-ordered allocator: reused only by work enqueued after these kernels
     count_launch();
   } else if (best == 1) {

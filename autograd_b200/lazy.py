@@ -49,7 +49,7 @@ _ROW_TUNE = tuple(int(v) for v in __import__("os").environ.get("B200AG_ROW_TUNE"
     if __import__("os").environ.get("B200AG_ROW_TUNE") else None
 _GRID_MULT = int(__import__("os").environ.get("B200AG_GRID_MULT", "16"))
 EXPAND_MIN_COST = 12     # cheaper sub-expressions (a max, a compare) are recomputed in place: reading them back costs as much
-EXPAND_WORK = 3.0e7     # repeated op-units (elements x cost) that justify one extra launch, see materialize()
+EXPAND_WORK = float(__import__("os").environ.get("B200AG_EXPAND_WORK", "3.0e7"))     # repeated op-units (elements x cost) that justify one extra launch, see materialize()
 KEEP_COST = 96
 # Re-materialising nodes that keep being recomputed was measured on C4 (fluidsim): +1 % speed for +65 % retained
 # memory (the 200-step tape would no longer fit 180 GB), so it is off; the hook stays for experiments.
@@ -101,24 +101,70 @@ class Buffer:
 GEMM_QUEUE_MAX = 16
 DEFER_GEMMS = __import__("os").environ.get("B200AG_DEFER_GEMM", "1") != "0"
 _gemm_queue = []
+_gemm_by_buf = {}      # id(output Buffer) -> queued record
 
 
-def defer_gemm(out: "Mat", a: "Mat", b: "Mat", M: int, N: int, K: int) -> None:
-    """Queue out[M,N] = a[M,K] @ b[K,N] (2-D strided operands, float32/float64)."""
-    rec = (out, a, b, M, N, K, a.ptr, b.ptr)      # taking the operand addresses flushes what THEY still wait for
+class _QueuedGemm:
+    """out[M,N] = a[M,K] @ b[K,N], not launched yet.  While it waits, basic slices taken of the result are noted
+    (``note_view``): if, when it is finally launched, nobody can reach the full result any more (its array object is
+    gone) and every window on it is a column range ``[:, c0:c1]``, only those columns are computed - the VJP of
+    ``hstack((input, hiddens, ones)) @ W`` (numpy_vjps.py:615-624, :750-759) is G @ W^T over all 641 columns, of which
+    autograd slices out the 512 that belong to the traced ``hiddens``."""
+
+    __slots__ = ("out", "a", "b", "M", "N", "K", "a_ptr", "b_ptr", "node_ref", "lo", "hi", "all")
+
+    def __init__(self, out, a, b, M, N, K):
+        self.out, self.a, self.b, self.M, self.N, self.K = out, a, b, M, N, K
+        self.a_ptr, self.b_ptr = a.ptr, b.ptr      # taking the operand addresses launches what THEY still wait for
+        self.node_ref, self.lo, self.hi, self.all = None, None, None, False
+
+    def problem(self):
+        out, a, b = self.out, self.a, self.b
+        c0, n = 0, self.N
+        if SLICE_GEMMS and not self.all and self.lo is not None and self.node_ref is not None and self.node_ref() is None:
+            c0, n = self.lo, self.hi - self.lo
+        return (out.buf.ptr + (out.offset + c0 * out.strides[1]) * out.dtype.itemsize, out.dtype,
+                (out.strides[0], out.strides[1]), self.a_ptr, a.dtype, (a.strides[0], a.strides[1]),
+                self.b_ptr + c0 * b.strides[1] * b.dtype.itemsize, b.dtype, (b.strides[0], b.strides[1]), self.M, n, self.K)
+
+
+SLICE_GEMMS = __import__("os").environ.get("B200AG_SLICE_GEMM", "1") != "0"
+
+
+def defer_gemm(out: "Mat", a: "Mat", b: "Mat", M: int, N: int, K: int) -> "Node":
+    """Queue out[M,N] = a[M,K] @ b[K,N] (2-D strided operands, float32/float64); returns the leaf node of ``out``."""
+    rec = _QueuedGemm(out, a, b, M, N, K)
+    node = leaf(out)
     if not DEFER_GEMMS:
-        backend.get().gemm_grouped([_gemm_problem(rec)])
-        return
+        backend.get().gemm_grouped([rec.problem()])
+        return node
+    rec.node_ref = weakref.ref(node)
     out.buf.pending = True
     _gemm_queue.append(rec)
+    _gemm_by_buf[id(out.buf)] = rec
     if len(_gemm_queue) >= GEMM_QUEUE_MAX:
         flush_gemms()
+    return node
 
 
-def _gemm_problem(rec):
-    out, a, b, M, N, K, a_ptr, b_ptr = rec
-    return (out.buf.ptr + out.offset * out.dtype.itemsize, out.dtype, (out.strides[0], out.strides[1]),
-            a_ptr, a.dtype, (a.strides[0], a.strides[1]), b_ptr, b.dtype, (b.strides[0], b.strides[1]), M, N, K)
+def _demand_all(buf) -> None:
+    rec = _gemm_by_buf.get(id(buf))
+    if rec is not None:
+        rec.all = True
+
+
+def note_view(m: "Mat", view: "Mat") -> None:
+    """A basic slice ``view`` of ``m`` was taken while ``m``'s buffer is still waiting for a queued product."""
+    rec = _gemm_by_buf.get(id(m.buf))
+    if rec is None:
+        return
+    if m is rec.out and len(view.shape) == 2 and view.shape[0] == rec.M and view.strides == m.strides and view.shape[1] > 0:
+        c0 = view.offset - m.offset
+        if 0 <= c0 and c0 + view.shape[1] <= rec.N:
+            rec.lo = c0 if rec.lo is None else min(rec.lo, c0)
+            rec.hi = c0 + view.shape[1] if rec.hi is None else max(rec.hi, c0 + view.shape[1])
+            return
+    rec.all = True
 
 
 def flush_gemms() -> None:
@@ -127,9 +173,10 @@ def flush_gemms() -> None:
         return
     queue = _gemm_queue[:]
     del _gemm_queue[:]
+    _gemm_by_buf.clear()
     for rec in queue:
-        rec[0].buf.pending = False
-    backend.get().gemm_grouped([_gemm_problem(rec) for rec in queue])
+        rec.out.buf.pending = False
+    backend.get().gemm_grouped([rec.problem() for rec in queue])
 
 
 def flush_readers(buf) -> None:
@@ -165,7 +212,9 @@ class Mat:
 
     __slots__ = ("buf", "shape", "strides", "offset", "dtype", "shifts")
 
-    def __init__(self, buf, shape, strides, offset, dtype, shifts=None):
+    def __init__(self, buf, shape, strides, offset, dtype, shifts=None, track=True):
+        if track and buf.pending:
+            _demand_all(buf)      # an untracked new window on the output of a queued product: all of it may be read
         self.buf = buf
         self.shape = tuple(shape)
         self.strides = tuple(strides)

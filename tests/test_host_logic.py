@@ -177,46 +177,6 @@ def test_scatter_bodies_never_share_reciprocals(fake_dev):
         assert "body_exact" not in generated and "b200_div(" not in generated and " / " in generated
 
 
-def test_roll_push_down_is_exact_and_fuses_sweeps(fake_dev, monkeypatch):
-    """Experimental B200AG_ROLL_PUSH: np.roll of a small pending expression is pushed down to its leaves, so two
-    Jacobi sweeps (fluidsim.py:21-30) become one kernel; values and gradients stay bit-identical to the unfused path."""
-    import autograd_b200 as b200
-    from autograd import value_and_grad
-    from autograd_b200 import array as A
-
-    from examples import workloads as w
-
-    rows = cols = 16
-    p, s0, tg = w.fluid_data(rows, cols)
-    with b200.host_arrays():
-        want_v, want_g = value_and_grad(w.fluid_objective)(p, s0, tg, rows, cols, 2)
-    launches = {}
-    results = {}
-    for limit in (0, 12):
-        monkeypatch.setattr(A, "_ROLL_PUSH_NODES", limit)
-        n0 = fake_dev.launch_count()
-        v, g = value_and_grad(w.fluid_objective)(b200.asarray(p), b200.asarray(s0), b200.asarray(tg), rows, cols, 2)
-        results[limit] = (float(v.get()), g.get())
-        launches[limit] = fake_dev.launch_count() - n0
-    assert results[12][0] == results[0][0] == want_v
-    assert onp.array_equal(results[12][1], results[0][1])
-    cases.assert_close(results[12][1], want_g, cases.TOL_REDUCE, "fluid gradient with roll push-down")
-    assert launches[12] < launches[0]
-
-    # rolls of broadcast operands, negative shifts, several axes at once, a gather underneath
-    monkeypatch.setattr(A, "_ROLL_PUSH_NODES", 12)
-    r = onp.random.RandomState(5)
-    a, b = r.randn(6, 7), r.randn(1, 7)
-    idx = r.randint(0, 6, (6, 7))
-
-    def f(a, b, idx):
-        e = a * 2.0 + b
-        g = a[idx, idx % 7]
-        return onp.roll(e, (2, -3), axis=(0, 1)) + onp.roll(onp.roll(e, 1, 0), -1, 1) * onp.roll(g + b, 5, axis=1) + onp.roll(e, 4)
-
-    cases.check(f, a, b, idx, tol=0, what="roll push-down semantics")
-
-
 def test_lstm_gate_products_are_launched_as_groups(fake_dev):
     """np.dot on device operands is queued, not launched: the four gate products of an LSTM cell that share
     hstack(input, hiddens, 1) (examples/lstm.py:38-49) reach the GPU as ONE grouped launch, and so do the G.B^T / A^T.G
@@ -258,3 +218,52 @@ def test_deferred_products_see_the_operands_they_were_given(fake_dev):
     from autograd_b200 import lazy
 
     assert not lazy._gemm_queue and not f._mat().buf.pending
+
+
+def test_queued_products_compute_only_the_columns_that_can_still_be_read(fake_dev, monkeypatch):
+    """A queued product whose full result is unreachable by the time it is launched computes only the column range its
+    slices cover (the hidden-state columns of an LSTM cell's input gradient); anything else computes everything."""
+    import gc
+
+    import autograd_b200 as b200
+
+    r = onp.random.RandomState(9)
+    A, B = r.randn(12, 7), r.randn(7, 20)
+    a, b = b200.asarray(A), b200.asarray(B)
+    seen = []
+    orig = fake_dev.gemm_grouped
+    monkeypatch.setattr(fake_dev, "gemm_grouped", lambda probs: (seen.extend(p[10] for p in probs), orig(probs))[1])
+
+    c = onp.dot(a, b)
+    s1, s2 = c[:, 3:9], c[:, 6:11]
+    del c
+    gc.collect()
+    got1, got2 = s1.get(), s2.get()
+    assert seen == [8]                                     # columns 3..10 only
+    cases.assert_close(got1, (A @ B)[:, 3:9], cases.TOL_REDUCE, "slice 1 of a narrowed product")
+    cases.assert_close(got2, (A @ B)[:, 6:11], cases.TOL_REDUCE, "slice 2 of a narrowed product")
+
+    del seen[:]
+    c = onp.dot(a, b)
+    s = c[:, 3:9]
+    got = s.get()                                          # the full result is still reachable: all 20 columns
+    assert seen == [20]
+    cases.assert_close(c.get(), A @ B, cases.TOL_REDUCE, "full product")
+
+    del seen[:]
+    c = onp.dot(a, b)
+    s = c[:, 3:9][:, 1:3]                                  # a window on a window is not tracked: everything
+    del c
+    gc.collect()
+    cases.assert_close(s.get(), (A @ B)[:, 4:6], cases.TOL_REDUCE, "nested slice")
+    assert seen == [20]
+
+    del seen[:]
+    c = onp.dot(a, b)
+    s = c[2:5, :]                                          # a row range is not a column range: everything
+    t = c.T
+    del c
+    gc.collect()
+    cases.assert_close(s.get(), (A @ B)[2:5, :], cases.TOL_REDUCE, "row slice")
+    cases.assert_close(t.get(), (A @ B).T, cases.TOL_REDUCE, "transposed view")
+    assert seen == [20]
