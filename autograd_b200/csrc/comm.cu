@@ -34,6 +34,29 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   return v;
 }
 
+// Flag rounds are done by `world` threads in parallel - thread p signals / polls rank p - instead of one thread walking
+// all ranks: a release store to a remote GPU costs a NVLink round trip, eight of them in sequence were a third of
+// the 46 us an 8-rank allreduce took.
+__device__ __forceinline__ void signal_all(uint32_t* const* peer_flags, int offset, int world, uint32_t epoch) {
+  if ((int)threadIdx.x < world) {
+    __threadfence_system();     // everything this GPU wrote before (earlier kernels, the CTA barrier before this call)
+    st_release_sys(peer_flags[threadIdx.x] + offset, epoch);
+  }
+}
+// Every thread of the CTA gets the verdict; a timed-out wait sets *status (mapped host memory).
+__device__ __forceinline__ int wait_all(const uint32_t* my_flags, int world, uint32_t epoch, uint32_t* status, int good_in) {
+  int good = good_in;
+  if ((int)threadIdx.x < world && good) {
+    const uint32_t* f = my_flags + threadIdx.x;
+    long long spins = 0;
+    while (ld_acquire_sys(f) != epoch) {
+      if (++spins > 20000000LL) { good = 0; *status = 1; break; }   // a peer died or never arrived; do not hang the GPU
+      __nanosleep(32);
+    }
+  }
+  return __syncthreads_and(good);
+}
+
 struct AllreduceArgs {
   double* out;
   const double* peer_data[16];   // slot base of every rank's buffer (index = rank), as mapped in THIS process
@@ -56,26 +79,10 @@ __global__ void __launch_bounds__(256) peer_publish_kernel(double* slots, const 
 }
 
 __global__ void __launch_bounds__(256) peer_allreduce_kernel(AllreduceArgs a) {
-  __shared__ int ok;
   const uint32_t epoch = *a.epoch;           // same value on every rank: each call advances every counter once
   const int slot = epoch & 1;
-  if (threadIdx.x == 0) {
-    if (blockIdx.x == 0) {
-      __threadfence_system();                // this rank's vector (written by earlier kernels) is visible system-wide
-      for (int p = 0; p < a.world; ++p) st_release_sys(a.peer_flags[p] + slot * a.world + a.rank, epoch);
-    }
-    int good = 1;
-    for (int p = 0; p < a.world && good; ++p) {
-      const uint32_t* f = a.my_flags + slot * a.world + p;
-      long long spins = 0;
-      while (ld_acquire_sys(f) != epoch) {
-        if (++spins > 20000000LL) { good = 0; *a.status = 1; break; }   // ~ 2 s: a peer died; do not hang the GPU
-        __nanosleep(64);
-      }
-    }
-    ok = good;
-  }
-  __syncthreads();
+  if (blockIdx.x == 0) signal_all(a.peer_flags, slot * a.world + a.rank, a.world, epoch);
+  const int ok = wait_all(a.my_flags + slot * a.world, a.world, epoch, a.status, 1);
   if (ok) {
     // every thread owns ONE pair of doubles (grid sized to the vector): a single NVLink round trip, all peer loads
     // of a thread issued back to back, summed in rank order so every rank produces the same bits
@@ -120,28 +127,12 @@ __global__ void __launch_bounds__(256) peer_allreduce_kernel(AllreduceArgs a) {
 // moves 2 x (world-1)/world of the vector instead of (world-1) x the vector, and every rank receives the same bits.
 //   flags A: "my input is published"  flags B: "my reduced chunk is ready"  (both carry the epoch, double-slotted)
 __global__ void __launch_bounds__(256) peer_allreduce2_kernel(AllreduceArgs a, double* my_result) {
-  __shared__ int ok;
   __shared__ unsigned last;
   const uint32_t epoch = *a.epoch;
   const int slot = epoch & 1;
   uint32_t* flagsB_mine = a.my_flags + 256;          // B flags live 1024 bytes after the A flags
-  if (threadIdx.x == 0) {
-    if (blockIdx.x == 0) {
-      __threadfence_system();
-      for (int p = 0; p < a.world; ++p) st_release_sys(a.peer_flags[p] + slot * a.world + a.rank, epoch);
-    }
-    int good = 1;
-    for (int p = 0; p < a.world && good; ++p) {
-      const uint32_t* f = a.my_flags + slot * a.world + p;
-      long long spins = 0;
-      while (ld_acquire_sys(f) != epoch) {
-        if (++spins > 20000000LL) { good = 0; *a.status = 1; break; }
-        __nanosleep(64);
-      }
-    }
-    ok = good;
-  }
-  __syncthreads();
+  if (blockIdx.x == 0) signal_all(a.peer_flags, slot * a.world + a.rank, a.world, epoch);
+  int ok = wait_all(a.my_flags + slot * a.world, a.world, epoch, a.status, 1);
   const int64_t off = (int64_t)slot * a.slot_elems;
   const int64_t npairs = (a.n + 1) >> 1;                         // vectors are padded to an even length in the slots
   const int64_t chunk = (npairs + a.world - 1) / a.world;        // double2 pairs per rank
@@ -169,25 +160,12 @@ __global__ void __launch_bounds__(256) peer_allreduce2_kernel(AllreduceArgs a, d
     last = (done == gridDim.x - 1);
   }
   __syncthreads();
-  if (last && threadIdx.x == 0) {
-    a.epoch[2] = 0;
-    __threadfence_system();
-    for (int p = 0; p < a.world; ++p) st_release_sys(a.peer_flags[p] + 256 + slot * a.world + a.rank, epoch);
+  if (last) {
+    if (threadIdx.x == 0) a.epoch[2] = 0;
+    signal_all(a.peer_flags, 256 + slot * a.world + a.rank, a.world, epoch);
   }
   // gather: wait for every rank's reduced chunk, copy it out
-  if (threadIdx.x == 0) {
-    int good = ok;
-    for (int p = 0; p < a.world && good; ++p) {
-      const uint32_t* f = flagsB_mine + slot * a.world + p;
-      long long spins = 0;
-      while (ld_acquire_sys(f) != epoch) {
-        if (++spins > 20000000LL) { good = 0; *a.status = 1; break; }
-        __nanosleep(64);
-      }
-    }
-    ok = good;
-  }
-  __syncthreads();
+  ok = wait_all(flagsB_mine + slot * a.world, a.world, epoch, a.status, ok);
   if (ok) {
     for (int64_t i = tid; i < npairs; i += step) {
       const int p = (int)(i / chunk);
@@ -227,28 +205,12 @@ __device__ __forceinline__ void multimem_st(double* mc, double v) {
 
 __global__ void __launch_bounds__(256) nvls_allreduce_kernel(AllreduceArgs a, const double* mc_slots, double* mc_result,
                                                              const double* my_result) {
-  __shared__ int ok;
   __shared__ unsigned last;
   const uint32_t epoch = *a.epoch;
   const int slot = epoch & 1;
   uint32_t* flagsB_mine = a.my_flags + 256;
-  if (threadIdx.x == 0) {
-    if (blockIdx.x == 0) {
-      __threadfence_system();
-      for (int p = 0; p < a.world; ++p) st_release_sys(a.peer_flags[p] + slot * a.world + a.rank, epoch);
-    }
-    int good = 1;
-    for (int p = 0; p < a.world && good; ++p) {
-      const uint32_t* f = a.my_flags + slot * a.world + p;
-      long long spins = 0;
-      while (ld_acquire_sys(f) != epoch) {
-        if (++spins > 20000000LL) { good = 0; *a.status = 1; break; }
-        __nanosleep(64);
-      }
-    }
-    ok = good;
-  }
-  __syncthreads();
+  if (blockIdx.x == 0) signal_all(a.peer_flags, slot * a.world + a.rank, a.world, epoch);
+  int ok = wait_all(a.my_flags + slot * a.world, a.world, epoch, a.status, 1);
   const int64_t off = (int64_t)slot * a.slot_elems;
   const int64_t chunk = (a.n + a.world - 1) / a.world;
   const int64_t c_lo = (int64_t)a.rank * chunk, c_hi = min(c_lo + chunk, a.n);
@@ -264,24 +226,11 @@ __global__ void __launch_bounds__(256) nvls_allreduce_kernel(AllreduceArgs a, co
     last = (done == gridDim.x - 1);
   }
   __syncthreads();
-  if (last && threadIdx.x == 0) {
-    a.epoch[2] = 0;
-    __threadfence_system();
-    for (int p = 0; p < a.world; ++p) st_release_sys(a.peer_flags[p] + 256 + slot * a.world + a.rank, epoch);
+  if (last) {
+    if (threadIdx.x == 0) a.epoch[2] = 0;
+    signal_all(a.peer_flags, 256 + slot * a.world + a.rank, a.world, epoch);
   }
-  if (threadIdx.x == 0) {
-    int good = ok;
-    for (int p = 0; p < a.world && good; ++p) {
-      const uint32_t* f = flagsB_mine + slot * a.world + p;
-      long long spins = 0;
-      while (ld_acquire_sys(f) != epoch) {
-        if (++spins > 20000000LL) { good = 0; *a.status = 1; break; }
-        __nanosleep(64);
-      }
-    }
-    ok = good;
-  }
-  __syncthreads();
+  ok = wait_all(flagsB_mine + slot * a.world, a.world, epoch, a.status, ok);
   if (ok) {
     for (int64_t i = tid; i < a.n; i += step) a.out[i] = __ldcv(my_result + i);     // local HBM: every chunk was broadcast here
   }
@@ -342,31 +291,17 @@ __global__ void __launch_bounds__(256) peer_push_kernel(PushArgs a) {
     last = (done == gridDim.x - 1);
   }
   __syncthreads();
-  if (last && threadIdx.x == 0) {
-    a.epoch[4] = 0;
-    __threadfence_system();
-    for (int p = 0; p < a.world; ++p) st_release_sys(a.peer_flags[p] + 384 + par * a.world + a.rank, epoch);
+  if (last) {
+    if (threadIdx.x == 0) a.epoch[4] = 0;
+    signal_all(a.peer_flags, 384 + par * a.world + a.rank, a.world, epoch);
   }
 }
 
 __global__ void __launch_bounds__(256) peer_push_reduce_kernel(PushArgs a) {
-  __shared__ int ok;
   __shared__ unsigned last;
   const uint32_t epoch = *a.epoch;
   const int par = epoch & 1;
-  if (threadIdx.x == 0) {
-    int good = 1;
-    for (int p = 0; p < a.world && good; ++p) {
-      const uint32_t* f = a.my_flags + 384 + par * a.world + p;
-      long long spins = 0;
-      while (ld_acquire_sys(f) != epoch) {
-        if (++spins > 20000000LL) { good = 0; *a.status = 1; break; }
-        __nanosleep(32);
-      }
-    }
-    ok = good;
-  }
-  __syncthreads();
+  const int ok = wait_all(a.my_flags + 384 + par * a.world, a.world, epoch, a.status, 1);
   if (ok) {
     const double* base = a.my_inbox + (int64_t)par * a.world * a.slot_elems;
     const int64_t npairs = a.n >> 1;

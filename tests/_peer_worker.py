@@ -126,7 +126,18 @@ t_peer = timeit(lambda: dist.allreduce_sum_(y))
 dist._peer["ready"] = False
 t_nccl = timeit(lambda: dist.allreduce_sum_(y))
 dist._peer["ready"] = True
+# latency against message size (pull / NVLS / NCCL): what a split of the gradient into an early and a late message could hide
+sizes = {}
+for n_el in (2048, 22000, 178110):
+    yy = b200.asarray(all_vecs[rank][:n_el].copy()).materialize()
+    row = {}
+    for name, mode in (("pull", 1), ("push", 3)) + ((("nvls", 4),) if NVLS else ()):
+        be.comm_mode(mode)
+        row[name] = timeit(lambda: dist.allreduce_sum_(yy), reps=100)
+    be.comm_mode(0)
+    sizes[n_el] = row
 if rank == 0:
+    print("allreduce latency by size (us):", {k: {a: round(b, 1) for a, b in v.items()} for k, v in sizes.items()}, flush=True)
     print(f"peer-memory allreduce 1.42 MB x{world}: one-shot pull {t_one:.1f} us, two-shot {t_two:.1f} us, push {t_push:.1f} us, automatic {t_peer:.1f} us/call; "
           f"NVLS multimem {'%.1f us' % t_nvls if t_nvls is not None else 'n/a'}; NCCL via torch: {t_nccl:.1f} us/call", flush=True)
 print(f"rank {rank}/{world} peer allreduce ok", flush=True)
