@@ -12,6 +12,8 @@
 // float32 keeps the simple CUDA-core kernels (no config uses it).
 #include <cuda_pipeline.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b200ag {
@@ -22,6 +24,7 @@ int conv2d_direct_try(double* out, const double* A, const double* B, int64_t N, 
 int conv2d_wgrad_direct_try(double* dB, const double* A, const double* G, int64_t N, int C, int H, int W, int F, int kh,
                             int kw, int Ho, int Wo);
 int g_conv_direct = 1;   // b200ag_conv_mode: 0 = implicit-GEMM DMMA kernels only
+static int g_conv_direct_cmax = []() { const char* e = getenv("B200AG_CONV_DIRECT_CMAX"); return e ? atoi(e) : 4; }();
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -390,7 +393,11 @@ int b200ag_conv2d(void* out, const void* A, const void* B, int dtype, int64_t N,
   }
   int64_t total = N * F * Ho * Wo;
   if (total == 0) return 0;
-  if (dtype == B200AG_F64 && g_conv_direct && F <= 8 && C <= 4) {
+  // few OUTPUT channels: the register-tiled direct kernel.  Forward layers qualify with few input channels (conv1 of
+  // LeNet: C = 1); the 'full' correlation that is a layer's INPUT gradient (mode 1: conv2's dX has C = 16 cotangent
+  // channels, F = 6) qualifies up to 16 because the direct kernel skips the taps that fall into the zero padding,
+  // which the implicit-GEMM formulation multiplies (2.25x the true flops for a 5x5 filter over an 8x8 map).
+  if (dtype == B200AG_F64 && g_conv_direct && F <= 8 && (C <= 4 || (mode == 1 && C <= (g_conv_direct_cmax)))) {
     int rc = conv2d_direct_try((double*)out, (const double*)A, (const double*)B, N, (int)C, (int)H, (int)W, (int)F, (int)kh,
                                (int)kw, (int)Ho, (int)Wo, (int)py, (int)px, flip);
     if (rc != 2) return rc;

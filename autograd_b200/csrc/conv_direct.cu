@@ -82,6 +82,12 @@ __global__ void __launch_bounds__(192) conv2d_direct_kernel(DirectArgs g) {
       for (int f = 0; f < F; ++f)
 #pragma unroll
         for (int t = 0; t < TH; ++t) acc[f][t] = 0.0;
+      // filter rows whose whole TH-row window lies in the zero padding contribute nothing ('full' mode: the input
+      // gradient of a layer): row i reads input rows y0 + i - py .. y0 + i - py + TH - 1
+      int i_lo = g.py - y0 - (TH - 1);
+      if (i_lo < 0) i_lo = 0;
+      int i_hi = g.H - 1 + g.py - y0;
+      if (i_hi > g.kh - 1) i_hi = g.kh - 1;
       for (int c = 0; c < g.C; ++c) {
         const double* plane = img + c * g.H * g.W;
 #pragma unroll
@@ -92,10 +98,10 @@ __global__ void __launch_bounds__(192) conv2d_direct_kernel(DirectArgs g) {
           double prev[TH];                            // sliding window over the rows: input rows y0+i-py .. +TH-1
 #pragma unroll
           for (int t = 0; t < TH; ++t) {
-            const int yy = y0 + t - g.py;
+            const int yy = y0 + t + i_lo - g.py;
             prev[t] = (yy >= 0 && yy < g.H) ? plane[yy * g.W + xx] : 0.0;
           }
-          for (int i = 0; i < g.kh; ++i) {
+          for (int i = i_lo; i <= i_hi; ++i) {
             const double* wv = wcol + i * F;
             double w[F];
             if constexpr (F % 2 == 0) {                // [i][f] rows are 16-byte aligned: 128-bit broadcast loads

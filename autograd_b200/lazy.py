@@ -57,6 +57,7 @@ REUSE_LIMIT = int(__import__("os").environ.get("B200AG_REUSE_LIMIT", str(1 << 30
 # B200AG_EXACT=1 keeps one IEEE rounding per recorded ufunc call in every generated kernel (no contraction anywhere);
 # by default only values that are still bit-reproducible against NumPy are computed that way (Buffer.inexact).
 RELAXED = __import__("os").environ.get("B200AG_EXACT", "0") in ("", "0")
+UNROLL_WINDOWS = __import__("os").environ.get("B200AG_UNROLL_WINDOWS", "1") != "0"
 # Hard caps that force a flush while a graph is still being built.
 MAX_NODES = 1500
 MAX_LEAVES = 48
@@ -431,10 +432,10 @@ class Program:
     """Structural description of one fused kernel; ``key`` identifies the generated code."""
 
     __slots__ = ("instrs", "leaves", "consts", "outputs", "ndim", "idx64", "vec", "key", "cost", "tables", "mode", "bx",
-                 "bdims", "share", "relax")
+                 "bdims", "share", "relax", "unroll")
 
     def __init__(self, instrs, leaves, consts, outputs, ndim, idx64, vec, cost, tables=(), mode="flat", bx=256,
-                 bdims=None, share=None, relax=()):
+                 bdims=None, share=None, relax=(), unroll=()):
         self.instrs = instrs      # tuple of (op, in_dtype chars, out dtype char, arg refs)
         self.leaves = leaves      # tuple of (dtype char, layout class 'C'|'S'|'G', has_shift)
         self.consts = consts      # tuple of C scalar kinds: 'd' | 'q' | '?'
@@ -456,13 +457,23 @@ class Program:
         # (downstream of a Buffer.inexact operand or of a transcendental function) and which the generated code may
         # therefore contract into an FMA / compute with a shared reciprocal (codegen.relax_plan)
         self.relax = relax
-        self.key = (instrs, leaves, consts, outputs, ndim, idx64, vec, tables, mode, bx, bdims, share, relax)
+        # flat kernels over window layouts: iteration dims of tiny extent (the 2 x 2 of a pooling window) that one THREAD
+        # walks itself, fully unrolled, instead of one thread per element: operands that broadcast along those dims
+        # (the pooled cotangent, the window maximum, the tie count) are then loaded and computed once per window - the
+        # compiler merges the identical sub-expressions of the unrolled bodies - and the coordinate split is done once
+        self.unroll = unroll
+        self.key = (instrs, leaves, consts, outputs, ndim, idx64, vec, tables, mode, bx, bdims, share, relax, unroll)
 
     def launch_config(self, sm_count):
         block = 256
         return block, block * self.vec, sm_count * 16
 
     def grid(self, n, dims, sm_count):
+        if self.unroll:
+            per_thread = 1
+            for d in self.unroll:
+                per_thread *= dims[d]
+            n = n // per_thread
         per_block = 256 * self.vec
         max_grid = sm_count * _GRID_MULT
         if self.mode == "row":
@@ -730,8 +741,28 @@ def materialize(root: Node, store_root: bool = True) -> Mat:
     instrs = tuple(instrs)
     inexact = codegen.taint(instrs, leaf_taint, table_taint)
     relax = codegen.relax_plan(instrs, inexact) if RELAXED else ()
+    unroll = ()
+    if UNROLL_WINDOWS and mode == "flat" and g_layouts and not table_descs and n >= (1 << 20) and len(dims) >= 2:
+        # dims of extent <= 4 - neither the outermost nor the INNERMOST one, whose consecutive elements belong to consecutive
+        # threads - along which a real array operand (one that varies along at least two other dims: the pooled cotangent,
+        # the window maximum, not a bias) broadcasts: that operand's loads and everything computed from it alone is what
+        # the unrolling shares.  Measured on the B200 (scripts/gpu_r2_unroll.sh): the 226 M-element max-pool VJP of C5
+        # 1.59 -> 1.28 ms with the window rows unrolled; unrolling the innermost dim instead breaks up the coalesced /
+        # vector accesses and loses (pooled-size kernels 0.14 -> 0.26 ms), so it is never picked.
+        picked, per_thread = [], 1
+        shifted = any(any(leaf_ptrs[slot][2]) for slot in g_slots)
+        for d in range(len(dims) - 2, 0, -1):
+            if shifted:
+                break
+            if dims[d] <= 4 and per_thread * dims[d] <= 8 and any(
+                    leaf_ptrs[slot][1][d] == 0 and sum(1 for st in leaf_ptrs[slot][1] if st) >= 2 for slot in g_slots):
+                picked.append(d)
+                per_thread *= dims[d]
+        if per_thread >= 2 and total_cost >= 8:
+            unroll = tuple(sorted(picked))
+            vec = 1
     program = Program(instrs, tuple(leaf_descs), tuple(const_kinds), outputs, ndim, idx64, vec, total_cost,
-                      tuple(table_descs), mode, bx, bdims, share, relax)
+                      tuple(table_descs), mode, bx, bdims, share, relax, unroll)
     out_mats = [Mat.empty(root_shape, o.dtype, inexact=inexact[j] and o.dtype.kind == "f") for o, (j, _) in zip(outs, outputs)]
     backend.get().run_program(program, (leaf_ptrs, dims, table_rt), const_values, [m.ptr for m in out_mats], n)
     if not store_root and root.op == "scatter":

@@ -316,21 +316,22 @@ class FakeBackend:
         the CPU suite: the aliased value must be the SAME BITS (signed zeros included; NaNs compare equal)."""
         from autograd_b200 import codegen
 
-        rep, sgn, _den_of, _den_uses = codegen._value_numbers(program.instrs)
+        rep, scl, _den_of, _den_uses, _pure = codegen._value_numbers(program.instrs, getattr(program, "relax", ()))
         for j, r in enumerate(rep):
             if r == j:
                 continue
             a = np.asarray(vals[j])
             b = np.asarray(vals[r])
-            if sgn[j] < 0:
-                b = -b
+            ratio = scl[j] / scl[r]       # +-1 on exact values; +-2^k on values the generator may rescale (exact too)
+            if ratio != 1.0:
+                b = b * b.dtype.type(ratio) if b.dtype.kind == "f" else -b
             a, b = np.broadcast_arrays(a, b)
             if a.dtype.kind == "f":
                 nan = np.isnan(a)
                 assert np.array_equal(nan, np.isnan(b)), f"value numbering: NaN pattern of instr {j} vs {r} differs"
                 ai = np.where(nan, 0, a).view(f"i{a.dtype.itemsize}")
                 bi = np.where(nan, 0, b).view(f"i{b.dtype.itemsize}")
-                assert np.array_equal(ai, bi), f"value numbering: instr {j} ({program.instrs[j][0]}) is not bit-identical to {'-' if sgn[j] < 0 else ''}v{r}"
+                assert np.array_equal(ai, bi), f"value numbering: instr {j} ({program.instrs[j][0]}) is not bit-identical to {ratio} * v{r}"
             else:
                 assert np.array_equal(a, b), f"value numbering: instr {j} differs from v{r}"
 

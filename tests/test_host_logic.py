@@ -98,7 +98,7 @@ def test_c2_kernel_shares_reciprocals_and_prefetches(fake_dev):
     prog = max(fake_dev.programs.values(), key=lambda p: len(p.instrs))
     ops = [i[0] for i in prog.instrs]
     assert len(ops) > 300 and ops.count("divide") > 30
-    rep, sgn, den_of, den_uses = codegen._value_numbers(prog.instrs)
+    rep, sgn, den_of, den_uses, _pure = codegen._value_numbers(prog.instrs)
     assert sum(1 for j, r in enumerate(rep) if r == j) < 0.6 * len(ops)          # > 40 % of the body is redundant
     shared = {d: c for d, c in den_uses.items() if c >= 2}
     assert 2 <= len(shared) <= 4 and sum(shared.values()) >= 18
@@ -125,10 +125,15 @@ def test_c2_kernel_shares_reciprocals_and_prefetches(fake_dev):
     assert not inexact[0] and sum(inexact) > 0.95 * len(ops)            # 2*x is exact, exp(-2x) and all after it are not
     assert prog.relax == codegen.relax_plan(prog.instrs, inexact) and len(prog.relax) > 60
     src, body = variant(prog.relax)
-    assert body.count("__fma_rn(") >= 40 and "b200_div(" not in body
+    assert body.count("__fma_rn(") >= 30 and "b200_div(" not in body
     # the denominators are y**2, y**4, y**8, y**16 of ONE y = 1 + exp(-2x): a single Newton-refined reciprocal, the others
     # are products of it; every denominator (and factor) is range-checked once
     assert body.count("b200_rcp(") == 1 and 4 <= body.count("b200_den_ok(") <= 6
+    # factors of +-2^k (the 2.0 of d/dx exp(-2x), every `2 * y * dy`) are not multiplied out: they ride on FMAs or end up
+    # in the single scale applied to the result
+    rep_r, scl_r, _d, _u, pure = codegen._value_numbers(prog.instrs, prog.relax)
+    assert len(pure) > 100 and sum(1 for j, c in enumerate(scl_r) if abs(c) not in (1.0,)) > 50
+    assert sum(1 for line in body.splitlines() if " * " in line or "__fma_rn" in line or " + " in line or " - " in line) < 175
     assert "body_exact(" in body and "__noinline__ Outs body_exact" in src
 
 
@@ -153,7 +158,7 @@ def test_exact_values_are_never_contracted(fake_dev):
     y = (a * s + c)
     y.get()
     prog = max(fake_dev.programs.values(), key=lambda p: len(p.instrs))
-    assert len(prog.relax) == 1
+    assert len(prog.relax) == 2          # the product and the sum that absorbs it
     src, _n, _ = codegen.generate(prog)
     assert "__fma_rn(" in src[src.index("void body("):]
     assert y._mat().buf.inexact and not (a * b)._mat().buf.inexact
