@@ -114,7 +114,7 @@ class DeviceArray:
     def materialize(self):
         """Force evaluation of pending lazy work behind this array (no host sync)."""
         if self._mat().buf.pending:
-            lazy.flush_gemms()
+            lazy.flush_deferred()
         return self
 
     def get(self, out=None) -> np.ndarray:

@@ -126,7 +126,7 @@ class CudaBackend:
     def synchronize(self) -> None:
         from . import lazy
 
-        lazy.flush_gemms()       # queued contractions are work the caller expects to be done after a synchronisation
+        lazy.flush_deferred()       # queued contractions are work the caller expects to be done after a synchronisation
         self._check(self._lib.b200ag_synchronize())
         self._check_index_error()
 
@@ -219,14 +219,14 @@ class CudaBackend:
     def graph_begin(self) -> None:
         from . import lazy
 
-        lazy.flush_gemms()       # work queued before the capture must not be recorded into it
+        lazy.flush_deferred()       # work queued before the capture must not be recorded into it
         self._check(self._lib.b200ag_graph_begin())
         self.capturing = True
 
     def graph_end(self) -> int:
         from . import lazy
 
-        lazy.flush_gemms()       # everything recorded so far belongs to this graph
+        lazy.flush_deferred()       # everything recorded so far belongs to this graph
         p = C.c_void_p()
         self.capturing = False
         self._check(self._lib.b200ag_graph_end(C.byref(p)))
@@ -413,7 +413,9 @@ def set_backend(b) -> None:
         from . import lazy
 
         try:
-            lazy.flush_gemms()           # queued work belongs to the backend that is being replaced
+            lazy.flush_deferred()           # queued work belongs to the backend that is being replaced
         except Exception:
             del lazy._gemm_queue[:]
+            lazy._gemm_by_buf.clear()
+            lazy._scatter_queue.clear()
     _current = b

@@ -184,6 +184,8 @@ def flush_readers(buf) -> None:
     """Compute every pending expression that reads ``buf`` (called before an in-place write to it)."""
     if _gemm_queue:
         flush_gemms()          # a queued product may read the buffer that is about to change
+    if _scatter_queue:
+        flush_scatters(reading=buf)
     readers = buf.readers
     if not readers:
         return
@@ -228,7 +230,7 @@ class Mat:
         """Device address of the first element.  Every kernel launch takes its operand addresses from here, so this
         is also where a deferred contraction that still has to produce the payload is launched."""
         if self.buf.pending:
-            flush_gemms()
+            flush_deferred()
         return self.buf.ptr + self.offset * self.dtype.itemsize
 
     @property
@@ -404,16 +406,70 @@ def make_gather(table: Node, idx_nodes):
     return node
 
 
+# np.add.at calls are QUEUED per target and launched together: the VJP of a bilinear interpolation
+# `(1-rw)*((1-bw)*f[l,t] + bw*f[l,b]) + rw*(...)` (examples/fluidsim/fluidsim.py:45-68) is four np.add.at calls into one
+# accumulator (core.py:191-203 -> numpy_vjps.py:946-948) whose index and weight expressions share nearly everything: as
+# one kernel they read the cotangent and the velocity fields once and issue four atomics per element.
+DEFER_SCATTER = __import__("os").environ.get("B200AG_DEFER_SCATTER", "1") != "0"
+SCATTER_GROUP_MAX = 8
+_scatter_queue = {}     # (id(buffer), offset, shape) -> [target Mat, shared table leaf, [scatter nodes], {id(buffer) read}]
+
+
 def scatter_add(target: Mat, idx_nodes, value):
-    """``np.add.at(target, (idx0, idx1, ...), value)`` with every axis indexed, as ONE generated kernel: index
-    and value expressions are evaluated in registers and accumulated with FP64 atomics (RED.ADD in L2), so
-    neither the index arrays nor the cotangent being scattered are ever written to HBM
-    (VJP of integer-array ``__getitem__``, autograd/numpy/numpy_vjps.py:941-954)."""
-    args = (leaf(target),) + tuple(idx_nodes) + (value,)
+    """``np.add.at(target, (idx0, idx1, ...), value)`` with every axis indexed, as a generated kernel: index and value
+    expressions are evaluated in registers and accumulated with FP64 atomics (RED.ADD in L2), so neither the index
+    arrays nor the cotangent being scattered are ever written to HBM (VJP of integer-array ``__getitem__``,
+    autograd/numpy/numpy_vjps.py:941-954).  The launch is deferred until the target is read (or written by something
+    else), so consecutive scatters into one target share a kernel."""
+    key = (id(target.buf), target.offset, target.shape)
+    rec = _scatter_queue.get(key) if DEFER_SCATTER else None
+    table = rec[1] if rec is not None else leaf(target)
+    args = (table,) + tuple(idx_nodes) + (value,)
     shapes = [a.shape for a in args[1:] if type(a) is Node]
     shape = broadcast_shapes(shapes) if shapes else ()
     root = Node("scatter", args, (target.dtype,) + (I64,) * len(idx_nodes) + (target.dtype,), shape, target.dtype)
+    if target.buf.readers is not None:
+        target.buf.readers.discard(root)        # it WRITES the target; as a "reader" it would be flushed by its own group
+    target.buf.inexact = True                   # atomic accumulation order is not NumPy's sequential order
+    if not DEFER_SCATTER:
+        materialize(root, store_root=False)
+        return
+    if rec is not None and (rec[2][0].shape != shape or len(rec[2]) >= SCATTER_GROUP_MAX):
+        _flush_scatter_group(key)
+        rec = None
+        root.args = (leaf(target),) + root.args[1:]
+        if target.buf.readers is not None:
+            target.buf.readers.discard(root)
+    if rec is None:
+        rec = _scatter_queue[key] = [target, root.args[0], [], set()]
+    rec[2].append(root)
+    _, leaves_ = _collect([a for a in args[1:] if type(a) is Node])
+    rec[3].update(id(ln.mat.buf) for ln in leaves_)
+    target.buf.pending = True
+
+
+def _flush_scatter_group(key) -> None:
+    target, _table, nodes, _reads = _scatter_queue.pop(key)
+    if not any(k[0] == key[0] for k in _scatter_queue):
+        target.buf.pending = bool(_gemm_by_buf.get(key[0]))
+    root = nodes[0]
+    for nd_ in nodes[1:]:                        # a value that depends on every scatter of the group; never stored
+        root = Node("add", (root, nd_), (target.dtype, target.dtype), root.shape, target.dtype)
     materialize(root, store_root=False)
+
+
+def flush_scatters(reading=None) -> None:
+    """Launch the queued np.add.at groups - all of them, or only those whose index / value expressions read ``reading``
+    (a Buffer about to be written in place)."""
+    for key in list(_scatter_queue):
+        if key in _scatter_queue and (reading is None or id(reading) in _scatter_queue[key][3]):
+            _flush_scatter_group(key)
+
+
+def flush_deferred() -> None:
+    """Everything that was queued instead of launched: contractions first (a scatter may accumulate into a product)."""
+    flush_gemms()
+    flush_scatters()
 
 
 def _maybe_flush_growing(node):
@@ -765,8 +821,6 @@ def materialize(root: Node, store_root: bool = True) -> Mat:
                       tuple(table_descs), mode, bx, bdims, share, relax, unroll)
     out_mats = [Mat.empty(root_shape, o.dtype, inexact=inexact[j] and o.dtype.kind == "f") for o, (j, _) in zip(outs, outputs)]
     backend.get().run_program(program, (leaf_ptrs, dims, table_rt), const_values, [m.ptr for m in out_mats], n)
-    if not store_root and root.op == "scatter":
-        root.args[0].mat.buf.inexact = True     # atomic accumulation order is not NumPy's sequential order
     for o, m in zip(outs, out_mats):
         o.mat = m
     if not store_root:

@@ -165,7 +165,7 @@ class FakeBackend:
     def synchronize(self):
         from autograd_b200 import lazy
 
-        lazy.flush_gemms()
+        lazy.flush_deferred()
 
     def launch_count(self):
         return self._launches

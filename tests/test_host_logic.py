@@ -175,6 +175,7 @@ def test_scatter_bodies_never_share_reciprocals(fake_dev):
     i, j = b200.asarray(r.randint(0, 8, 50)), b200.asarray(r.randint(0, 8, 50))
     a, d = b200.asarray(r.randn(50)), b200.asarray(r.rand(50) + 1.0)
     onp.add.at(t, (i, j), a / d + (a * a) / d)
+    t.get()                                                   # np.add.at is queued: reading the target launches it
     progs = [p for p in fake_dev.programs.values() if any(ins[0] == "scatter" for ins in p.instrs)]
     assert progs
     for p in progs:
@@ -272,3 +273,37 @@ def test_queued_products_compute_only_the_columns_that_can_still_be_read(fake_de
     cases.assert_close(s.get(), (A @ B)[2:5, :], cases.TOL_REDUCE, "row slice")
     cases.assert_close(t.get(), (A @ B).T, cases.TOL_REDUCE, "transposed view")
     assert seen == [20]
+
+
+def test_consecutive_add_at_into_one_target_share_a_kernel(fake_dev):
+    """np.add.at calls are queued per target: the four corner scatters of a bilinear-interpolation VJP become one
+    generated kernel; reading the target, or writing an operand of a queued scatter, launches the queue first."""
+    import autograd_b200 as b200
+
+    r = onp.random.RandomState(2)
+    n = 5000
+    i0, j0 = r.randint(0, 31, n), r.randint(0, 31, n)
+    g, wgt = r.randn(n), r.rand(n)
+    want = onp.zeros((32, 32))
+    for di, dj, ww in ((0, 0, (1 - wgt)), (0, 1, wgt), (1, 0, wgt * 0.5), (1, 1, (1 - wgt) * 0.5)):
+        onp.add.at(want, (i0 + di, j0 + dj), g * ww)
+    t = b200.array.zeros((32, 32)).copy()
+    di0, dj0, dg, dw = (b200.asarray(a) for a in (i0, j0, g, wgt))
+    fake_dev.programs.clear()
+    n0 = fake_dev.launch_count()
+    for di, dj, ww in ((0, 0, (1 - dw)), (0, 1, dw), (1, 0, dw * 0.5), (1, 1, (1 - dw) * 0.5)):
+        onp.add.at(t, (di0 + di, dj0 + dj), dg * ww)
+    assert fake_dev.launch_count() == n0                       # nothing launched yet
+    got = t.get()
+    assert fake_dev.launch_count() == n0 + 1                   # one kernel for the four scatters
+    prog = [p for p in fake_dev.programs.values() if any(ins[0] == "scatter" for ins in p.instrs)]
+    assert len(prog) == 1 and sum(1 for ins in prog[0].instrs if ins[0] == "scatter") == 4 and len(prog[0].tables) == 1
+    cases.assert_close(got, want, cases.TOL_REDUCE, "grouped np.add.at")
+    # a queued scatter sees the operand values of the time it was issued
+    t2 = b200.array.zeros((32, 32)).copy()
+    v = b200.asarray(g.copy())
+    onp.add.at(t2, (di0, dj0), v * 2.0)
+    v[0] = 1e6                                                 # in-place write to an operand: the queue runs first
+    want2 = onp.zeros((32, 32))
+    onp.add.at(want2, (i0, j0), g * 2.0)
+    cases.assert_close(t2.get(), want2, cases.TOL_REDUCE, "queued np.add.at before an operand write")
