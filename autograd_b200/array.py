@@ -452,7 +452,15 @@ class DeviceArray:
         """Make sure this handle is backed by real memory that may be written in place."""
         node = self._node
         if node.mat is None:
-            lazy.materialize(node)
+            if node.op == "full" and isinstance(node.args[0], Const) and node.args[0].value == 0 and prod(node.shape) > 0 \
+                    and str(node.args[0].value)[0] != "-":
+                # the zero accumulator of a sparse cotangent (vs.zeros() handed to np.add.at, core.py:212-215): a memset at
+                # copy-engine speed instead of a generated fill kernel
+                zm = Mat.empty(node.shape, node.dtype)
+                backend.get().memset(zm.ptr, 0, zm.buf.nbytes)
+                node.mat, node.args, node.cost, node.lo, node.leafset = zm, (), 0, node.nid, frozenset((node.nid,))
+            else:
+                lazy.materialize(node)
         m = node.mat
         lazy.flush_readers(m.buf)     # pending expressions that read this buffer must see the OLD contents
         m.buf.version += 1            # an in-place write follows: memoised copies of the old contents are stale

@@ -58,6 +58,8 @@ REUSE_LIMIT = int(__import__("os").environ.get("B200AG_REUSE_LIMIT", str(1 << 30
 # by default only values that are still bit-reproducible against NumPy are computed that way (Buffer.inexact).
 RELAXED = __import__("os").environ.get("B200AG_EXACT", "0") in ("", "0")
 UNROLL_WINDOWS = __import__("os").environ.get("B200AG_UNROLL_WINDOWS", "1") != "0"
+KEEP_WIDE = __import__("os").environ.get("B200AG_KEEP_WIDE", "1") != "0"
+KEEP_WIDE_USES = int(__import__("os").environ.get("B200AG_KEEP_WIDE_USES", "1"))
 # Hard caps that force a flush while a graph is still being built.
 MAX_NODES = 1500
 MAX_LEAVES = 48
@@ -633,10 +635,29 @@ def materialize(root: Node, store_root: bool = True) -> Mat:
     # interior nodes that Python still holds and that are costly to recompute become extra outputs
     # (b) or that have already been recomputed REUSE_LIMIT times (a loop keeps coming back to them: the
     #     Jacobi right-hand side of fluidsim.py:21-30 is read by all ten sweeps)
+    # (c) or that are being recomputed a second time although reading them back would move FEWER bytes than their
+    #     inputs do: the Jacobi right-hand side `div` above is two shifted reads each of vx and vy (16 B per cell) where
+    #     the stored value is 8 B - kept from the second sweep on, the other eight read one array instead of two.
+    #     Values whose inputs are no wider than themselves (the advection weights: one velocity field + a broadcast
+    #     arange) stay recomputed, so nothing extra is retained by the tape.
     outs = [root] if store_root else []
+    leaf_by_nid = None
+    has_tables = any(nd_.op in ("gather", "scatter") for nd_ in order)   # (c) is for stencil loops, not for lookups
     for nd_ in order:
         if nd_ is not root and nd_.nhandles > 0 and nd_.shape == root_shape and nd_.op not in ("full", "scatter"):
-            if nd_.cost >= KEEP_COST or (nd_.uses >= REUSE_LIMIT and len(nd_.leafset) > 1):
+            keep = nd_.cost >= KEEP_COST or (nd_.uses >= REUSE_LIMIT and len(nd_.leafset) > 1)
+            if not keep and KEEP_WIDE and not has_tables and nd_.uses >= KEEP_WIDE_USES and len(nd_.leafset) > 1 and n >= 65536:
+                if leaf_by_nid is None:
+                    leaf_by_nid = {ln.nid: ln for ln in leaf_nodes}
+                seen_bufs, width = set(), 0.0
+                for nid in nd_.leafset:
+                    ln = leaf_by_nid.get(nid)
+                    if ln is None or id(ln.mat.buf) in seen_bufs:
+                        continue
+                    seen_bufs.add(id(ln.mat.buf))
+                    width += ln.mat.dtype.itemsize * min(1.0, prod(ln.mat.shape) / float(n))
+                keep = width > nd_.dtype.itemsize * 1.25
+            if keep:
                 outs.append(nd_)
             else:
                 nd_.uses += 1
