@@ -48,7 +48,11 @@ _HEAVY_VEC = int(__import__("os").environ.get("B200AG_HEAVY_VEC", "2"))
 _ROW_TUNE = tuple(int(v) for v in __import__("os").environ.get("B200AG_ROW_TUNE", "").split(",")) \
     if __import__("os").environ.get("B200AG_ROW_TUNE") else None
 _GRID_MULT = int(__import__("os").environ.get("B200AG_GRID_MULT", "16"))
-EXPAND_MIN_COST = 12     # cheaper sub-expressions (a max, a compare) are recomputed in place: reading them back costs as much
+# Repeated op-units per element of the SMALLER space (sub-expression cost x (replication - 1)) below which a broadcast
+# sub-expression is recomputed in place: writing it out and reading it back (16 B per element) costs the FP64 pipe time of
+# roughly 50 instructions.  Measured on C5 (scripts/gpu_r2_zstr.sh): the max-pool VJP chain (chooser of the outer max, cost
+# ~30, replicated 2x into the chooser of the inner max) 10.68 ms fully fused against 11.93 ms cut in two.
+EXPAND_MIN_COST = int(__import__("os").environ.get("B200AG_EXPAND_MIN_COST", "64"))
 EXPAND_WORK = float(__import__("os").environ.get("B200AG_EXPAND_WORK", "3.0e7"))     # repeated op-units (elements x cost) that justify one extra launch, see materialize()
 KEEP_COST = 96
 # Re-materialising nodes that keep being recomputed was measured on C4 (fluidsim): +1 % speed for +65 % retained
@@ -58,6 +62,7 @@ REUSE_LIMIT = int(__import__("os").environ.get("B200AG_REUSE_LIMIT", str(1 << 30
 # by default only values that are still bit-reproducible against NumPy are computed that way (Buffer.inexact).
 RELAXED = __import__("os").environ.get("B200AG_EXACT", "0") in ("", "0")
 UNROLL_WINDOWS = __import__("os").environ.get("B200AG_UNROLL_WINDOWS", "1") != "0"
+UNROLL_INNER = __import__("os").environ.get("B200AG_UNROLL_INNER", "1") != "0"
 KEEP_WIDE = __import__("os").environ.get("B200AG_KEEP_WIDE", "1") != "0"
 KEEP_WIDE_USES = int(__import__("os").environ.get("B200AG_KEEP_WIDE_USES", "1"))
 # Hard caps that force a flush while a graph is still being built.
@@ -490,10 +495,10 @@ class Program:
     """Structural description of one fused kernel; ``key`` identifies the generated code."""
 
     __slots__ = ("instrs", "leaves", "consts", "outputs", "ndim", "idx64", "vec", "key", "cost", "tables", "mode", "bx",
-                 "bdims", "share", "relax", "unroll")
+                 "bdims", "share", "relax", "unroll", "zstr")
 
     def __init__(self, instrs, leaves, consts, outputs, ndim, idx64, vec, cost, tables=(), mode="flat", bx=256,
-                 bdims=None, share=None, relax=(), unroll=()):
+                 bdims=None, share=None, relax=(), unroll=(), zstr=None):
         self.instrs = instrs      # tuple of (op, in_dtype chars, out dtype char, arg refs)
         self.leaves = leaves      # tuple of (dtype char, layout class 'C'|'S'|'G', has_shift)
         self.consts = consts      # tuple of C scalar kinds: 'd' | 'q' | '?'
@@ -520,7 +525,12 @@ class Program:
         # (the pooled cotangent, the window maximum, the tie count) are then loaded and computed once per window - the
         # compiler merges the identical sub-expressions of the unrolled bodies - and the coordinate split is done once
         self.unroll = unroll
-        self.key = (instrs, leaves, consts, outputs, ndim, idx64, vec, tables, mode, bx, bdims, share, relax, unroll)
+        # flat kernels over large general-layout spaces: per leaf, the bitmask of iteration dims along which the leaf
+        # does NOT move (stride 0: a bias, a pooled cotangent inside its window).  Those terms of the element offset are
+        # left out of the generated code instead of multiplied by a zero read from the parameter block - the max-pool
+        # VJP of C5 spent more instructions on `x * 0` address terms than on its arithmetic.
+        self.zstr = zstr
+        self.key = (instrs, leaves, consts, outputs, ndim, idx64, vec, tables, mode, bx, bdims, share, relax, unroll, zstr)
 
     def launch_config(self, sm_count):
         block = 256
@@ -625,7 +635,7 @@ def materialize(root: Node, store_root: bool = True) -> Mat:
             for a in nd_.args:
                 if type(a) is Node and a.mat is None and a.op not in ("full", "scatter"):
                     an = prod(a.shape)
-                    if an and an * 2 <= pn and a.cost >= EXPAND_MIN_COST and float(pn - an) * a.cost >= EXPAND_WORK:
+                    if an and an * 2 <= pn and a.cost * (pn // an - 1) >= EXPAND_MIN_COST and float(pn - an) * a.cost >= EXPAND_WORK:
                         small.append(a)
         if small:
             for a in small:
@@ -803,6 +813,12 @@ def materialize(root: Node, store_root: bool = True) -> Mat:
             vec = tv
 
     bdims = tuple(int(d) for d in dims[1:]) if (mode == "flat" and g_layouts and n >= (1 << 20)) else None
+    zstr = None
+    if bdims is not None:
+        zstr = [0] * len(leaf_descs)
+        for slot in g_slots:
+            zstr[slot] = sum(1 << d for d, st in enumerate(leaf_ptrs[slot][1]) if st == 0)
+        zstr = tuple(zstr) if any(zstr) else None
     share = None
     if mode == "flat" and len(g_slots) > 1:
         rep, first = list(range(len(leaf_descs))), {}
@@ -835,11 +851,26 @@ def materialize(root: Node, store_root: bool = True) -> Mat:
                     leaf_ptrs[slot][1][d] == 0 and sum(1 for st in leaf_ptrs[slot][1] if st) >= 2 for slot in g_slots):
                 picked.append(d)
                 per_thread *= dims[d]
+        # ... except when the innermost dim IS a window dim of extent 2 over 8-byte elements and every operand either
+        # does not move along it or has unit stride with 16-byte aligned rows: then one thread reads / writes the pair
+        # as a 16-byte vector (consecutive threads still touch consecutive 16-byte pieces) and the whole 2 x 2 window
+        # is one thread's work - half the index arithmetic and window-level arithmetic per element again
+        # (scripts/gpu_r2_window.sh)
+        last = len(dims) - 1
+        if (UNROLL_INNER and not shifted and dims[last] == 2 and per_thread * 2 <= 8
+                and all(o.dtype.itemsize == 8 for o in outs)
+                and all(np.dtype(ch).itemsize == 8 for ch, cls, _s, _f in leaf_descs if cls != "S")
+                and all(lp[0] % 16 == 0 for (ch, cls, _s, _f), lp in zip(leaf_descs, leaf_ptrs) if cls == "C")
+                and all(leaf_ptrs[slot][1][last] == 0 or leaf_descs[slot][3] == "R" for slot in g_slots)
+                and (picked or any(leaf_ptrs[slot][1][last] == 0 and sum(1 for st in leaf_ptrs[slot][1] if st) >= 2
+                                   for slot in g_slots))):
+            picked.append(last)
+            per_thread *= 2
         if per_thread >= 2 and total_cost >= 8:
             unroll = tuple(sorted(picked))
             vec = 1
     program = Program(instrs, tuple(leaf_descs), tuple(const_kinds), outputs, ndim, idx64, vec, total_cost,
-                      tuple(table_descs), mode, bx, bdims, share, relax, unroll)
+                      tuple(table_descs), mode, bx, bdims, share, relax, unroll, zstr)
     out_mats = [Mat.empty(root_shape, o.dtype, inexact=inexact[j] and o.dtype.kind == "f") for o, (j, _) in zip(outs, outputs)]
     backend.get().run_program(program, (leaf_ptrs, dims, table_rt), const_values, [m.ptr for m in out_mats], n)
     for o, m in zip(outs, out_mats):

@@ -1073,6 +1073,23 @@ def grad_case_max_pool():
         check_grad(pooled, (X, bias), TOL_REDUCE, f"max-pool grad wrt arg {argnum}", argnum=argnum)
     check_grad(lambda x: np.sum(np.mean(np.reshape(x, (40, 6, 12, 2, 12, 2)), axis=(3, 5)) ** 2), (X,), TOL_REDUCE,
                "average-pool grad")
+    # > 2^20 elements: the window kernels (lazy.Program.unroll: one thread per 2 x 2 window, 16-byte vector accesses along
+    # the innermost window dim, zero-stride terms left out of the offsets) - same values, ties and NaN-free maxima included
+    Xl = r.randn(320, 6, 24, 24)
+    Xl[0, 0, 0, 0] = Xl[0, 0, 0, 1] = Xl[0, 0, 1, 0] = Xl[0, 0, 1, 1] = 3.0      # a four-way tie
+    Xl[5, 2, 6, 8] = Xl[5, 2, 7, 9] = 9.0                                           # a diagonal tie
+
+    def pooled_large(x, b):
+        y6 = np.reshape(x + b, (320, 6, 12, 2, 12, 2))
+        p = np.max(np.max(y6, axis=3), axis=4)
+        return np.sum(p ** 2 * np.arange(1.0, 13.0))
+
+    for argnum in (0, 1):
+        check_grad(pooled_large, (Xl, bias), TOL_REDUCE, f"large max-pool grad wrt arg {argnum}", argnum=argnum)
+    check_grad(lambda x: np.sum(np.max(np.reshape(x, (320, 6, 24, 12, 2)), axis=4) ** 3), (Xl,), TOL_REDUCE,
+               "large 1-d max-pool grad (window = innermost dim only)")
+    check_grad(lambda x: np.sum(np.max(np.reshape(x, (320, 6, 12, 2, 24)), axis=3) ** 3), (Xl,), TOL_REDUCE,
+               "large row-pair max-pool grad (window = a middle dim only)")
 
 
 GRAD_CASES["max_pool"] = grad_case_max_pool

@@ -307,3 +307,39 @@ def test_consecutive_add_at_into_one_target_share_a_kernel(fake_dev):
     want2 = onp.zeros((32, 32))
     onp.add.at(want2, (i0, j0), g * 2.0)
     cases.assert_close(t2.get(), want2, cases.TOL_REDUCE, "queued np.add.at before an operand write")
+
+
+def test_pooling_window_gradient_is_one_window_per_thread_kernel(fake_dev):
+    """The max-pool VJP chain (grad_chooser of the outer and the inner max, numpy_vjps.py:515-530) over a large batch is ONE
+    generated kernel in which a thread owns a whole 2 x 2 window: both window dims unrolled (the innermost one through
+    16-byte vector accesses), offsets in 32-bit arithmetic without terms for dims an operand does not move along, and the
+    plain-division twin taking the parameter block by value (no local-memory copy of the kernel parameters)."""
+    import autograd.numpy as np
+    from autograd import grad
+
+    import autograd_b200 as b200
+    from autograd_b200 import codegen
+
+    r = onp.random.RandomState(3)
+    X, bias, W = r.randn(320, 6, 24, 24), r.randn(1, 6, 1, 1), r.randn(864, 3)
+    X[0, 0, 0, 0] = X[0, 0, 0, 1] = X[0, 0, 1, 1] = 5.0
+
+    def pooled(x, b, w):
+        p = np.max(np.max(np.reshape(x + b, (320, 6, 12, 2, 12, 2)), axis=3), axis=4)
+        return np.sum(np.dot(np.reshape(p, (320, 864)), w))     # a contraction consumes the pooled values, as in the convnet
+
+    fake_dev.programs.clear()
+    g = grad(pooled)(b200.asarray(X), b200.asarray(bias), b200.asarray(W)).get()
+    cases.assert_close(g, grad(pooled)(X, bias, W), cases.TOL_REDUCE, "max-pool gradient")
+    window = [p for p in fake_dev.programs.values() if p.unroll and p.ndim == 6]
+    assert len(window) == 1, [(p.ndim, p.unroll) for p in fake_dev.programs.values()]
+    prog = window[0]
+    assert prog.unroll == (3, 5) and prog.zstr is not None and not prog.idx64
+    src = codegen.generate(prog)[0]
+    kernel = src[src.index('extern "C" __global__'):]
+    assert kernel.count("body(") == 4 and kernel.count("ldg_pack<double, 2>") >= 3
+    assert kernel.count("*reinterpret_cast<Pack<double, 2>*>(p.o0") == 2          # two 16-byte stores per window
+    assert "(i64)x" not in src and "const Params p," in src
+    # every operand is loaded once per window: no load is emitted twice
+    loads = [ln.split("=")[1].strip() for ln in kernel.splitlines() if "__ldg(" in ln or "ldg_pack<" in ln]
+    assert len(loads) == len(set(loads))
