@@ -21,6 +21,8 @@ namespace b200ag {
 // conv_direct.cu: register-tiled CUDA-core kernels for layers with few output channels (0 done, 1 error, 2 not covered)
 int conv2d_direct_try(double* out, const double* A, const double* B, int64_t N, int C, int H, int W, int F, int kh, int kw,
                       int Ho, int Wo, int py, int px, int flip);
+int conv2d_full_lanes_try(double* out, const double* A, const double* B, int64_t N, int C, int H, int W, int F, int kh, int kw,
+                          int flip);
 int conv2d_wgrad_direct_try(double* dB, const double* A, const double* G, int64_t N, int C, int H, int W, int F, int kh,
                             int kw, int Ho, int Wo);
 int g_conv_direct = 1;   // b200ag_conv_mode: 0 = implicit-GEMM DMMA kernels only
@@ -397,6 +399,13 @@ int b200ag_conv2d(void* out, const void* A, const void* B, int dtype, int64_t N,
   // LeNet: C = 1); the 'full' correlation that is a layer's INPUT gradient (mode 1: conv2's dX has C = 16 cotangent
   // channels, F = 6) qualifies up to 16 because the direct kernel skips the taps that fall into the zero padding,
   // which the implicit-GEMM formulation multiplies (2.25x the true flops for a 5x5 filter over an 8x8 map).
+  // a layer's INPUT gradient over a large batch: lanes = images, the taps that fall into the zero padding are skipped
+  // exactly (conv_direct.cu); other shapes / small batches fall through
+  if (dtype == B200AG_F64 && g_conv_direct && mode == 1) {
+    int rc = conv2d_full_lanes_try((double*)out, (const double*)A, (const double*)B, N, (int)C, (int)H, (int)W, (int)F, (int)kh,
+                                   (int)kw, flip);
+    if (rc != 2) return rc;
+  }
   if (dtype == B200AG_F64 && g_conv_direct && F <= 8 && (C <= 4 || (mode == 1 && C <= (g_conv_direct_cmax)))) {
     int rc = conv2d_direct_try((double*)out, (const double*)A, (const double*)B, N, (int)C, (int)H, (int)W, (int)F, (int)kh,
                                (int)kw, (int)Ho, (int)Wo, (int)py, (int)px, flip);

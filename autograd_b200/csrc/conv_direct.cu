@@ -14,6 +14,8 @@
 // and falls back to the DMMA kernels when the shape is outside the instantiated set.
 #include <cuda_pipeline.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b200ag {
@@ -176,6 +178,178 @@ int conv2d_direct_try(double* out, const double* A, const double* B, int64_t N, 
   B200AG_DIRECT_CASE(1, 5) B200AG_DIRECT_CASE(2, 5) B200AG_DIRECT_CASE(3, 5) B200AG_DIRECT_CASE(4, 5)
   B200AG_DIRECT_CASE(6, 5) B200AG_DIRECT_CASE(8, 5)
 #undef B200AG_DIRECT_CASE
+  return 2;
+}
+
+// ------------------------------------------------------------------------------- 'full' correlation, lane = image
+// The INPUT gradient of a convolution layer is the 'full' correlation of the output cotangent with the filters
+// (autograd/scipy/signal.py:153-190): out[n,f,y,x] = sum_{c,a,j} A[n,c,y-a,x+j-(KW-1)] * Bk[c,f,KH-1-a,j] with everything
+// outside A zero.  For a 5x5 filter over an 8x8 map only 44 % of the (position, tap) pairs touch A at all; a kernel whose
+// lanes are neighbouring POSITIONS cannot skip the rest (each lane has its own valid range, the warp runs the union), and
+// the implicit-GEMM kernel multiplies the zero padding outright.  Here the 32 lanes of a warp are 32 IMAGES at the same
+// output column x: which taps exist is the same for every lane, so the skipping is exact and free of divergence, the
+// filter values are warp-wide broadcasts, and the image values are conflict-free (odd image pitch).  A thread owns one
+// output column (all F channels) in two passes of HALF rows; the valid (row, tap) pairs of a pass are enumerated at
+// compile time.  Channels are staged CC at a time through a two-stage cp.async ring.
+struct FullArgs {
+  double* out; const double* A; const double* B;
+  int64_t N;
+  int C, flip;
+};
+
+template <int F, int KH, int KW, int H, int W>
+struct FullCfg {
+  static constexpr int HO = H + KH - 1, WO = W + KW - 1;
+  static constexpr int HALF = (HO + 1) / 2;
+  static constexpr int CC = 4;                       // channels per stage
+  static constexpr int HW = H * W;
+  static constexpr int PITCH = CC * HW + 1;          // odd: lane r reads bank (r + const) mod 16
+  static constexpr int THREADS = 32 * WO;
+};
+
+template <int F, int KH, int KW, int H, int W, int P>
+__device__ __forceinline__ void full_lanes_pass(const double* __restrict__ in, const double* __restrict__ Ws, int cc_n,
+                                                int c0, int x, double (&acc)[F][FullCfg<F, KH, KW, H, W>::HALF]) {
+  using Cfg = FullCfg<F, KH, KW, H, W>;
+  constexpr int HALF = Cfg::HALF;
+  constexpr int Y_LO = P * HALF, Y_HI = (Y_LO + HALF < Cfg::HO) ? Y_LO + HALF : Cfg::HO;
+  constexpr int YY_LO = (Y_LO - (KH - 1) > 0) ? Y_LO - (KH - 1) : 0, YY_HI = (Y_HI < H) ? Y_HI : H;   // input rows used
+  for (int cc = 0; cc < cc_n; ++cc) {
+#pragma unroll
+    for (int j = 0; j < KW; ++j) {
+      const int xx = x + j - (KW - 1);
+      if (xx < 0 || xx >= W) continue;                // warp-uniform
+      const double* col = in + cc * Cfg::HW + xx;
+      double v[YY_HI - YY_LO];
+#pragma unroll
+      for (int r = 0; r < YY_HI - YY_LO; ++r) v[r] = col[(YY_LO + r) * W];
+      const double* wj = Ws + (((c0 + cc) * KW + j) * KH) * F;
+#pragma unroll
+      for (int a = 0; a < KH; ++a) {
+        double w[F];
+        if constexpr (F % 2 == 0) {
+#pragma unroll
+          for (int f = 0; f < F; f += 2) {
+            const double2 w2 = *reinterpret_cast<const double2*>(wj + a * F + f);
+            w[f] = w2.x; w[f + 1] = w2.y;
+          }
+        } else {
+#pragma unroll
+          for (int f = 0; f < F; ++f) w[f] = wj[a * F + f];
+        }
+#pragma unroll
+        for (int t = 0; t < HALF; ++t) {
+          const int yy = Y_LO + t - a;                // compile-time after unrolling
+          if (Y_LO + t < Y_HI && yy >= YY_LO && yy < YY_HI) {
+#pragma unroll
+            for (int f = 0; f < F; ++f) acc[f][t] = fma(v[yy - YY_LO], w[f], acc[f][t]);
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int F, int KH, int KW, int H, int W>
+__global__ void __launch_bounds__(FullCfg<F, KH, KW, H, W>::THREADS, 1) conv2d_full_lanes_kernel(FullArgs g) {
+  using Cfg = FullCfg<F, KH, KW, H, W>;
+  constexpr int HALF = Cfg::HALF, CC = Cfg::CC, PITCH = Cfg::PITCH, NT = Cfg::THREADS;
+  extern __shared__ double smem[];
+  const int wcount = g.C * KW * KH * F;
+  double* Ws = smem;                                   // [c][j][a][f], a = KH-1-i
+  double* bufs = smem + ((wcount + 1) & ~1);           // [2][32][PITCH]
+  const int tid = threadIdx.x, lane = tid & 31, x = tid >> 5;
+  for (int e = tid; e < wcount; e += NT) {
+    const int f = e % F, a = (e / F) % KH, j = (e / (F * KH)) % KW, c = e / (F * KH * KW);
+    const int i = KH - 1 - a;
+    const int bi = g.flip ? KH - 1 - i : i, bj = g.flip ? KW - 1 - j : j;
+    Ws[e] = g.B[((c * F + f) * KH + bi) * KW + bj];
+  }
+  const int nchunks = (g.C + CC - 1) / CC;
+  const int64_t groups = (g.N + 31) / 32;
+  const int64_t my_groups = blockIdx.x < groups ? (groups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t steps = my_groups * 2 * nchunks;       // (group, pass, chunk), chunk fastest
+  // stage(step): the CC channels of chunk `step % nchunks` of the step's 32 images -> ring slot step & 1
+  auto stage = [&](int64_t step) {
+    const int chunk = (int)(step % nchunks);
+    const int64_t n0 = (blockIdx.x + (step / (2 * nchunks)) * gridDim.x) * 32;
+    const int cc_n = (g.C - chunk * CC) < CC ? (g.C - chunk * CC) : CC;
+    double* dst = bufs + (step & 1) * (32 * PITCH);
+    const int per_img = cc_n * Cfg::HW;
+    for (int e = tid; e < 32 * per_img; e += NT) {
+      const int r = e / per_img, o = e - r * per_img;
+      if (n0 + r < g.N)
+        __pipeline_memcpy_async(dst + r * PITCH + o, g.A + ((n0 + r) * g.C + chunk * CC) * Cfg::HW + o, 8);
+    }
+    __pipeline_commit();
+  };
+  if (steps > 0) stage(0);
+  double acc[F][HALF];
+  for (int64_t step = 0; step < steps; ++step) {
+    const int chunk = (int)(step % nchunks), pass = (int)((step / nchunks) & 1);
+    const int64_t n0 = (blockIdx.x + (step / (2 * nchunks)) * gridDim.x) * 32;
+    if (step + 1 < steps) {
+      stage(step + 1);                                 // the slot was released by the barrier that ended step - 1
+      __pipeline_wait_prior(1);
+    } else {
+      __pipeline_wait_prior(0);
+    }
+    __syncthreads();
+    if (chunk == 0) {
+#pragma unroll
+      for (int f = 0; f < F; ++f)
+#pragma unroll
+        for (int t = 0; t < HALF; ++t) acc[f][t] = 0.0;
+    }
+    const double* in = bufs + (step & 1) * (32 * PITCH) + lane * PITCH;
+    const int cc_n = (g.C - chunk * CC) < CC ? (g.C - chunk * CC) : CC;
+    if (pass == 0) full_lanes_pass<F, KH, KW, H, W, 0>(in, Ws, cc_n, chunk * CC, x, acc);
+    else full_lanes_pass<F, KH, KW, H, W, 1>(in, Ws, cc_n, chunk * CC, x, acc);
+    if (chunk == nchunks - 1 && n0 + lane < g.N) {
+      double* o = g.out + (n0 + lane) * (int64_t)(F * Cfg::HO * Cfg::WO) + x;
+#pragma unroll
+      for (int f = 0; f < F; ++f)
+#pragma unroll
+        for (int t = 0; t < HALF; ++t) {
+          const int y = pass * HALF + t;
+          if (y < Cfg::HO) o[(f * Cfg::HO + y) * Cfg::WO] = acc[f][t];
+        }
+    }
+    __syncthreads();                                   // slot step & 1 may be refilled by the next round's prefetch
+  }
+}
+
+template <int F, int KH, int KW, int H, int W>
+static int launch_full_lanes(FullArgs g) {
+  using Cfg = FullCfg<F, KH, KW, H, W>;
+  const size_t wbytes = (size_t)((g.C * KW * KH * F + 1) & ~1) * 8;
+  const size_t smem = wbytes + 2 * (size_t)32 * Cfg::PITCH * 8;
+  if (smem > 220 * 1024) return 2;
+  static bool cfg = false;
+  if (!cfg) {
+    B200AG_CUDA(cudaFuncSetAttribute(conv2d_full_lanes_kernel<F, KH, KW, H, W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     220 * 1024));
+    cfg = true;
+  }
+  const int64_t groups = (g.N + 31) / 32;
+  const int64_t cap = sm_count();
+  conv2d_full_lanes_kernel<F, KH, KW, H, W><<<(unsigned)(groups < cap ? groups : cap), Cfg::THREADS, smem, stream()>>>(g);
+  B200AG_LAUNCH_CHECK();
+  return 0;
+}
+
+// 'full' correlation with lanes = images; returns 0 = done, 1 = error, 2 = shape not instantiated / batch too small
+int conv2d_full_lanes_try(double* out, const double* A, const double* B, int64_t N, int C, int H, int W, int F, int kh, int kw,
+                          int flip) {
+  static const bool on = []() { const char* e = getenv("B200AG_CONV_FULL_LANES"); return !e || atoi(e) != 0; }();
+  if (!on || N < 32 * 8) return 2;                     // small batches: the position-parallel kernels fill the machine better
+  FullArgs g{out, A, B, N, C, flip};
+#define B200AG_FULL_CASE(FV, KV, HV) \
+  if (F == FV && kh == KV && kw == KV && H == HV && W == HV) return launch_full_lanes<FV, KV, KV, HV, HV>(g);
+  B200AG_FULL_CASE(6, 5, 8) B200AG_FULL_CASE(4, 5, 8) B200AG_FULL_CASE(8, 5, 8) B200AG_FULL_CASE(3, 5, 8)
+  B200AG_FULL_CASE(6, 3, 8) B200AG_FULL_CASE(4, 3, 8) B200AG_FULL_CASE(8, 3, 8)
+  B200AG_FULL_CASE(6, 3, 10) B200AG_FULL_CASE(4, 3, 10) B200AG_FULL_CASE(6, 5, 4) B200AG_FULL_CASE(6, 3, 6)
+#undef B200AG_FULL_CASE
   return 2;
 }
 

@@ -443,7 +443,11 @@ def case_conv2d():
     r = rs(16)
     shapes = [((5, 3, 12, 10), (3, 4, 5, 3)), ((9, 1, 28, 28), (1, 6, 5, 5)), ((17, 6, 12, 12), (6, 16, 5, 5)),
               ((3, 2, 7, 9), (2, 8, 3, 3)), ((4, 5, 6, 6), (5, 3, 1, 1)), ((2, 3, 9, 8), (3, 20, 3, 2)),
-              ((33, 4, 11, 13), (4, 9, 4, 6)), ((1, 1, 5, 5), (1, 1, 5, 5))]
+              ((33, 4, 11, 13), (4, 9, 4, 6)), ((1, 1, 5, 5), (1, 1, 5, 5)),
+              # batches large enough for the lanes-are-images input-gradient kernel (conv_direct.cu: full correlation with
+              # exact skipping of the padding taps): LeNet's conv2 (its VJP wrt A), and a direct 'full' call with a
+              # channel count that is not a multiple of the staging chunk and a ragged last group of images
+              ((300, 6, 12, 12), (6, 16, 5, 5)), ((290, 5, 8, 8), (5, 6, 3, 3))]
     for a_shape, b_shape in shapes:
         A, B = r.randn(*a_shape), r.randn(*b_shape)
         for mode in ("valid", "full"):
