@@ -890,6 +890,10 @@ def reshape(a, shape=None, order="C", *, newshape=None, copy=None):
         general = _reshape_strided_lazy(node, shape)
         if general is not None:
             return DeviceArray(general)
+        if lazy.LAZY_RESHAPE and size >= 4096 and a.dtype.kind != "b" and node.op != "scatter":
+            # some operand cannot be re-viewed by itself (a broadcast meshgrid row being flattened): record the reshape
+            # and let lazy.materialize pick one iteration space for both sides of it (lazy._plan_reshapes)
+            return DeviceArray(Node("reshape", (node,), (a.dtype,), shape, a.dtype))
     m = a._mat()
     new_strides = _reshape_strides(m, shape)
     if new_strides is None:
@@ -1023,7 +1027,7 @@ def _select_lazy(node, ndim, axis, index, memo):
                                 m.offset + i * m.strides[ax], m.dtype, shifts))
     elif node.op == "full":
         res = Node("full", node.args, node.in_dtypes, shape[:ax] + shape[ax + 1:], node.dtype)
-    elif node.op == "scatter":
+    elif node.op in ("scatter", "reshape"):
         res = None
     else:
         args = []
@@ -1056,7 +1060,7 @@ def _insert_axis_lazy(node, ndim, pos, memo):
                             m.dtype, shifts))
     elif node.op == "full":
         res = Node("full", node.args, node.in_dtypes, shape[:p] + (1,) + shape[p:], node.dtype)
-    elif node.op == "scatter":
+    elif node.op in ("scatter", "reshape"):
         res = None
     else:
         args = []

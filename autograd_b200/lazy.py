@@ -38,6 +38,7 @@ _COST = {
     "logical_and": 1, "logical_or": 1, "logical_not": 1, "logical_xor": 1,
     "isfinite": 1, "isnan": 1, "isinf": 1, "floor": 1, "ceil": 1, "trunc": 1, "rint": 1,
     "divide": 6, "reciprocal": 6, "sqrt": 6, "remainder": 4, "floor_divide": 4, "gather": 4,
+    "reshape": 0,
 }
 _DEFAULT_COST = 12  # transcendental functions
 
@@ -62,6 +63,7 @@ REUSE_LIMIT = int(__import__("os").environ.get("B200AG_REUSE_LIMIT", str(1 << 30
 # by default only values that are still bit-reproducible against NumPy are computed that way (Buffer.inexact).
 RELAXED = __import__("os").environ.get("B200AG_EXACT", "0") in ("", "0")
 UNROLL_WINDOWS = __import__("os").environ.get("B200AG_UNROLL_WINDOWS", "1") != "0"
+LAZY_RESHAPE = __import__("os").environ.get("B200AG_LAZY_RESHAPE", "1") != "0"
 UNROLL_INNER = __import__("os").environ.get("B200AG_UNROLL_INNER", "1") != "0"
 KEEP_WIDE = __import__("os").environ.get("B200AG_KEEP_WIDE", "1") != "0"
 KEEP_WIDE_USES = int(__import__("os").environ.get("B200AG_KEEP_WIDE_USES", "1"))
@@ -615,6 +617,73 @@ def _collapse_dims(root_shape, leaf_layouts):
     return dims, lay
 
 
+def _settle_reshape(nd_):
+    """Turn a pending ``reshape`` node into a leaf: compute what is behind it (contiguous), view it under the new shape."""
+    arg = nd_.args[0]
+    m = arg.mat if arg.mat is not None else materialize(arg)
+    if not m.is_contiguous:
+        m = materialize(Node("positive", (leaf(m),), (m.dtype,), m.shape, m.dtype))
+    nd_.mat = Mat(m.buf, nd_.shape, c_strides(nd_.shape), m.offset, m.dtype)
+    nd_.args = ()
+    nd_.cost = 0
+    nd_.lo = nd_.nid
+    nd_.leafset = frozenset((nd_.nid,))
+
+
+def _plan_reshapes(root):
+    """A pending expression may contain ``reshape`` nodes (array.reshape of a pending value whose operands cannot be
+    re-viewed one by one: ``(cell_xs - vx).ravel()`` with ``cell_xs`` a broadcast meshgrid row, examples/fluidsim.py:37-41).
+    Row-major order is the same on both sides of such a node, so ONE kernel can evaluate all of it provided the operands
+    that need coordinates (broadcast / strided / rolled ones) all live under the same shape: that shape becomes the
+    iteration space, and every full-size contiguous operand - whatever shape it is recorded under - is just the flat
+    index.  Returns (iteration shape, {leaf nid: Mat seen in that space}) or None (then the reshapes are computed first)."""
+    root_shape = root.shape
+    level, leaf_levels, leaf_node = {}, {}, {}
+    stack = [(root, root_shape)]
+    while stack:
+        nd_, lv = stack.pop()
+        if nd_.mat is not None:
+            leaf_levels.setdefault(nd_.nid, set()).add(lv)
+            leaf_node[nd_.nid] = nd_
+            continue
+        prev = level.get(nd_.nid)
+        if prev is not None:
+            if prev != lv:
+                return None
+            continue
+        level[nd_.nid] = lv
+        if nd_.op == "reshape":
+            if nd_.shape != lv:
+                return None                      # a reshaped value broadcast into a larger space
+            stack.append((nd_.args[0], nd_.args[0].shape))
+        else:
+            for k, a in enumerate(nd_.args):
+                if type(a) is Node and not (nd_.op in ("gather", "scatter") and k == 0):
+                    stack.append((a, lv))
+    g_levels, views = set(), {}
+    for nid, lvs in leaf_levels.items():
+        m = leaf_node[nid].mat
+        if prod(m.shape) == 1:
+            continue
+        if m.shifts is None and m.is_contiguous and all(m.shape == lv for lv in lvs):
+            views[nid] = None                    # flat order: re-viewed under the iteration shape below
+            continue
+        if len(lvs) != 1:
+            return None
+        g_levels.add(next(iter(lvs)))
+    if len(g_levels) > 1:
+        return None
+    iter_shape = next(iter(g_levels)) if g_levels else root_shape
+    if prod(iter_shape) != prod(root_shape):
+        return None
+    out = {}
+    for nid in views:
+        m = leaf_node[nid].mat
+        if m.shape != iter_shape:
+            out[nid] = Mat(m.buf, iter_shape, c_strides(iter_shape), m.offset, m.dtype)
+    return iter_shape, out
+
+
 def materialize(root: Node, store_root: bool = True) -> Mat:
     """Compute ``root`` (and any still-visible expensive interior node) with one fused kernel."""
     if root.mat is not None:
@@ -622,6 +691,28 @@ def materialize(root: Node, store_root: bool = True) -> Mat:
     order, leaf_nodes = _collect([root])
     root_shape = root.shape
     n = prod(root_shape)
+    iter_shape, leaf_view = root_shape, {}
+    if any(nd_.op == "reshape" for nd_ in order):
+        settled = False
+        for nd_ in order:                        # what is behind a reshape has been computed meanwhile: plain views
+            if nd_.op == "reshape" and nd_.mat is None and nd_.args[0].mat is not None:
+                _settle_reshape(nd_)
+                settled = True
+        if root.mat is not None:
+            return root.mat
+        if settled:
+            order, leaf_nodes = _collect([root])
+        if any(nd_.op == "reshape" for nd_ in order):
+            plan = _plan_reshapes(root) if n >= 2 else None
+            if plan is None:
+                for nd_ in order:
+                    if nd_.op == "reshape" and nd_.mat is None:
+                        _settle_reshape(nd_)
+                if root.mat is not None:
+                    return root.mat
+                order, leaf_nodes = _collect([root])
+            else:
+                iter_shape, leaf_view = plan
 
     # A pending sub-expression that lives on a SMALLER iteration space and is broadcast into a larger one would be
     # recomputed once per element of the larger space (the tanh VJP at pooled resolution feeding the 4x larger
@@ -692,8 +783,8 @@ def materialize(root: Node, store_root: bool = True) -> Mat:
     for ln in leaf_nodes:
         if ln.nid not in elementwise_leaf:
             continue
-        m = ln.mat
-        strides, shifts = _aligned_strides(m, root_shape)
+        m = leaf_view.get(ln.nid) or ln.mat
+        strides, shifts = _aligned_strides(m, iter_shape)
         sig = (m.buf.ptr, m.offset, m.dtype.char, tuple(strides), tuple(shifts))
         if sig in dedup:
             leaf_index[ln.nid] = dedup[sig]
@@ -701,7 +792,7 @@ def materialize(root: Node, store_root: bool = True) -> Mat:
         has_shift = any(shifts)
         if all(st == 0 for st in strides) or n <= 1:
             cls = "S"
-        elif not has_shift and m.shape == root_shape and m.is_contiguous:
+        elif not has_shift and m.shape == iter_shape and m.is_contiguous:
             cls = "C"
         else:
             cls = "G"
@@ -716,7 +807,7 @@ def materialize(root: Node, store_root: bool = True) -> Mat:
             g_slots.append(idx)
 
     if g_layouts:
-        dims, lay = _collapse_dims(root_shape, g_layouts)
+        dims, lay = _collapse_dims(iter_shape, g_layouts)
         for slot, (s, sh) in zip(g_slots, lay):
             leaf_ptrs[slot][1] = s
             leaf_ptrs[slot][2] = sh
@@ -774,7 +865,8 @@ def materialize(root: Node, store_root: bool = True) -> Mat:
                         const_values.append(v)
                     refs.append(("c", ci))
         instr_index[nd_.nid] = len(instrs)
-        instrs.append((nd_.op, tuple(d.char for d in nd_.in_dtypes), nd_.dtype.char, tuple(refs)))
+        instrs.append(("positive" if nd_.op == "reshape" else nd_.op, tuple(d.char for d in nd_.in_dtypes), nd_.dtype.char,
+                       tuple(refs)))
 
     outputs = tuple((instr_index[o.nid], o.dtype.char) for o in outs)
 

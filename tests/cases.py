@@ -1058,6 +1058,57 @@ def case_short_axis_reductions():
 OP_CASES["short_axis_reductions"] = case_short_axis_reductions
 
 
+def case_pending_reshape():
+    """reshape / ravel of a PENDING expression whose operands cannot be re-viewed one by one (a broadcast row being
+    flattened: ``(cell_xs - vx).ravel()`` of examples/fluidsim.py:37-41) stays pending as a ``reshape`` node;
+    lazy._plan_reshapes picks one iteration space for both sides, or computes the reshaped value first when no single
+    space serves every operand.  Values must match NumPy on every path."""
+    r = rs(123)
+    x = r.randn(64, 96)
+    row, col = r.randn(96), r.randn(64, 1)
+    table = r.randn(64, 96)
+    check(lambda a, b: (a + b).ravel() * 2.0, x, row, tol=TOL_ELEMENTWISE, what="broadcast row flattened")
+    check(lambda a, b, c: onp.floor((a - b).ravel()) + (a * c).ravel(), x, row, col, tol=TOL_ELEMENTWISE,
+          what="two flattened expressions over one 2-d space")
+    check(lambda a, b: ((a + b).ravel() * 2.0).reshape(96, 64) + 1.0, x, row, tol=TOL_ELEMENTWISE,
+          what="reshape of a reshape (levels (96,64) <- (6144,) <- (64,96))")
+    check(lambda a, b: ((a + b).ravel() * 2.0).reshape(96, 64) + onp.arange(64.0), x, row, tol=TOL_ELEMENTWISE,
+          what="two levels that both need coordinates (falls back to computing the inner one first)")
+    check(lambda a, b: (a + b).ravel()[None, :] * onp.array([[1.0], [2.0], [3.0]]), x, row, tol=TOL_ELEMENTWISE,
+          what="reshaped value broadcast into a larger space")
+    check(lambda a, b: onp.roll((a + b).ravel(), 5) - (a + b).ravel(), x, row, tol=TOL_ELEMENTWISE, what="roll of a reshaped value")
+    check(lambda a, b: onp.sum((a * b).ravel()), x, row, tol=TOL_REDUCE, what="reduction of a reshaped value")
+    check(lambda a, b: ((a * 10).astype(onp.int64) + onp.arange(96)).ravel() % 7, x, row, what="int64 through a reshape")
+    check(lambda a, b, t: t[onp.mod(onp.floor((a * 20 + b).ravel()).astype(int), 64),
+                            onp.mod(onp.floor((a * 30 - b).ravel()).astype(int), 96)] * (a + b).ravel(), x, row, table,
+          tol=TOL_ELEMENTWISE, what="gather through indices computed from flattened broadcast expressions (advect)")
+    check(lambda a, b: ((a + b).reshape(32, 2, 96) * 2.0).reshape(64, 96) - a, x, row, tol=TOL_ELEMENTWISE,
+          what="there and back again")
+    check(lambda a, b: (a + b).ravel().reshape(64, 96)[::2, 1:] * 3.0, x, row, tol=TOL_ELEMENTWISE, what="slice of a reshaped value")
+    check(lambda a, b: onp.concatenate([(a + b).ravel(), (a - b).ravel()]), x, row, tol=TOL_ELEMENTWISE, what="concatenate")
+    y = x.copy()
+
+    def inplace(a, b):
+        v = (a + b).ravel()
+        a = a * 1.0
+        a[0, 0] = 100.0              # the operand behind the pending reshape is a different buffer: v keeps its values
+        return v + a.ravel()
+
+    check(inplace, y, row, tol=TOL_ELEMENTWISE, what="pending reshape unaffected by later writes to a copy")
+
+    def inplace_operand(a, b):
+        a = a.copy()
+        v = (a + b).ravel()
+        a[0, 0] = 100.0              # written AFTER v was recorded: v must hold the old value (eager semantics)
+        a[5:7] = -1.0
+        return v * 1.0 + a.ravel()
+
+    check(inplace_operand, y, row, tol=TOL_ELEMENTWISE, what="pending reshape reads its operand before a later in-place write")
+
+
+OP_CASES["pending_reshape"] = case_pending_reshape
+
+
 def grad_case_max_pool():
     """Max-pool block of examples/convnet.py:109-118 with the grad_chooser VJP (numpy_vjps.py:515-530), ties included
     (equal maxima share the cotangent)."""
@@ -1764,7 +1815,12 @@ def grad_case_checkpoint():
     for v, g, what in ((v1, g1, "plain tape"), (v2, g2, "autograd.checkpoint"), (v3, g3, "autograd_b200.checkpoint")):
         assert_close(g, gw, TOL_REDUCE, f"fluid gradient, {what}")
         assert abs(v - float(vw)) <= TOL_REDUCE * abs(float(vw)), what
-    assert ckpt_peak < 0.7 * plain_peak, f"checkpoint kept {ckpt_peak} bytes, plain tape {plain_peak}"
+    # the checkpointed run retains the state between steps (3 arrays per step) plus one step's tape; the plain tape of this
+    # workload is itself lean since reshapes of pending values stay pending (4.7 arrays per step, 11 before), so the
+    # bound is stated in arrays per step as well as relative to the plain tape
+    arr = rows * cols * 8
+    assert ckpt_peak < 0.9 * plain_peak, f"checkpoint kept {ckpt_peak} bytes, plain tape {plain_peak}"
+    assert ckpt_peak < 4.5 * steps * arr, f"checkpoint kept {ckpt_peak / arr / steps:.2f} arrays per step"
     assert ref_ckpt_peak > 0.8 * plain_peak            # documents the reference's behaviour; not a requirement on us
 
 
