@@ -268,14 +268,16 @@ class CudaBackend:
 
             source, name, packer = codegen.generate(program)
             handle, image = self.compile(source, name)
-            rec = (handle, image, packer, program.launch_config(self.sm_count))
+            occ = C.c_int(0)
+            self._check(self._lib.b200ag_kernel_max_active_blocks(handle, 256, 0, C.byref(occ)))
+            rec = (handle, image, packer, program.launch_config(self.sm_count), max(1, occ.value))
             self._kernels[program.key] = rec
-        handle, _image, packer, (block, _elems_per_block, _max_grid) = rec
+        handle, _image, packer, (block, _elems_per_block, _max_grid), occ = rec
         if n == 0:
             return
         params = packer(n, tuple(leaf_ptrs) + (self._index_flag,) if program.tables else leaf_ptrs, const_values, out_ptrs,
                         program)
-        grid = program.grid(n, leaf_ptrs[1], self.sm_count)
+        grid = program.grid(n, leaf_ptrs[1], self.sm_count, occ)
         if self.profile is None:
             self._check(self._lib.b200ag_kernel_launch(handle, grid, block, 0, params, len(params)))
         else:

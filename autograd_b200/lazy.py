@@ -49,6 +49,7 @@ _HEAVY_VEC = int(__import__("os").environ.get("B200AG_HEAVY_VEC", "2"))
 _ROW_TUNE = tuple(int(v) for v in __import__("os").environ.get("B200AG_ROW_TUNE", "").split(",")) \
     if __import__("os").environ.get("B200AG_ROW_TUNE") else None
 _GRID_MULT = int(__import__("os").environ.get("B200AG_GRID_MULT", "16"))
+_GRID_MULT_HEAVY = int(__import__("os").environ.get("B200AG_GRID_MULT_HEAVY", __import__("os").environ.get("B200AG_GRID_MULT", "64")))
 # Repeated op-units per element of the SMALLER space (sub-expression cost x (replication - 1)) below which a broadcast
 # sub-expression is recomputed in place: writing it out and reading it back (16 B per element) costs the FP64 pipe time of
 # roughly 50 instructions.  Measured on C5 (scripts/gpu_r2_zstr.sh): the max-pool VJP chain (chooser of the outer max, cost
@@ -538,14 +539,25 @@ class Program:
         block = 256
         return block, block * self.vec, sm_count * 16
 
-    def grid(self, n, dims, sm_count):
+    def grid(self, n, dims, sm_count, resident=None):
+        """CTAs to launch.  Grid-stride kernels are capped at a WHOLE number of waves - ``resident`` CTAs per SM (asked
+        from the occupancy calculator for the compiled kernel) times about _GRID_MULT / resident: a cap of 16 CTAs per
+        SM is 5.33 waves of a kernel that fits 3 per SM, and the last third-full wave costs as much as a full one
+        (C2, scripts/gpu_r2_c2_sweep.sh: 2.285 ms at 16 per SM, 2.231 at 32)."""
         if self.unroll:
             per_thread = 1
             for d in self.unroll:
                 per_thread *= dims[d]
             n = n // per_thread
         per_block = 256 * self.vec
-        max_grid = sm_count * _GRID_MULT
+        # ALU-bound bodies (hundreds of FP64 instructions per element) run faster from MANY short CTAs than from a
+        # few long ones (C2, scripts/gpu_r2_waves2.sh: 2.53 ms from one resident wave, 2.28 at 16 CTAs per SM, 2.22 at
+        # 64, 2.21 at 128); bandwidth-bound kernels do not (C4: 210 ms at 16, 212 at 32, 228 at 64)
+        mult = _GRID_MULT_HEAVY if self.cost > 400 else _GRID_MULT
+        if resident:
+            max_grid = sm_count * resident * max(1, (mult + resident // 2) // resident)
+        else:
+            max_grid = sm_count * mult
         if self.mode == "row":
             inner = dims[-1]
             span = self.bx * self.vec

@@ -25,8 +25,14 @@ elif cfg == "c4":
     f = value_and_grad(w.fluid_objective)
 elif cfg == "c5":
     n, _p, loss = w.convnet_make(); W, X, T = w.convnet_data(size or 65536, n); a = (b200.asarray(W), b200.asarray(X), b200.asarray(T)); f = grad(loss)
+elif cfg == "c2":
+    import numpy as onp
+    from autograd import elementwise_grad as egrad
+    import autograd.numpy as np
+    f = egrad(egrad(egrad(egrad(np.tanh))))
+    a = (b200.asarray(onp.linspace(-7.0, 7.0, size or (1 << 28))),)
 else:
-    raise SystemExit("config must be c1 | c3 | c4 | c5")
+    raise SystemExit("config must be c1 | c2 | c3 | c4 | c5")
 fast = b200.capture(f)
 fast(*a); fast(*a); be.synchronize()
 e0, e1 = be.event_create(), be.event_create()
