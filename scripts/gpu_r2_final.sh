@@ -14,3 +14,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 ncu --set full --clock-control none --import-source on -k regex:fused_ -s 4 -c 1 -o gpurun_out/r02_prof_c2 $CMD > gpurun_out/c2_ncu_full.log 2>&1
 tail -1 gpurun_out/c2_ncu_full.log
 head -c 1500 gpurun_out/bench_n1.log
+# launch lists of the other configs as committed (eager calls: every generated / library kernel of one gradient)
+ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/r02_c3_launches.csv python scripts/profile_config.py c3 4 > gpurun_out/ncu_c3.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/r02_c5_launches.csv python scripts/profile_config.py c5 65536 > gpurun_out/ncu_c5.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/r02_c4_launches.csv python scripts/profile_config.py c4 2 > gpurun_out/ncu_c4.log 2>&1
+for c in c3 c4 c5; do python scripts/summarize_launches.py gpurun_out/r02_${c}_launches.csv 6; done
