@@ -453,12 +453,13 @@ class DeviceArray:
         node = self._node
         if node.mat is None:
             if node.op == "full" and isinstance(node.args[0], Const) and node.args[0].value == 0 and prod(node.shape) > 0 \
-                    and str(node.args[0].value)[0] != "-":
+                    and str(node.args[0].value)[0] != "-" and node.alias is None:
                 # the zero accumulator of a sparse cotangent (vs.zeros() handed to np.add.at, core.py:212-215): a memset at
                 # copy-engine speed instead of a generated fill kernel
                 zm = Mat.empty(node.shape, node.dtype)
                 backend.get().memset(zm.ptr, 0, zm.buf.nbytes)
                 node.mat, node.args, node.cost, node.lo, node.leafset = zm, (), 0, node.nid, frozenset((node.nid,))
+                lazy.payload_set(node)
             else:
                 lazy.materialize(node)
         m = node.mat
@@ -882,18 +883,21 @@ def reshape(a, shape=None, order="C", *, newshape=None, copy=None):
         return a
     node = a._node
     if node.mat is None:
+        res = None
         if _reshape_transparent(node):
-            return DeviceArray(_reshape_lazy(node, shape, node.shape, {}))
-        unit = _reshape_unit_axes_lazy(node, shape)
-        if unit is not None:
-            return DeviceArray(unit)
-        general = _reshape_strided_lazy(node, shape)
-        if general is not None:
-            return DeviceArray(general)
-        if lazy.LAZY_RESHAPE and size >= 4096 and a.dtype.kind != "b" and node.op != "scatter":
+            res = _reshape_lazy(node, shape, node.shape, {})
+        if res is None:
+            res = _reshape_unit_axes_lazy(node, shape)
+        if res is None:
+            res = _reshape_strided_lazy(node, shape)
+        if res is None and lazy.LAZY_RESHAPE and size >= 4096 and a.dtype.kind != "b" and node.op != "scatter":
             # some operand cannot be re-viewed by itself (a broadcast meshgrid row being flattened): record the reshape
             # and let lazy.materialize pick one iteration space for both sides of it (lazy._plan_reshapes)
-            return DeviceArray(Node("reshape", (node,), (a.dtype,), shape, a.dtype))
+            res = Node("reshape", (node,), (a.dtype,), shape, a.dtype)
+        if res is not None:
+            if res.mat is None:
+                lazy.link_alias(res, node)       # NumPy: a view of ``a`` - in-place writes through either must alias
+            return DeviceArray(res)
     m = a._mat()
     new_strides = _reshape_strides(m, shape)
     if new_strides is None:

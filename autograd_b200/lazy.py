@@ -76,7 +76,7 @@ MAX_LEAVES = 48
 class Buffer:
     """Owner of one device allocation; freed back to the pool when unreferenced."""
 
-    __slots__ = ("ptr", "nbytes", "version", "inexact", "readers", "pending", "__weakref__")
+    __slots__ = ("ptr", "nbytes", "version", "inexact", "readers", "aliases", "pending", "__weakref__")
 
     def __init__(self, nbytes: int, upload: bool = False):
         self.nbytes = int(nbytes)
@@ -90,6 +90,7 @@ class Buffer:
         # pending (not yet computed) expression nodes that read this buffer directly; an in-place write materialises them
         # first so that `y = x * 2; x[0] = 100` leaves y computed from the old x, as NumPy's eager evaluation does
         self.readers = None
+        self.aliases = None       # alias groups (lazy._AliasGroup) whose payload lives here
         self.pending = False      # True while a deferred contraction (defer_gemm) still has to write this buffer
         be = backend.get()
         self.ptr = be.malloc_upload(self.nbytes) if upload else be.malloc(self.nbytes)
@@ -196,6 +197,8 @@ def flush_readers(buf) -> None:
         flush_gemms()          # a queued product may read the buffer that is about to change
     if _scatter_queue:
         flush_scatters(reading=buf)
+    if buf.aliases:
+        settle_aliases(buf)    # pending reshapes of an array that lives here become views of it: they must see the write
     readers = buf.readers
     if not readers:
         return
@@ -277,9 +280,11 @@ _EMPTY = frozenset()
 
 class Node:
     __slots__ = ("op", "args", "in_dtypes", "shape", "dtype", "mat", "nid", "lo", "cost", "leafset", "nhandles",
-                 "uses", "__weakref__")
+                 "uses", "alias", "consumers", "__weakref__")
 
     def __init__(self, op, args, in_dtypes, shape, dtype, mat=None):
+        self.alias = None     # the group of arrays that are symbolic RESHAPES of one another (NumPy: views of one buffer)
+        self.consumers = None # weakrefs to the nodes recorded with this one as a PENDING operand (see payload_set)
         self.op = op
         self.args = args
         self.in_dtypes = in_dtypes
@@ -298,6 +303,10 @@ class Node:
                             lo = a.lo
                         cost += a.cost
                         leafset = leafset | a.leafset if leafset else a.leafset
+                        if a.consumers is None:
+                            a.consumers = [weakref.ref(self)]
+                        else:
+                            a.consumers.append(weakref.ref(self))
                     else:
                         leafset = leafset | a.leafset
                         buf = a.mat.buf
@@ -629,17 +638,98 @@ def _collapse_dims(root_shape, leaf_layouts):
     return dims, lay
 
 
+class _AliasGroup:
+    """Arrays that NumPy would hand out as VIEWS of one buffer: an array and its (chained) reshapes.  While they are pending
+    they are independent expressions - that is what lets a reshape fuse into its consumers and what keeps the tape from
+    holding a buffer for each of them.  The first member that is given a payload provides the buffer of the group; any
+    other member is turned into a strided view of it the moment it would be computed (materialize) or the buffer is about
+    to be written in place (flush_readers), so a write through one handle is seen through all of them."""
+
+    __slots__ = ("members", "__weakref__")
+
+    def __init__(self):
+        self.members = []        # weakrefs to Nodes
+
+    def payload(self):
+        for ref in self.members:
+            nd_ = ref()
+            if nd_ is not None and nd_.mat is not None:
+                m = nd_.mat
+                if m.shifts is None and m.is_contiguous:
+                    return m
+        return None
+
+
+def link_alias(view: Node, src: Node) -> None:
+    """Record that ``view`` is a symbolic reshape of the pending ``src`` (see _AliasGroup)."""
+    group = src.alias
+    if group is None:
+        group = src.alias = _AliasGroup()
+        group.members.append(weakref.ref(src))
+    view.alias = group
+    group.members.append(weakref.ref(view))
+
+
+def _become_leaf(nd_, m):
+    nd_.mat = m
+    nd_.args = ()
+    nd_.cost = 0
+    nd_.lo = nd_.nid
+    nd_.leafset = frozenset((nd_.nid,))
+
+
+def _adopt_group_payload(nd_) -> bool:
+    """If an array of ``nd_``'s alias group already has a payload, ``nd_`` (pending) becomes a view of it."""
+    m = nd_.alias.payload()
+    if m is None or prod(m.shape) != prod(nd_.shape):
+        return False
+    _become_leaf(nd_, Mat(m.buf, nd_.shape, c_strides(nd_.shape), m.offset, m.dtype))
+    payload_set(nd_)
+    return True
+
+
+def payload_set(nd_) -> None:
+    """``nd_`` has just been given a payload.  (1) Expressions that were recorded with it as a PENDING operand and are
+    themselves still pending now read its buffer: they are registered as readers of that buffer, so that a later
+    in-place write to it evaluates them first (flush_readers; NumPy would have computed them when they were written
+    down).  (2) Its alias group is noted on the buffer: before an in-place write, the group's pending members become
+    views of it."""
+    cons, nd_.consumers = nd_.consumers, None
+    buf = nd_.mat.buf
+    if cons:
+        for ref in cons:
+            c = ref()
+            if c is not None and c.mat is None and c.args:
+                if buf.readers is None:
+                    buf.readers = weakref.WeakSet()
+                buf.readers.add(c)
+    if nd_.alias is not None:
+        if buf.aliases is None:
+            buf.aliases = [nd_.alias]
+        elif nd_.alias not in buf.aliases:
+            buf.aliases.append(nd_.alias)
+
+
+def settle_aliases(buf) -> None:
+    """Before an in-place write to ``buf``: the pending members of the alias groups living in it become views of it."""
+    groups, buf.aliases = buf.aliases, None
+    for group in groups or ():
+        for ref in list(group.members):
+            nd_ = ref()
+            if nd_ is not None and nd_.mat is None:
+                _adopt_group_payload(nd_)
+    if groups:
+        buf.aliases = groups           # later reshapes of the same arrays join the same groups
+
+
 def _settle_reshape(nd_):
     """Turn a pending ``reshape`` node into a leaf: compute what is behind it (contiguous), view it under the new shape."""
     arg = nd_.args[0]
     m = arg.mat if arg.mat is not None else materialize(arg)
     if not m.is_contiguous:
         m = materialize(Node("positive", (leaf(m),), (m.dtype,), m.shape, m.dtype))
-    nd_.mat = Mat(m.buf, nd_.shape, c_strides(nd_.shape), m.offset, m.dtype)
-    nd_.args = ()
-    nd_.cost = 0
-    nd_.lo = nd_.nid
-    nd_.leafset = frozenset((nd_.nid,))
+    _become_leaf(nd_, Mat(m.buf, nd_.shape, c_strides(nd_.shape), m.offset, m.dtype))
+    payload_set(nd_)
 
 
 def _plan_reshapes(root):
@@ -701,6 +791,14 @@ def materialize(root: Node, store_root: bool = True) -> Mat:
     if root.mat is not None:
         return root.mat
     order, leaf_nodes = _collect([root])
+    adopted = False
+    for nd_ in order:                            # a reshape of an array that has been computed meanwhile: a view of it
+        if nd_.alias is not None and nd_.mat is None and _adopt_group_payload(nd_):
+            adopted = True
+    if adopted:
+        if root.mat is not None:
+            return root.mat
+        order, leaf_nodes = _collect([root])
     root_shape = root.shape
     n = prod(root_shape)
     iter_shape, leaf_view = root_shape, {}
@@ -979,6 +1077,8 @@ def materialize(root: Node, store_root: bool = True) -> Mat:
     backend.get().run_program(program, (leaf_ptrs, dims, table_rt), const_values, [m.ptr for m in out_mats], n)
     for o, m in zip(outs, out_mats):
         o.mat = m
+        if o.consumers or o.alias is not None:
+            payload_set(o)
     if not store_root:
         root.args = ()
     # drop the graph behind everything that is now materialised or no longer needed

@@ -1109,6 +1109,60 @@ def case_pending_reshape():
 OP_CASES["pending_reshape"] = case_pending_reshape
 
 
+def case_reshape_is_a_view():
+    """NumPy's reshape / ravel / expand_dims / squeeze of a contiguous array are VIEWS: a later in-place write through either
+    handle is seen through the other.  A reshape of a PENDING expression is recorded symbolically (two independent
+    expressions, so that it can fuse); the two become one buffer the moment either gets a payload (lazy.link_alias), and
+    values that were computed - or recorded - from either before the write keep the old contents."""
+    r = rs(321)
+    x, row = r.randn(64, 96), r.randn(96)
+
+    def write_through_the_reshape(a0, b0, make):
+        a = make(a0, b0)
+        v = a.reshape(-1)
+        v[5] = 555.0
+        v[200:300] = -1.0
+        return a * 1.0, v * 1.0
+
+    def write_through_the_source(a0, b0, make):
+        a = make(a0, b0)
+        v = a.reshape(-1)
+        w = v * 2.0                     # recorded BEFORE the write: old values
+        a[0, 5] = 555.0
+        a[3] = -1.0
+        return a * 1.0, v * 1.0, w
+
+    def chain(a0, b0, make):
+        a = make(a0, b0)
+        c = onp.expand_dims(onp.ravel(a), 0).reshape(32, 192)
+        c[1, 2] = 7.0
+        d = onp.squeeze(a.reshape(64, 1, 96), 1)
+        d[63, 95] = 9.0
+        return a * 1.0, c * 1.0, d * 1.0
+
+    def write_through_a_slice_of_the_source(a0, b0, make):
+        a = make(a0, b0)
+        v = a.reshape(96, 64)
+        s_ = a[0:2]
+        s_[...] = 7.0
+        return a * 1.0, v * 1.0
+
+    def flatten_is_a_copy(a0, b0, make):
+        a = make(a0, b0)
+        f = a.flatten()
+        f[0] = 555.0
+        return a * 1.0, f * 1.0
+
+    for what, make in (("contiguous operands", lambda a, b: a + 1.0), ("a broadcast operand", lambda a, b: a + b),
+                       ("a materialised array", lambda a, b: a.copy())):
+        for fn in (write_through_the_reshape, write_through_the_source, chain, write_through_a_slice_of_the_source,
+                   flatten_is_a_copy):
+            check(lambda a, b: fn(a, b, make), x, row, tol=TOL_ELEMENTWISE, what=f"{fn.__name__} ({what})")
+
+
+OP_CASES["reshape_is_a_view"] = case_reshape_is_a_view
+
+
 def grad_case_max_pool():
     """Max-pool block of examples/convnet.py:109-118 with the grad_chooser VJP (numpy_vjps.py:515-530), ties included
     (equal maxima share the cotangent)."""
@@ -1720,6 +1774,13 @@ def case_inplace_write_semantics():
         s2 = asarr(onp.arange(10.0))
         s2[:-1] = s2[1:]
         out += [s2 * 1.0]
+        # a value recorded from a PENDING operand that is given its payload later, and written after that
+        p = asarr(onp.arange(12.0).reshape(3, 4)) + 1.0      # pending
+        q = p * 2.0                                          # recorded with p pending
+        q2 = xp.exp(q) + p[1:2]                              # (a slice computes p)
+        p[0, 0] = 100.0                                      # q and q2 must keep the old p
+        p[2] = -1.0
+        out += [q, q2, p * 1.0]
         return out
 
     want = script(onp, lambda h: h.copy())
