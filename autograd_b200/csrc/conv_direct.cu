@@ -149,6 +149,14 @@ static int launch_direct(DirectArgs g) {
   int threads = (img * strips + 31) / 32 * 32;
   if (threads > 192) threads = 192;
   if (threads < 64) threads = 64;
+  // several rounds of work items per staged group: the two barriers of a group are paid once per `rounds` items of a
+  // thread instead of once per item (register-limited to ~10 warps per SM, the kernel spent as long at barriers as
+  // issuing: ncu stall_barrier 1.03 per issue at one round).  C5, scripts/gpu_r2_conv1.sh: 8.68 / 8.53 / 8.60 / 8.59 ms at
+  // 1 / 2 / 3 / 4 rounds
+  static const int max_rounds = []() { const char* e = getenv("B200AG_CONV_DIRECT_ROUNDS"); return e ? atoi(e) : 2; }();
+  int rounds = 1;
+  while (rounds < max_rounds && wbytes + 2 * (size_t)(img * (rounds + 1)) * img_bytes + 16 <= 100 * 1024) ++rounds;
+  img *= rounds;
   g.IMG = img;
   const size_t smem = wbytes + 2 * (size_t)((img * (size_t)g.C * g.H * g.W + 1) & ~size_t(1)) * 8;
   static bool cfg = false;
@@ -369,7 +377,7 @@ __global__ void __launch_bounds__(256) conv2d_wgrad_direct_kernel(WDirectArgs g)
   const int P = g.Ho * g.Wo;
   const int chw = g.C * g.H * g.W;
   const int a_elems = (chw + 1) & ~1;
-  const int buf_elems = a_elems + ((F * P + 1) & ~1);  // one staged image: As [C][H][W] then Gs [y][x][F]
+  const int buf_elems = a_elems + ((F * P + 1) & ~1);  // one staged image: As [C][H][W] then Gs [F][y][x]
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int CI = g.C * g.kh;
   const int slices = g.Ho * g.SX;
@@ -393,10 +401,10 @@ __global__ void __launch_bounds__(256) conv2d_wgrad_direct_kernel(WDirectArgs g)
     const double* a = g.A + n * chw;
     for (int e = tid; e < chw; e += nthr) __pipeline_memcpy_async(As + e, a + e, 8);
     const double* gg = g.G + n * (int64_t)F * P;
-    for (int e = tid; e < F * P; e += nthr) {            // coalesced read of [f][p], transposed landing at [p][f]
-      const int f = e / P, p = e - f * P;
-      __pipeline_memcpy_async(Gs + p * F + f, gg + e, 8);
-    }
+    // [f][p] as it lies in HBM: lanes at neighbouring x then read neighbouring words.  (Landing it transposed, [p][f], for
+    // 128-bit reads of the F values was measured slower: the scattered landing and the wide reads kept the shared-memory
+    // pipe 72 % busy; C5 8.60 -> 8.46 ms without it.)
+    for (int e = tid; e < F * P; e += nthr) __pipeline_memcpy_async(Gs + e, gg + e, 8);
     __pipeline_commit();
   };
   if (n_begin < n_end) stage(0, n_begin);
@@ -420,18 +428,10 @@ __global__ void __launch_bounds__(256) conv2d_wgrad_direct_kernel(WDirectArgs g)
 #pragma unroll
         for (int j = 0; j + 1 < KW; ++j) win[j] = win[j + 1];
         win[KW - 1] = arow[x + KW - 1];
-        const double* gv = Gs + (y * g.Wo + x) * F;
         double gval[F];
-        if constexpr (F % 2 == 0) {
+        const double* gv = Gs + y * g.Wo + x;
 #pragma unroll
-          for (int f = 0; f < F; f += 2) {
-            const double2 g2 = *reinterpret_cast<const double2*>(gv + f);
-            gval[f] = g2.x; gval[f + 1] = g2.y;
-          }
-        } else {
-#pragma unroll
-          for (int f = 0; f < F; ++f) gval[f] = gv[f];
-        }
+        for (int f = 0; f < F; ++f) gval[f] = gv[f * P];
 #pragma unroll
         for (int f = 0; f < F; ++f)
 #pragma unroll
