@@ -296,13 +296,9 @@ __global__ void __launch_bounds__(FullCfg<F, KH, KW, H, W>::THREADS, 1) conv2d_f
   for (int64_t step = 0; step < steps; ++step) {
     const int chunk = (int)(step % nchunks), pass = (int)((step / nchunks) & 1);
     const int64_t n0 = (blockIdx.x + (step / (2 * nchunks)) * gridDim.x) * 32;
-    if (step + 1 < steps) {
-      stage(step + 1);                                 // the slot was released by the barrier that ended step - 1
-      __pipeline_wait_prior(1);
-    } else {
-      __pipeline_wait_prior(0);
-    }
-    __syncthreads();
+    __pipeline_wait_prior(0);                          // this thread's copies of step `step` (issued one step ago) landed
+    __syncthreads();                                   // ... everyone's did, and everyone is done computing step - 1,
+    if (step + 1 < steps) stage(step + 1);             // whose slot the next step's operands now stream into
     if (chunk == 0) {
 #pragma unroll
       for (int f = 0; f < F; ++f)
@@ -323,7 +319,6 @@ __global__ void __launch_bounds__(FullCfg<F, KH, KW, H, W>::THREADS, 1) conv2d_f
           if (y < Cfg::HO) o[(f * Cfg::HO + y) * Cfg::WO] = acc[f][t];
         }
     }
-    __syncthreads();                                   // slot step & 1 may be refilled by the next round's prefetch
   }
 }
 
