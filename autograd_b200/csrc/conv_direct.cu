@@ -64,13 +64,9 @@ __global__ void __launch_bounds__(192) conv2d_direct_kernel(DirectArgs g) {
   for (int it = 0; grp < groups; grp += gridDim.x, ++it) {
     const int buf = it & 1;
     const int64_t next = grp + gridDim.x;
-    if (next < groups) {
-      stage(buf ^ 1, next);                            // the other buffer was released by the barrier ending the last round
-      __pipeline_wait_prior(1);
-    } else {
-      __pipeline_wait_prior(0);
-    }
-    __syncthreads();
+    __pipeline_wait_prior(0);                          // this thread's copies of this group (issued a round ago) landed
+    __syncthreads();                                   // ... everyone's did, and everyone is done with the previous group,
+    if (next < groups) stage(buf ^ 1, next);           // whose buffer the next group now streams into
     const int64_t n0 = grp * g.IMG;
     const int ng = (int)((g.N - n0) < g.IMG ? (g.N - n0) : g.IMG);
     const double* gimgs = imgs + buf * buf_elems;
@@ -134,7 +130,6 @@ __global__ void __launch_bounds__(192) conv2d_direct_kernel(DirectArgs g) {
         for (int t = 0; t < TH; ++t)
           if (y0 + t < g.Ho) o[(int64_t)f * g.Ho * g.Wo + (y0 + t) * g.Wo] = acc[f][t];
     }
-    __syncthreads();                                   // this buffer may be refilled by the next round's prefetch
   }
 }
 
@@ -405,13 +400,9 @@ __global__ void __launch_bounds__(256) conv2d_wgrad_direct_kernel(WDirectArgs g)
   if (n_begin < n_end) stage(0, n_begin);
   for (int64_t n = n_begin; n < n_end; ++n) {
     const int buf = (int)((n - n_begin) & 1);
-    if (n + 1 < n_end) {
-      stage(buf ^ 1, n + 1);
-      __pipeline_wait_prior(1);
-    } else {
-      __pipeline_wait_prior(0);
-    }
-    __syncthreads();
+    __pipeline_wait_prior(0);
+    __syncthreads();                                   // image n is complete and everyone is done with image n - 1
+    if (n + 1 < n_end) stage(buf ^ 1, n + 1);
     if (active) {
       const double* As = smem + buf * buf_elems;
       const double* Gs = As + a_elems;
@@ -433,8 +424,9 @@ __global__ void __launch_bounds__(256) conv2d_wgrad_direct_kernel(WDirectArgs g)
           for (int j = 0; j < KW; ++j) acc[f][j] = fma(win[j], gval[f], acc[f][j]);
       }
     }
-    __syncthreads();                                   // this buffer may be refilled by the next round's prefetch
   }
+  __pipeline_wait_prior(0);
+  __syncthreads();                                     // the staging area is reused for the reduction below
   // reduce the slices' partial sums: shared-memory staging, then one FP64 atomic per output and CTA
   double* red = smem;                                   // [workers][F*KW], reuses the staging area
   if (active) {
