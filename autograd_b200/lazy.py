@@ -667,6 +667,8 @@ def link_alias(view: Node, src: Node) -> None:
         group = src.alias = _AliasGroup()
         group.members.append(weakref.ref(src))
     view.alias = group
+    if len(group.members) >= 32:             # an array reshaped again and again in a loop: forget the handles that died
+        group.members = [r for r in group.members if r() is not None]
     group.members.append(weakref.ref(view))
 
 
