@@ -50,6 +50,8 @@ cfg = sys.argv[1]
 if cfg == "c5":
     N = int(sys.argv[2]) if len(sys.argv) > 2 else 512
     n, _p, loss = w.convnet_make(); W, X, T = w.convnet_data(N, n); a = (b200.asarray(W), b200.asarray(X), b200.asarray(T)); f = grad(loss)
+elif cfg == "c1":
+    params, X, T = w.mlp_data(); a = (tree_to_dev(params), b200.asarray(X), b200.asarray(T), 1.0); f = grad(w.mlp_objective)
 elif cfg == "c4":
     st = int(sys.argv[2]) if len(sys.argv) > 2 else 2
     G_ = int(sys.argv[3]) if len(sys.argv) > 3 else 256; p, s0, tg = w.fluid_data(G_, G_); a = (b200.asarray(p), b200.asarray(s0), b200.asarray(tg), G_, G_, st); f = value_and_grad(w.fluid_objective)
