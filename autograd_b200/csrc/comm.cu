@@ -462,7 +462,9 @@ int b200ag_comm_allreduce_sum_f64(void* out, const void* src, int64_t n) {
   if (((uintptr_t)out & 15) != 0) B200AG_FAIL("comm_allreduce: output must be 16-byte aligned");
   // measured at 1.42 MB: one-shot 21 / 43 us at 2 / 8 ranks, two-shot 31 / 66 us (two flag rounds + a grid-wide arrival):
   // the two-shot form only pays once the (world-1)x larger one-shot traffic dominates, i.e. for multi-megabyte vectors
-  const bool nvls = g_comm.mc && (g_comm_mode == 4 || (g_comm_mode == 0 && g_comm.world >= 4));
+  // in-switch reduction pays from 8 ranks on (1.42 MB: 25-26 us against 34 pull / 33 push); at 4 ranks the one-shot kernels
+  // are faster (21 us against 26), at 2 ranks too (17-19 against 27): profiles/r02_peer_allreduce_latency.txt
+  const bool nvls = g_comm.mc && (g_comm_mode == 4 || (g_comm_mode == 0 && g_comm.world > 4));
   if (nvls) {
     int64_t per_rank = (n + g_comm.world - 1) / g_comm.world;
     unsigned grid = (unsigned)((per_rank + 255) / 256);

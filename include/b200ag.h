@@ -262,7 +262,7 @@ int b200ag_comm_allreduce_sum_f64(void* out, const void* src, int64_t n);
 /* 1 when a collective gave up waiting for a peer (bounded spin): the flag lives in mapped host memory, is also
  * reported by b200ag_index_error (bit 1) after any synchronisation, and is never cleared — replicas may have diverged. */
 int b200ag_comm_status(int* timed_out);
-/* 0 = choose automatically (NVLS from 4 ranks up when a multicast mapping is attached, else one-shot; two-shot
+/* 0 = choose automatically (NVLS above 4 ranks when a multicast mapping is attached, else one-shot; two-shot
  * reduce-scatter + all-gather from 4 ranks and 4 MB up), 1 = one-shot (pull), 2 = two-shot, 3 = one-shot push (every
  * rank writes its vector into the peers' inboxes, the sum reads local memory only), 4 = NVLS multimem. */
 int b200ag_comm_mode(int mode, int* previous);
