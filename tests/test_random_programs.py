@@ -1,0 +1,137 @@
+"""Randomised differential test of the lazy host logic (no GPU): seeded random "user programs" - chains of elementwise
+ops with broadcasting, reshapes / ravels / transposes / slices / rolls, reductions, gathers, products, and IN-PLACE writes
+through arrays and through their views - run once on NumPy and once on DeviceArrays over tests/fakedev.FakeBackend; every
+array alive at the end (and at random points in between) must agree.
+
+The emulation executes the same recorded `lazy.Program`s the CUDA backend would, operand by operand with the strides,
+shifts and iteration space `lazy.materialize` chose, so this exercises what the parity cases cannot enumerate: the
+interplay of pending expressions with later writes (Buffer.readers, Node.consumers), of symbolic reshapes with NumPy's
+view semantics (lazy._AliasGroup), of reshape nodes with the iteration-space planning (lazy._plan_reshapes), of queued
+products / scatters with whatever reads or overwrites their operands.  NumPy's eager evaluation is the oracle.
+"""
+
+import numpy as onp
+import pytest
+
+import cases
+
+ROWS, COLS = 64, 96            # 6144 elements: above the 4096 threshold of pending reshape nodes
+
+
+class _Prog:
+    """One random program, generated against NumPy arrays and replayed verbatim on device arrays."""
+
+    def __init__(self, seed):
+        self.r = onp.random.RandomState(seed)
+        self.steps = []          # (fn(env) -> None, description)
+
+    # ---- program construction: every step is a closure over NAMES in an environment dict
+    def build(self, n_steps):
+        r = self.r
+        names2d, names1d = ["a", "b"], []
+        counter = [0]
+
+        def fresh(prefix):
+            counter[0] += 1
+            return f"{prefix}{counter[0]}"
+
+        def pick(seq):
+            return seq[r.randint(len(seq))]
+
+        for _ in range(n_steps):
+            kind = r.randint(14)
+            if kind == 0:                                            # elementwise binary, same shape
+                x, y, out = pick(names2d), pick(names2d), fresh("e")
+                op = pick(["add", "subtract", "multiply", "maximum"])
+                self.steps.append((lambda env, x=x, y=y, out=out, op=op: env.__setitem__(out, getattr(onp, op)(env[x], env[y])),
+                                   f"{out} = {op}({x}, {y})"))
+                names2d.append(out)
+            elif kind == 1:                                          # broadcast against the row / the column
+                x, out, which = pick(names2d), fresh("e"), pick(["row", "col"])
+                self.steps.append((lambda env, x=x, out=out, which=which: env.__setitem__(out, env[x] * 0.5 + env[which]),
+                                   f"{out} = {x} * 0.5 + {which}"))
+                names2d.append(out)
+            elif kind == 2:                                          # ravel / reshape(-1) of whatever the operand is
+                x, out = pick(names2d), fresh("f")
+                self.steps.append((lambda env, x=x, out=out: env.__setitem__(out, env[x].ravel()), f"{out} = {x}.ravel()"))
+                names1d.append(out)
+            elif kind == 3 and names1d:                              # back to 2-d, sometimes another 2-d shape
+                x, out = pick(names1d), fresh("e")
+                shape = pick([(ROWS, COLS), (ROWS, COLS), (COLS, ROWS)])
+                if shape == (ROWS, COLS):
+                    names2d.append(out)
+                self.steps.append((lambda env, x=x, out=out, shape=shape: env.__setitem__(out, env[x].reshape(shape)),
+                                   f"{out} = {x}.reshape{shape}"))
+            elif kind == 4 and names1d:                              # 1-d elementwise
+                x, y, out = pick(names1d), pick(names1d), fresh("f")
+                self.steps.append((lambda env, x=x, y=y, out=out: env.__setitem__(out, env[x] - 2.0 * env[y]),
+                                   f"{out} = {x} - 2 * {y}"))
+                names1d.append(out)
+            elif kind == 5:                                          # in-place write into a 2-d array (scalar / row block)
+                x = pick(names2d)
+                i, j, v = r.randint(ROWS), r.randint(COLS), float(r.randint(-50, 50))
+                if r.randint(2):
+                    self.steps.append((lambda env, x=x, i=i, j=j, v=v: env[x].__setitem__((i, j), v), f"{x}[{i}, {j}] = {v}"))
+                else:
+                    self.steps.append((lambda env, x=x, i=i, v=v: env[x].__setitem__(slice(i, i + 3), v), f"{x}[{i}:{i + 3}] = {v}"))
+            elif kind == 6 and names1d:                              # in-place write through a flattened handle
+                x = pick(names1d)
+                i, v = r.randint(ROWS * COLS - 8), float(r.randint(-50, 50))
+                self.steps.append((lambda env, x=x, i=i, v=v: env[x].__setitem__(slice(i, i + 5), v), f"{x}[{i}:{i + 5}] = {v}"))
+            elif kind == 7:                                          # a slice view, later possibly written through
+                x, out = pick(names2d), fresh("s")
+                i = r.randint(ROWS - 8)
+                self.steps.append((lambda env, x=x, out=out, i=i: env.__setitem__(out, env[x][i:i + 8]), f"{out} = {x}[{i}:{i + 8}]"))
+                self.steps.append((lambda env, out=out: env[out].__setitem__((slice(2, 4), slice(None)), -3.0), f"{out}[2:4] = -3"))
+            elif kind == 8:                                          # roll + stencil-like combination
+                x, out = pick(names2d), fresh("e")
+                sh, ax = pick([1, -1, 5]), pick([0, 1])
+                self.steps.append((lambda env, x=x, out=out, sh=sh, ax=ax: env.__setitem__(out, (env[x] + onp.roll(env[x], sh, axis=ax)) / 4.0),
+                                   f"{out} = ({x} + roll({x}, {sh}, {ax})) / 4"))
+                names2d.append(out)
+            elif kind == 9:                                          # reduction over an axis, broadcast back
+                x, out, ax = pick(names2d), fresh("e"), pick([0, 1])
+                self.steps.append((lambda env, x=x, out=out, ax=ax: env.__setitem__(out, env[x] - onp.sum(env[x], axis=ax, keepdims=True) * 0.001),
+                                   f"{out} = {x} - 0.001 * sum({x}, {ax}, keepdims)"))
+                names2d.append(out)
+            elif kind == 10 and names1d:                             # gather through indices computed from a flattened expression
+                x, t, out = pick(names1d), pick(names2d), fresh("f")
+                self.steps.append((lambda env, x=x, t=t, out=out: env.__setitem__(
+                    out, env[t][onp.mod(onp.floor(env[x] * 7.0).astype(int), ROWS), onp.mod(onp.floor(env[x] * 3.0).astype(int), COLS)]),
+                                   f"{out} = {t}[floor(7 {x}) % R, floor(3 {x}) % C]"))
+                names1d.append(out)
+            elif kind == 11:                                         # a product (queued on the device)
+                x, out = pick(names2d), fresh("p")
+                self.steps.append((lambda env, x=x, out=out: env.__setitem__(out, onp.dot(env[x], env["w"])), f"{out} = dot({x}, w)"))
+            elif kind == 12 and names1d:                             # np.add.at into a flattened handle
+                x = pick(names1d)
+                self.steps.append((lambda env, x=x: onp.add.at(env[x], env["idx"], 1.5), f"add.at({x}, idx, 1.5)"))
+            elif kind == 13:                                         # transpose twice with work in between
+                x, out = pick(names2d), fresh("e")
+                self.steps.append((lambda env, x=x, out=out: env.__setitem__(out, (env[x].T * 2.0).T + 1.0), f"{out} = ({x}.T * 2).T + 1"))
+                names2d.append(out)
+        return self
+
+    def run(self, make):
+        r = onp.random.RandomState(12345)
+        env = {"a": make(r.randn(ROWS, COLS)), "b": make(r.randn(ROWS, COLS)), "row": make(r.randn(COLS)),
+               "col": make(r.randn(ROWS, 1)), "w": make(r.randn(COLS, 5)),
+               "idx": make(r.randint(0, ROWS * COLS, 50))}
+        for fn, _desc in self.steps:
+            fn(env)
+        return env
+
+
+@pytest.mark.parametrize("seed", range(60))
+def test_random_program_matches_numpy(seed, fake_dev):
+    import autograd_b200 as b200
+
+    prog = _Prog(seed).build(18)
+    want = prog.run(lambda h: h.copy())
+    got = prog.run(lambda h: b200.asarray(h))
+    listing = "\n".join(d for _f, d in prog.steps)
+    for name in sorted(want):
+        g = cases.to_host(got[name])
+        w = want[name]
+        tol = cases.TOL_REDUCE if name.startswith("p") else cases.TOL_ELEMENTWISE
+        cases.assert_close(g, w, tol, f"seed {seed}, array {name} after\n{listing}\n")
