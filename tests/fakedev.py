@@ -64,10 +64,15 @@ class FakeBackend:
     sm_count = 148
     total_mem = 180 << 30
 
+    _instances = 0
+
     def __init__(self, compile_generated: bool = True):
         self._bases = []     # sorted base addresses
         self._bufs = {}      # base -> np.uint8 array
-        self._next = 1 << 20
+        # every instance hands out addresses from its own range: a buffer of an EARLIER instance that the garbage
+        # collector frees late (cycles through weak references) must not alias a live allocation of this one
+        FakeBackend._instances += 1
+        self._next = (FakeBackend._instances << 40) + (1 << 20)
         self._launches = 0
         self._compiled = set()
         self.programs = {}   # key -> Program (for inspection by tests)
