@@ -793,6 +793,14 @@ def materialize(root: Node, store_root: bool = True) -> Mat:
     if root.mat is not None:
         return root.mat
     order, leaf_nodes = _collect([root])
+    if any(ln.mat.buf.pending for ln in leaf_nodes):
+        # an operand is the result of a queued product / the target of queued scatters: launch those NOW, before the
+        # kernel is laid out - launching them computes expressions that may share nodes with this one (they become
+        # leaves), which must not happen between collecting the graph and numbering its operands (Mat.ptr would do it)
+        flush_deferred()
+        if root.mat is not None:
+            return root.mat
+        order, leaf_nodes = _collect([root])
     adopted = False
     for nd_ in order:                            # a reshape of an array that has been computed meanwhile: a view of it
         if nd_.alias is not None and nd_.mat is None and _adopt_group_payload(nd_):

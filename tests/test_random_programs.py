@@ -135,3 +135,60 @@ def test_random_program_matches_numpy(seed, fake_dev):
         w = want[name]
         tol = cases.TOL_REDUCE if name.startswith("p") else cases.TOL_ELEMENTWISE
         cases.assert_close(g, w, tol, f"seed {seed}, array {name} after\n{listing}\n")
+
+
+def _random_loss(seed):
+    """A random differentiable scalar function of (x, row, col, w) built from the op families of the BASELINE configs:
+    broadcasting arithmetic, tanh / exp, reshape + short-axis max (pooling), roll stencils, flattened gathers with
+    computed indices (advection), products, logsumexp-style reductions."""
+    import autograd.numpy as np
+
+    r = onp.random.RandomState(seed)
+    layers = [int(k) for k in r.randint(0, 9, size=6)]
+    shift = int(r.choice([1, -1, 3]))
+
+    def loss(x, row, col, w):
+        h = x
+        for k in layers:
+            if k == 0:
+                h = np.tanh(h * 0.5 + row)
+            elif k == 1:
+                h = h * col - np.roll(h, shift, axis=0) * 0.25
+            elif k == 2:                                   # 2 x 2 max pool and broadcast back (ties are measure-zero here)
+                p = np.max(np.max(np.reshape(h, (ROWS // 2, 2, COLS // 2, 2)), axis=1), axis=2)
+                h = h + np.reshape(np.repeat(np.repeat(p, 2, axis=0), 2, axis=1), (ROWS, COLS)) * 0.1
+            elif k == 3:                                   # flattened gather through indices computed from the values
+                f = (h * 3.0 + row).ravel()
+                ix = np.mod(np.floor(f).astype(int), ROWS)
+                iy = np.mod(np.floor(f * 0.5).astype(int), COLS)
+                frac = f - np.floor(f)
+                h = np.reshape(frac * x[ix, iy] + (1.0 - frac) * h.ravel(), (ROWS, COLS))
+            elif k == 4:
+                h = h - np.sum(h, axis=1, keepdims=True) / COLS
+            elif k == 5:
+                h = np.exp(-h * h * 0.1) + col
+            elif k == 6:
+                h = h + np.dot(np.tanh(np.dot(h, w)), w.T) * 0.05
+            elif k == 7:
+                h = (h + np.roll(h, 1, axis=1) + np.roll(h, -1, axis=1) + np.roll(h, 1, axis=0)) / 4.0
+            else:
+                h = np.reshape(np.reshape(h, (-1,)) * 1.5, (ROWS, COLS)).T.T + row
+        return np.sum(h * h) * 1e-3 + np.sum(np.log(np.sum(np.exp(h * 0.1), axis=1)))
+
+    return loss
+
+
+@pytest.mark.parametrize("seed", list(range(24)) + [1005])
+def test_random_gradient_matches_reference(seed, fake_dev):
+    """grad of a random composition, on device arrays, against reference autograd on NumPy (same tape rules)."""
+    from autograd import grad
+
+    import autograd_b200 as b200
+
+    r = onp.random.RandomState(100 + seed)
+    args = (r.randn(ROWS, COLS), r.randn(COLS), r.randn(ROWS, 1), r.randn(COLS, 5) * 0.3)
+    loss = _random_loss(seed)
+    for argnum in (0, 3):
+        want = grad(loss, argnum)(*args)
+        got = grad(loss, argnum)(*[b200.asarray(a) for a in args])
+        cases.assert_close(cases.to_host(got), want, cases.TOL_REDUCE, f"seed {seed}, gradient wrt argument {argnum}")
