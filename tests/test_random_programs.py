@@ -192,3 +192,98 @@ def test_random_gradient_matches_reference(seed, fake_dev):
         want = grad(loss, argnum)(*args)
         got = grad(loss, argnum)(*[b200.asarray(a) for a in args])
         cases.assert_close(cases.to_host(got), want, cases.TOL_REDUCE, f"seed {seed}, gradient wrt argument {argnum}")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Second family: library calls around the deferred-product queue - products whose results are sliced, dropped, fed to
+# other products; concatenate / where / cumsum / sort / einsum / take / clip / dtype round trips / stack / tile / batched
+# matmul - with in-place row writes in between.
+import gc
+
+
+def _build_library_program(seed, n_steps):
+    r = onp.random.RandomState(seed)
+    steps = []
+    mats = ["A", "B"]           # (48, 40) matrices
+    prods = []                  # (48, k) products
+    vecs = []
+    cnt = [0]
+    def fresh(p):
+        cnt[0] += 1; return f"{p}{cnt[0]}"
+    def pick(s): return s[r.randint(len(s))]
+    for _ in range(n_steps):
+        k = r.randint(12)
+        if k == 0:
+            x, out = pick(mats), fresh("P")
+            steps.append((lambda e, x=x, out=out: e.__setitem__(out, onp.dot(e[x], e["W"])), f"{out} = dot({x}, W)"))
+            prods.append(out)
+        elif k == 1 and prods:
+            x, out = pick(prods), fresh("S")
+            lo = r.randint(0, 20); hi = lo + r.randint(1, 12)
+            steps.append((lambda e, x=x, out=out, lo=lo, hi=hi: e.__setitem__(out, e[x][:, lo:hi]), f"{out} = {x}[:, {lo}:{hi}]"))
+            if r.randint(2):
+                steps.append((lambda e, x=x: e.__setitem__(x, None), f"del {x}"))
+                prods.remove(x)
+        elif k == 2 and prods:
+            x, out = pick(prods), fresh("M")
+            steps.append((lambda e, x=x, out=out: e.__setitem__(out, onp.tanh(e[x]) @ e["W"].T), f"{out} = tanh({x}) @ W.T"))
+            mats.append(out)
+        elif k == 3:
+            x, y, out = pick(mats), pick(mats), fresh("M")
+            steps.append((lambda e, x=x, y=y, out=out: e.__setitem__(out, onp.concatenate([e[x][:24], e[y][24:]], axis=0)), f"{out} = concat({x}[:24], {y}[24:])"))
+            mats.append(out)
+        elif k == 4:
+            x, out = pick(mats), fresh("M")
+            steps.append((lambda e, x=x, out=out: e.__setitem__(out, onp.where(e[x] > 0, e[x], e[x] * 0.1)), f"{out} = leaky({x})"))
+            mats.append(out)
+        elif k == 5:
+            x = pick(mats)
+            i = r.randint(48)
+            steps.append((lambda e, x=x, i=i: e[x].__setitem__(i, 0.5), f"{x}[{i}] = 0.5"))
+        elif k == 6:
+            x, out = pick(mats), fresh("M")
+            steps.append((lambda e, x=x, out=out: e.__setitem__(out, onp.cumsum(e[x], axis=1) * 0.01 + onp.sort(e[x], axis=0)), f"{out} = cumsum({x}) + sort({x})"))
+            mats.append(out)
+        elif k == 7:
+            x, out = pick(mats), fresh("M")
+            steps.append((lambda e, x=x, out=out: e.__setitem__(out, onp.einsum("ij,kj->ik", e[x], e[x])[:, :40] * 0.01), f"{out} = einsum({x},{x})[:, :40]"))
+            mats.append(out)
+        elif k == 8:
+            x, out = pick(mats), fresh("M")
+            steps.append((lambda e, x=x, out=out: e.__setitem__(out, onp.clip(e[x], -0.5, 0.5) + onp.take(e[x], e["ti"], axis=0)), f"{out} = clip({x}) + take({x})"))
+            mats.append(out)
+        elif k == 9:
+            x, out = pick(mats), fresh("M")
+            steps.append((lambda e, x=x, out=out: e.__setitem__(out, (e[x].astype(onp.float32) * 2).astype(onp.float64) + e[x]), f"{out} = f32 roundtrip {x}"))
+            mats.append(out)
+        elif k == 10:
+            x, out = pick(mats), fresh("M")
+            steps.append((lambda e, x=x, out=out: e.__setitem__(out, onp.stack([e[x], e[x] * 2]).sum(axis=0) + onp.tile(e[x][:1], (48, 1))), f"{out} = stack/tile {x}"))
+            mats.append(out)
+        elif k == 11:
+            x, out = pick(mats), fresh("M")
+            steps.append((lambda e, x=x, out=out: e.__setitem__(out, onp.matmul(e[x][None] * onp.ones((3, 1, 1)), e["W"][None])[1] @ e["W"].T), f"{out} = batched matmul {x}"))
+            mats.append(out)
+    return steps
+
+def _run_library_program(steps, make):
+    r = onp.random.RandomState(777)
+    e = {"A": make(r.randn(48, 40)), "B": make(r.randn(48, 40)), "W": make(r.randn(40, 24)), "ti": make(r.randint(0, 48, 48))}
+    for fn, _ in steps:
+        fn(e)
+        gc.collect()
+    return e
+
+
+
+@pytest.mark.parametrize("seed", range(30))
+def test_random_library_program_matches_numpy(seed, fake_dev):
+    import autograd_b200 as b200
+
+    steps = _build_library_program(seed, 20)
+    want = _run_library_program(steps, lambda h: h.copy())
+    got = _run_library_program(steps, lambda h: b200.asarray(h))
+    listing = "\n".join(d for _f, d in steps)
+    for name in sorted(want):
+        if want[name] is not None:
+            cases.assert_close(cases.to_host(got[name]), want[name], 1e-9, f"seed {seed}, array {name} after\n{listing}\n")
