@@ -788,6 +788,9 @@ def _plan_reshapes(root):
     return iter_shape, out
 
 
+_taint_memo = {}       # (instrs, leaf taint, table taint) -> (codegen.taint, codegen.relax_plan)
+
+
 def materialize(root: Node, store_root: bool = True) -> Mat:
     """Compute ``root`` (and any still-visible expensive interior node) with one fused kernel."""
     if root.mat is not None:
@@ -800,7 +803,8 @@ def materialize(root: Node, store_root: bool = True) -> Mat:
         flush_deferred()
         if root.mat is not None:
             return root.mat
-        order, leaf_nodes = _collect([root])
+        if any(nd_.mat is not None for nd_ in order):
+            order, leaf_nodes = _collect([root])
     adopted = False
     for nd_ in order:                            # a reshape of an array that has been computed meanwhile: a view of it
         if nd_.alias is not None and nd_.mat is None and _adopt_group_payload(nd_):
@@ -1044,8 +1048,16 @@ def materialize(root: Node, store_root: bool = True) -> Mat:
     from . import codegen
 
     instrs = tuple(instrs)
-    inexact = codegen.taint(instrs, leaf_taint, table_taint)
-    relax = codegen.relax_plan(instrs, inexact) if RELAXED else ()
+    memo_key = (instrs, tuple(leaf_taint), tuple(table_taint))
+    hit = _taint_memo.get(memo_key)
+    if hit is None:                              # (a training loop records the same bodies over and over)
+        inexact = codegen.taint(instrs, leaf_taint, table_taint)
+        relax = codegen.relax_plan(instrs, inexact) if RELAXED else ()
+        if len(_taint_memo) >= 4096:
+            _taint_memo.clear()
+        _taint_memo[memo_key] = (inexact, relax)
+    else:
+        inexact, relax = hit
     unroll = ()
     if UNROLL_WINDOWS and mode == "flat" and g_layouts and not table_descs and n >= (1 << 20) and len(dims) >= 2:
         # dims of extent <= 4 - neither the outermost nor the INNERMOST one, whose consecutive elements belong to consecutive
